@@ -1,0 +1,592 @@
+// bfilt_api.cu -- C ABI of libbfilt.so (see include/bfilt.h).  Host-side orchestration only: builds the
+// model constants, owns scratch + carry buffers, enqueues the kernels of pf_kernels.cuh / pf_resident.cuh /
+// gsf_kernels.cuh on the caller's stream.  No device synchronisation except in the *_host entry points.
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <new>
+#include <algorithm>
+#include "../../include/bfilt.h"
+#include "common.cuh"
+#include "models.cuh"
+#include "scan.cuh"
+#include "pf_kernels.cuh"
+#include "pf_resident.cuh"
+#include "gsf_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(BF_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define LAUNCH_OK()                                                                                \
+  do {                                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) return fail(BF_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* bf_last_error(void) { return g_err.c_str(); }
+extern "C" int bf_abi_version(void) { return BF_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------ model constants
+// fp32 Cholesky, like TFP's MultivariateNormalFullCovariance(cov) -> scale_tril = cholesky(cov).
+// An all-zero matrix yields L = 0 (degenerate noise); any other failure yields NaN like the reference would.
+static void chol32(const float* A, int n, float* L) {
+  bool allzero = true;
+  for (int i = 0; i < n * n; ++i) if (A[i] != 0.0f) allzero = false;
+  for (int i = 0; i < n * n; ++i) L[i] = 0.0f;
+  if (allzero) return;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      float s = A[i * n + j];
+      for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k];
+      if (i == j) L[i * n + i] = (s > 0.0f) ? sqrtf(s) : NAN;
+      else L[i * n + j] = s / L[j * n + j];
+    }
+}
+
+static int build_model_const(const bf_model_desc* d, ModelConst* mc) {
+  if (!d) return fail(BF_EINVAL, "model desc is NULL");
+  if (d->dx < 1 || d->dx > BF_MAXD || d->dq < 1 || d->dq > BF_MAXD || d->dy < 1 || d->dy > BF_MAXD || d->dr < 1 || d->dr > BF_MAXD)
+    return fail(BF_EINVAL, "model dims dx=%d dq=%d dy=%d dr=%d out of range [1,%d]", d->dx, d->dq, d->dy, d->dr, BF_MAXD);
+  if (d->n_theta < 0 || d->n_theta > BF_MAXTHETA) return fail(BF_EINVAL, "n_theta=%d out of range", d->n_theta);
+  if (!d->q0 || !d->Q || !d->r0 || !d->R || !d->m0 || !d->P0 || (d->n_theta > 0 && !d->theta))
+    return fail(BF_EINVAL, "model desc has a NULL array");
+  int want_dx = -1, want_dq = -1, want_dy = -1, want_theta = -1;
+  switch (d->model_id) {
+    case BF_MODEL_UNGM: want_dx = 1; want_dq = 1; want_dy = 1; want_theta = 5; break;
+    case BF_MODEL_BOT: want_dx = 4; want_dq = 2; want_dy = d->dy; want_theta = 3;
+      if (d->dy != 1 && d->dy != 2) return fail(BF_ENOMODEL, "BOT needs dy in {1,2}"); break;
+    case BF_MODEL_L63: want_dx = 3; want_dq = 3; want_dy = 1; want_theta = 5; break;
+    case BF_MODEL_LG: want_dx = d->dx; want_dq = d->dx; want_dy = d->dy; want_theta = d->dx * d->dx + d->dy * d->dx; break;
+    case BF_MODEL_SIN1D: want_dx = d->dx; want_dq = d->dx; want_dy = 1; want_theta = 2;
+      if (d->dx > 3) return fail(BF_ENOMODEL, "SIN1D needs dx <= 3"); break;
+    case BF_MODEL_L96: return fail(BF_ENOMODEL, "L96 runs through the large-state path (not built in this library version)");
+    default: return fail(BF_ENOMODEL, "unknown model_id %d", d->model_id);
+  }
+  if (d->dx != want_dx || d->dq != want_dq || d->dy != want_dy || d->dr != want_dy || d->n_theta != want_theta)
+    return fail(BF_EINVAL, "model %d: dims/theta (dx=%d dq=%d dy=%d dr=%d n_theta=%d) do not match the registry (dx=%d dq=%d dy=dr=%d n_theta=%d)",
+                d->model_id, d->dx, d->dq, d->dy, d->dr, d->n_theta, want_dx, want_dq, want_dy, want_theta);
+  memset(mc, 0, sizeof *mc);
+  mc->model_id = d->model_id; mc->dx = d->dx; mc->dq = d->dq; mc->dy = d->dy; mc->dr = d->dr;
+  for (int i = 0; i < d->n_theta; ++i) mc->theta[i] = d->theta[i];
+  for (int i = 0; i < d->dq; ++i) mc->q0[i] = d->q0[i];
+  for (int i = 0; i < d->dr; ++i) mc->r0[i] = d->r0[i];
+  for (int i = 0; i < d->dx; ++i) mc->m0[i] = d->m0[i];
+  for (int i = 0; i < d->dq * d->dq; ++i) mc->Q[i] = d->Q[i];
+  for (int i = 0; i < d->dr * d->dr; ++i) mc->R[i] = d->R[i];
+  for (int i = 0; i < d->dx * d->dx; ++i) mc->P0[i] = d->P0[i];
+  chol32(mc->Q, d->dq, mc->LQ);
+  chol32(mc->R, d->dr, mc->LR);
+  chol32(mc->P0, d->dx, mc->LP0);
+  float logdet = 0.0f;
+  for (int i = 0; i < d->dr; ++i) logdet += logf(mc->LR[i * d->dr + i]);
+  mc->lp_const = -logdet - 0.5f * (float)d->dy * 1.8378770664093453f;
+  if (mc->model_id == BF_MODEL_LG) {
+    bool ok = false;
+    const int pairs[][2] = {{1, 1}, {2, 1}, {2, 2}, {3, 1}, {3, 3}, {4, 2}, {4, 4}, {8, 8}};
+    for (auto& p : pairs) if (p[0] == mc->dx && p[1] == mc->dy) ok = true;
+    if (!ok) return fail(BF_ENOMODEL, "LG (dx=%d, dy=%d) is not an instantiated shape", mc->dx, mc->dy);
+  }
+  return BF_OK;
+}
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// ========================================================================================== particle filter
+struct bf_pf_s {
+  ModelConst mc;
+  bf_pf_config cfg;
+  int path;               // resolved: RESIDENT or STREAMED
+  int N, B, nsm;
+  int resident_warps;
+  size_t resident_smem;
+  int64_t launches;
+  bool have_carry;
+  DevBuf carry_x, carry_w, carry_uniform, carry_stats;
+  // streamed scratch
+  DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats;
+  int ntiles, grid_prop;
+  // host-call staging
+  DevBuf hbuf[24];
+};
+
+extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg, bf_pf_handle* out) {
+  if (!cfg || !out) return fail(BF_EINVAL, "NULL argument");
+  if (cfg->num_particles < 1 || cfg->num_particles > (int64_t)1 << 30) return fail(BF_EINVAL, "num_particles=%lld out of range", (long long)cfg->num_particles);
+  if (cfg->num_trials < 1) return fail(BF_EINVAL, "num_trials must be >= 1");
+  if (cfg->resampler != BF_RESAMPLE_MULTINOMIAL && cfg->resampler != BF_RESAMPLE_SYSTEMATIC) return fail(BF_EINVAL, "unknown resampler %d", cfg->resampler);
+  bf_pf_s* h = new (std::nothrow) bf_pf_s();
+  if (!h) return fail(BF_ENOMEM, "out of host memory");
+  int rc = build_model_const(model, &h->mc);
+  if (rc) { delete h; return rc; }
+  h->cfg = *cfg; h->N = (int)cfg->num_particles; h->B = cfg->num_trials; h->launches = 0; h->have_carry = false;
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) { delete h; return fail(BF_ECUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e)); }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) { delete h; return fail(BF_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+  h->nsm = prop.multiProcessorCount;
+  h->resident_warps = (h->N <= 1024) ? 8 : 32;
+  {
+    const int Npad = (h->N + 3) & ~3, dx = h->mc.dx, tile = h->resident_warps * 128;
+    const int nchunk = (h->N + 1 + tile - 1) / tile;
+    size_t fl = (size_t)2 * Npad * dx + Npad + (Npad + 4) + Npad + 32 * (2 + BF_MAXD) + (nchunk + 1 + h->resident_warps) + 16;
+    h->resident_smem = fl * sizeof(float);
+  }
+  const bool fits = h->resident_smem <= (size_t)prop.sharedMemPerBlockOptin && h->resident_smem <= 200 * 1024;
+  if (cfg->path == BF_PATH_RESIDENT) {
+    if (!fits) { delete h; return fail(BF_EINVAL, "N=%d does not fit the shared-memory resident path (%zu bytes)", h->N, h->resident_smem); }
+    h->path = BF_PATH_RESIDENT;
+  } else if (cfg->path == BF_PATH_STREAMED) h->path = BF_PATH_STREAMED;
+  else h->path = fits ? BF_PATH_RESIDENT : BF_PATH_STREAMED;
+  const size_t nx = (size_t)h->B * h->N * h->mc.dx;
+  if (h->carry_x.ensure(nx * 4) || h->carry_w.ensure((size_t)h->B * h->N * 4) || h->carry_uniform.ensure((size_t)h->B * 4) ||
+      h->carry_stats.ensure((size_t)h->B * sizeof(StepStats))) {
+    bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the carry failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (h->path == BF_PATH_STREAMED) {
+    h->ntiles = (int)(((int64_t)h->N + 1 + PF_TILE - 1) / PF_TILE);
+    h->grid_prop = (int)std::min<int64_t>(((int64_t)h->N + PF_PROP_THREADS - 1) / PF_PROP_THREADS, (int64_t)h->nsm * 8);
+    const size_t npad = (size_t)h->ntiles * PF_TILE;
+    if (h->xa.ensure((size_t)h->N * h->mc.dx * 4) || h->xb.ensure((size_t)h->N * h->mc.dx * 4) || h->LL.ensure(npad * 4) ||
+        h->E.ensure(npad * 4) || h->anc.ensure((size_t)h->N * 4) || h->tilesum.ensure((size_t)h->ntiles * 4) ||
+        h->Etile.ensure(((size_t)h->ntiles + 1) * 4) || h->partials.ensure((size_t)h->grid_prop * sizeof(PfPartial)) ||
+        h->counter.ensure(64)) {
+      bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the streamed scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaMemset(h->counter.p, 0, 64);
+    cudaMemset(h->LL.p, 0, npad * 4);
+  }
+  *out = h;
+  return BF_OK;
+}
+
+extern "C" int bf_pf_destroy(bf_pf_handle h) {
+  if (!h) return BF_OK;
+  DevBuf* all[] = {&h->carry_x, &h->carry_w, &h->carry_uniform, &h->carry_stats, &h->xa, &h->xb, &h->LL, &h->E, &h->anc,
+                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats};
+  for (DevBuf* b : all) b->release();
+  for (DevBuf& b : h->hbuf) b.release();
+  delete h;
+  return BF_OK;
+}
+
+extern "C" int bf_pf_kernel_launches(bf_pf_handle h, int64_t* out) {
+  if (!h || !out) return fail(BF_EINVAL, "NULL argument");
+  *out = h->launches; return BF_OK;
+}
+
+namespace {
+struct PfRun {
+  bf_pf_s* h; const bf_pf_io* io; cudaStream_t s;
+
+  template <class M> int resident() {
+    PfResidentArgs a;
+    a.N = h->N; a.T = io->T; a.t_offset = io->t_offset; a.resume = io->resume; a.resampler = h->cfg.resampler;
+    a.emissions_per_trial = io->emissions_per_trial; a.ess_threshold = h->cfg.ess_threshold; a.seed = h->cfg.seed;
+    a.emissions = io->emissions; a.inputs = io->inputs; a.init_particles = io->init_particles; a.init_weights = io->init_weights;
+    a.noise = io->noise; a.res_u = io->resample_u;
+    a.carry_x = h->carry_x.as<float>(); a.carry_w = h->carry_w.as<float>(); a.carry_uniform = h->carry_uniform.as<int>();
+    a.out_particles = io->out_particles; a.out_weights = io->out_weights; a.out_propagated = io->out_propagated;
+    a.out_norm_weights = io->out_norm_weights; a.out_ancestors = io->out_ancestors; a.out_mean = io->out_mean;
+    a.out_loglik = io->out_loglik; a.out_ess = io->out_ess; a.out_resampled = io->out_resampled;
+    a.final_particles = io->final_particles; a.final_weights = io->final_weights;
+    if (h->resident_warps == 8) {
+      CUDA_OK(cudaFuncSetAttribute(k_pf_resident<M, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resident_smem));
+      k_pf_resident<M, 8><<<h->B, 256, h->resident_smem, s>>>(h->mc, a);
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(k_pf_resident<M, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resident_smem));
+      k_pf_resident<M, 32><<<h->B, 1024, h->resident_smem, s>>>(h->mc, a);
+    }
+    LAUNCH_OK();
+    h->launches += 1;
+    return BF_OK;
+  }
+
+  template <class M> int streamed() {
+    constexpr int DX = M::DX, DQ = M::DQ, DY = M::DY;
+    const int N = h->N, B = h->B, T = io->T;
+    const size_t nst = (size_t)(T + 1);
+    CUDA_OK(h->stats.ensure(nst * sizeof(StepStats)));
+    StepStats* stats = h->stats.as<StepStats>();
+    const int grid_s = (int)std::min<int64_t>(((int64_t)N + 255) / 256, (int64_t)h->nsm * 8);
+    const int nchunk = (h->ntiles + 1 + PF_TILE - 1) / PF_TILE;
+    const size_t scan_smem = (size_t)(nchunk + 1 + PF_TILE_WARPS + 8) * sizeof(float);
+    for (int b = 0; b < B; ++b) {
+      float* cx = h->carry_x.as<float>() + (size_t)b * N * DX;
+      float* cw = h->carry_w.as<float>() + (size_t)b * N;
+      StepStats* cst = h->carry_stats.as<StepStats>() + b;
+      const float* x_prev;
+      if (io->resume) {
+        x_prev = cx;
+        CUDA_OK(cudaMemcpyAsync(stats, cst, sizeof(StepStats), cudaMemcpyDeviceToDevice, s));
+      } else {
+        if (io->init_particles) x_prev = io->init_particles + (size_t)b * N * DX;
+        else {
+          k_init_particles<DX><<<grid_s, 256, 0, s>>>(h->mc, cx, N, h->cfg.seed, b);
+          LAUNCH_OK(); h->launches++;
+          x_prev = cx;
+        }
+        if (io->init_weights) CUDA_OK(cudaMemcpyAsync(cw, io->init_weights + (size_t)b * N, (size_t)N * 4, cudaMemcpyDeviceToDevice, s));
+        k_init_stats<<<1, 1, 0, s>>>(stats, io->init_weights ? 0 : 1);
+        LAUNCH_OK(); h->launches++;
+      }
+      float* bufs[2] = {h->xa.as<float>(), h->xb.as<float>()};
+      for (int t = 0; t < T; ++t) {
+        const size_t bt = (size_t)b * T + t;
+        PfStepArgs a;
+        a.N = N; a.t = t; a.t_global = t + io->t_offset; a.trial = b; a.ess_threshold = h->cfg.ess_threshold;
+        a.resampler = h->cfg.resampler; a.seed = h->cfg.seed;
+        a.y = io->emissions + ((size_t)(io->emissions_per_trial ? b : 0) * T + t) * DY;
+        a.u_in = io->inputs ? io->inputs + t : nullptr;
+        a.x_prev = x_prev; a.x_cur = bufs[t & 1];
+        a.W = cw; a.LL = h->LL.as<float>(); a.E = h->E.as<float>(); a.anc = h->anc.as<int>();
+        a.tilesum = h->tilesum.as<float>(); a.Etile = h->Etile.as<float>();
+        a.partials = h->partials.as<PfPartial>(); a.counter = h->counter.as<unsigned int>();
+        a.prev = stats + t; a.cur = stats + t + 1;
+        a.noise = io->noise ? io->noise + ((size_t)t * B + b) * N * DQ : nullptr;
+        a.res_u = io->resample_u ? (h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC ? io->resample_u + (size_t)t * B + b
+                                                                               : io->resample_u + ((size_t)t * B + b) * N)
+                                 : nullptr;
+        a.out_particles = io->out_particles ? io->out_particles + bt * N * DX : nullptr;
+        a.out_weights = io->out_weights ? io->out_weights + bt * N : nullptr;
+        a.out_propagated = io->out_propagated ? io->out_propagated + bt * N * DX : nullptr;
+        a.out_norm_weights = io->out_norm_weights ? io->out_norm_weights + bt * N : nullptr;
+        a.out_ancestors = io->out_ancestors ? io->out_ancestors + bt * N : nullptr;
+        a.out_mean = io->out_mean ? io->out_mean + bt * DX : nullptr;
+        a.out_loglik = io->out_loglik ? io->out_loglik + bt : nullptr;
+        a.out_ess = io->out_ess ? io->out_ess + bt : nullptr;
+        a.out_resampled = io->out_resampled ? io->out_resampled + bt : nullptr;
+
+        k_propagate<M><<<h->grid_prop, PF_PROP_THREADS, 0, s>>>(h->mc, a);
+        k_weights<<<h->ntiles, PF_TILE_WARPS * 32, 0, s>>>(a);
+        k_scan_tiles<<<1, PF_TILE_WARPS * 32, scan_smem, s>>>(a.tilesum, a.Etile, h->ntiles, a.cur);
+        k_downsweep<<<h->ntiles, PF_TILE_WARPS * 32, 0, s>>>(a);
+        k_search<<<grid_s, 256, 0, s>>>(a);
+        h->launches += 5;
+        if (a.out_particles) { k_emit<DX><<<grid_s, 256, 0, s>>>(a.x_cur, a.anc, a.cur, N, a.out_particles); h->launches++; }
+        LAUNCH_OK();
+        x_prev = a.x_cur;
+      }
+      k_finalize<DX><<<grid_s, 256, 0, s>>>(x_prev, h->anc.as<int>(), stats + T, N, cx, cw,
+                                           io->final_particles ? io->final_particles + (size_t)b * N * DX : nullptr,
+                                           io->final_weights ? io->final_weights + (size_t)b * N : nullptr);
+      LAUNCH_OK(); h->launches++;
+      CUDA_OK(cudaMemcpyAsync(cst, stats + T, sizeof(StepStats), cudaMemcpyDeviceToDevice, s));
+      k_clear_gather<<<1, 1, 0, s>>>(cst);
+      LAUNCH_OK(); h->launches++;
+    }
+    return BF_OK;
+  }
+
+  template <class M> int run() {
+    if (h->path == BF_PATH_RESIDENT) return resident<M>();
+    return streamed<M>();
+  }
+};
+}  // namespace
+
+static int pf_check_io(bf_pf_s* h, const bf_pf_io* io) {
+  if (!h || !io) return fail(BF_EINVAL, "NULL argument");
+  if (io->T < 1) return fail(BF_EINVAL, "T must be >= 1 (got %d)", io->T);
+  if (!io->emissions) return fail(BF_EINVAL, "emissions is NULL");
+  if (io->resume && !h->have_carry) return fail(BF_EINVAL, "resume requested but the handle holds no carry yet");
+  return BF_OK;
+}
+
+extern "C" int bf_pf_run(bf_pf_handle h, const bf_pf_io* io, void* stream) {
+  int rc = pf_check_io(h, io);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  PfRun fn{h, io, (cudaStream_t)stream};
+  rc = bf_dispatch_model(h->mc, fn);
+  if (rc == -3) return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", h->mc.model_id, h->mc.dx, h->mc.dy);
+  if (rc == BF_OK) h->have_carry = true;
+  return rc;
+}
+
+extern "C" int bf_pf_step(bf_pf_handle h, const bf_pf_io* io, void* stream) {
+  if (!io) return fail(BF_EINVAL, "NULL argument");
+  bf_pf_io one = *io;
+  one.T = 1;
+  return bf_pf_run(h, &one, stream);
+}
+
+// copy helper for the *_host entry points
+static int stage_in(DevBuf& buf, const void* host, size_t bytes, cudaStream_t s, const void** dev) {
+  if (!host) { *dev = nullptr; return BF_OK; }
+  CUDA_OK(buf.ensure(bytes));
+  CUDA_OK(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, s));
+  *dev = buf.p;
+  return BF_OK;
+}
+static int stage_out(DevBuf& buf, void* host, size_t bytes, void** dev) {
+  if (!host) { *dev = nullptr; return BF_OK; }
+  CUDA_OK(buf.ensure(bytes));
+  *dev = buf.p;
+  return BF_OK;
+}
+
+extern "C" int bf_pf_run_host(bf_pf_handle h, const bf_pf_io* hio) {
+  int rc = pf_check_io(h, hio);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = 0;
+  const size_t N = h->N, B = h->B, T = hio->T, dx = h->mc.dx, dq = h->mc.dq, dy = h->mc.dy;
+  bf_pf_io d = *hio;
+  int k = 0;
+#define IN(field, count) if ((rc = stage_in(h->hbuf[k++], hio->field, (size_t)(count) * 4, s, (const void**)&d.field))) return rc;
+#define OUT(field, count) if ((rc = stage_out(h->hbuf[k++], hio->field, (size_t)(count) * 4, (void**)&d.field))) return rc;
+  IN(emissions, (hio->emissions_per_trial ? B : 1) * T * dy)
+  IN(inputs, T)
+  IN(init_particles, B * N * dx)
+  IN(init_weights, B * N)
+  IN(noise, T * B * N * dq)
+  IN(resample_u, h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC ? T * B : T * B * N)
+  OUT(out_particles, B * T * N * dx) OUT(out_weights, B * T * N) OUT(out_propagated, B * T * N * dx)
+  OUT(out_norm_weights, B * T * N) OUT(out_ancestors, B * T * N) OUT(out_mean, B * T * dx) OUT(out_loglik, B * T)
+  OUT(out_ess, B * T) OUT(out_resampled, B * T) OUT(final_particles, B * N * dx) OUT(final_weights, B * N)
+#undef IN
+#undef OUT
+  rc = bf_pf_run(h, &d, s);
+  if (rc) return rc;
+#define BACK(field, count) if (hio->field) CUDA_OK(cudaMemcpyAsync(hio->field, d.field, (size_t)(count) * 4, cudaMemcpyDeviceToHost, s));
+  BACK(out_particles, B * T * N * dx) BACK(out_weights, B * T * N) BACK(out_propagated, B * T * N * dx)
+  BACK(out_norm_weights, B * T * N) BACK(out_ancestors, B * T * N) BACK(out_mean, B * T * dx) BACK(out_loglik, B * T)
+  BACK(out_ess, B * T) BACK(out_resampled, B * T) BACK(final_particles, B * N * dx) BACK(final_weights, B * N)
+#undef BACK
+  CUDA_OK(cudaStreamSynchronize(s));
+  return BF_OK;
+}
+
+// ========================================================================================== Gaussian-sum filter
+struct bf_gsf_s {
+  ModelConst mc;
+  bf_gsf_config cfg;
+  int64_t launches;
+  bool have_carry;
+  DevBuf carry_w, carry_m, carry_P;
+  DevBuf hbuf[16];
+};
+
+extern "C" int bf_gsf_create(const bf_model_desc* model, const bf_gsf_config* cfg, bf_gsf_handle* out) {
+  if (!cfg || !out) return fail(BF_EINVAL, "NULL argument");
+  if (cfg->num_components < 1 || cfg->num_components > 1024) return fail(BF_EINVAL, "num_components=%d out of range [1,1024]", cfg->num_components);
+  if (cfg->num_trials < 1) return fail(BF_EINVAL, "num_trials must be >= 1");
+  bf_gsf_s* h = new (std::nothrow) bf_gsf_s();
+  if (!h) return fail(BF_ENOMEM, "out of host memory");
+  int rc = build_model_const(model, &h->mc);
+  if (rc) { delete h; return rc; }
+  h->cfg = *cfg; h->launches = 0; h->have_carry = false;
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) { delete h; return fail(BF_ECUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e)); }
+  const size_t bm = (size_t)cfg->num_trials * cfg->num_components, dx = h->mc.dx;
+  if (h->carry_w.ensure(bm * 4) || h->carry_m.ensure(bm * dx * 4) || h->carry_P.ensure(bm * dx * dx * 4)) {
+    bf_gsf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the carry failed");
+  }
+  *out = h;
+  return BF_OK;
+}
+
+extern "C" int bf_gsf_destroy(bf_gsf_handle h) {
+  if (!h) return BF_OK;
+  h->carry_w.release(); h->carry_m.release(); h->carry_P.release();
+  for (DevBuf& b : h->hbuf) b.release();
+  delete h;
+  return BF_OK;
+}
+
+extern "C" int bf_gsf_kernel_launches(bf_gsf_handle h, int64_t* out) {
+  if (!h || !out) return fail(BF_EINVAL, "NULL argument");
+  *out = h->launches; return BF_OK;
+}
+
+namespace {
+struct GsfRun {
+  bf_gsf_s* h; const bf_gsf_io* io; cudaStream_t s;
+  template <class M> int run() {
+    GsfArgs a;
+    a.M = h->cfg.num_components; a.T = io->T; a.resume = io->resume; a.emissions_per_trial = io->emissions_per_trial;
+    a.emissions = io->emissions; a.inputs = io->inputs; a.init_means = io->init_means; a.init_covs = io->init_covs;
+    a.init_weights = io->init_weights;
+    a.carry_w = h->carry_w.as<float>(); a.carry_m = h->carry_m.as<float>(); a.carry_P = h->carry_P.as<float>();
+    a.out_weights = io->out_weights; a.out_means = io->out_means; a.out_covs = io->out_covs;
+    a.out_pred_means = io->out_pred_means; a.out_pred_covs = io->out_pred_covs; a.out_loglik = io->out_loglik;
+    a.out_mix_mean = io->out_mix_mean;
+    const int threads = std::max(32, ((a.M + 31) / 32) * 32);
+    k_gsf<M><<<h->cfg.num_trials, threads, 0, s>>>(h->mc, a);
+    LAUNCH_OK();
+    h->launches += 1;
+    return BF_OK;
+  }
+};
+}  // namespace
+
+static int gsf_check_io(bf_gsf_s* h, const bf_gsf_io* io) {
+  if (!h || !io) return fail(BF_EINVAL, "NULL argument");
+  if (io->T < 1) return fail(BF_EINVAL, "T must be >= 1 (got %d)", io->T);
+  if (!io->emissions) return fail(BF_EINVAL, "emissions is NULL");
+  if (!io->resume && !io->init_means) return fail(BF_EINVAL, "init_means is NULL");
+  if (io->resume && !h->have_carry) return fail(BF_EINVAL, "resume requested but the handle holds no carry yet");
+  return BF_OK;
+}
+
+extern "C" int bf_gsf_run(bf_gsf_handle h, const bf_gsf_io* io, void* stream) {
+  int rc = gsf_check_io(h, io);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  GsfRun fn{h, io, (cudaStream_t)stream};
+  rc = bf_dispatch_model(h->mc, fn);
+  if (rc == -3) return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", h->mc.model_id, h->mc.dx, h->mc.dy);
+  if (rc == BF_OK) h->have_carry = true;
+  return rc;
+}
+
+extern "C" int bf_gsf_run_host(bf_gsf_handle h, const bf_gsf_io* hio) {
+  int rc = gsf_check_io(h, hio);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = 0;
+  const size_t M = h->cfg.num_components, B = h->cfg.num_trials, T = hio->T, dx = h->mc.dx, dy = h->mc.dy;
+  bf_gsf_io d = *hio;
+  int k = 0;
+#define IN(field, count) if ((rc = stage_in(h->hbuf[k++], hio->field, (size_t)(count) * 4, s, (const void**)&d.field))) return rc;
+#define OUT(field, count) if ((rc = stage_out(h->hbuf[k++], hio->field, (size_t)(count) * 4, (void**)&d.field))) return rc;
+  IN(emissions, (hio->emissions_per_trial ? B : 1) * T * dy)
+  IN(inputs, T)
+  IN(init_means, B * M * dx)
+  IN(init_covs, B * M * dx * dx)
+  IN(init_weights, B * M)
+  OUT(out_weights, B * T * M) OUT(out_means, B * T * M * dx) OUT(out_covs, B * T * M * dx * dx)
+  OUT(out_pred_means, B * T * M * dx) OUT(out_pred_covs, B * T * M * dx * dx) OUT(out_loglik, B * T) OUT(out_mix_mean, B * T * dx)
+#undef IN
+#undef OUT
+  rc = bf_gsf_run(h, &d, s);
+  if (rc) return rc;
+#define BACK(field, count) if (hio->field) CUDA_OK(cudaMemcpyAsync(hio->field, d.field, (size_t)(count) * 4, cudaMemcpyDeviceToHost, s));
+  BACK(out_weights, B * T * M) BACK(out_means, B * T * M * dx) BACK(out_covs, B * T * M * dx * dx)
+  BACK(out_pred_means, B * T * M * dx) BACK(out_pred_covs, B * T * M * dx * dx) BACK(out_loglik, B * T) BACK(out_mix_mean, B * T * dx)
+#undef BACK
+  CUDA_OK(cudaStreamSynchronize(s));
+  return BF_OK;
+}
+
+// ========================================================================================== stand-alone resampler
+static int scan_common(const float* w, int64_t n, cudaStream_t s, float** E_out, void** to_free) {
+  if (!w) return fail(BF_EINVAL, "NULL argument");
+  if (n < 1 || n > (int64_t)1 << 30) return fail(BF_EINVAL, "n=%lld out of range", (long long)n);
+  const int ntiles = (int)((n + 1 + PF_TILE - 1) / PF_TILE);
+  const size_t bytes = ((size_t)ntiles * PF_TILE + 2 * (size_t)ntiles + 8) * 4;
+  float* base;
+  CUDA_OK(cudaMallocAsync((void**)&base, bytes, s));
+  float* E = base;
+  float* tilesum = base + (size_t)ntiles * PF_TILE;
+  float* Etile = tilesum + ntiles;
+  const int nchunk = (ntiles + 1 + PF_TILE - 1) / PF_TILE;
+  const size_t scan_smem = (size_t)(nchunk + 1 + PF_TILE_WARPS + 8) * sizeof(float);
+  k_raw_tilesum<<<ntiles, PF_TILE_WARPS * 32, 0, s>>>(w, (int)n, tilesum);
+  k_scan_tiles<<<1, PF_TILE_WARPS * 32, scan_smem, s>>>(tilesum, Etile, ntiles, nullptr);
+  k_raw_downsweep<<<ntiles, PF_TILE_WARPS * 32, 0, s>>>(w, (int)n, Etile, E);
+  LAUNCH_OK();
+  *E_out = E; *to_free = base;
+  return BF_OK;
+}
+
+extern "C" int bf_cumsum(const float* w, float* cdf, int64_t n, void* stream) {
+  if (!cdf) return fail(BF_EINVAL, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* E; void* base;
+  int rc = scan_common(w, n, s, &E, &base);
+  if (rc) return rc;
+  k_shift_cdf<<<(int)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, s>>>(E, cdf, (int)n);
+  LAUNCH_OK();
+  CUDA_OK(cudaFreeAsync(base, s));
+  return BF_OK;
+}
+
+extern "C" int bf_resample(const float* w, const float* u, int32_t* anc, int64_t n, int32_t resampler, void* stream) {
+  if (!u || !anc) return fail(BF_EINVAL, "NULL argument");
+  if (resampler != BF_RESAMPLE_MULTINOMIAL && resampler != BF_RESAMPLE_SYSTEMATIC) return fail(BF_EINVAL, "unknown resampler %d", resampler);
+  cudaStream_t s = (cudaStream_t)stream;
+  float* E; void* base;
+  int rc = scan_common(w, n, s, &E, &base);
+  if (rc) return rc;
+  k_raw_search<<<(int)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, s>>>(E, u, anc, (int)n, resampler);
+  LAUNCH_OK();
+  CUDA_OK(cudaFreeAsync(base, s));
+  return BF_OK;
+}
+
+// ========================================================================================== model eval / sampler
+namespace {
+struct EvalRun {
+  const ModelConst* mc; int what; int n; const float* x; const float* aux; float u; float* out; cudaStream_t s;
+  template <class M> int run() {
+    const int grid = std::max(1, std::min((n + 127) / 128, 4096));
+    k_model_eval<M><<<grid, 128, 0, s>>>(*mc, what, n, x, aux, u, out);
+    LAUNCH_OK();
+    return BF_OK;
+  }
+};
+struct SampleRun {
+  const ModelConst* mc; int B, T; const float* inputs; unsigned long long seed; const float *z0, *qn, *rn; float *states, *emissions;
+  cudaStream_t s;
+  template <class M> int run() {
+    k_ssm_sample<M><<<(B + 63) / 64, 64, 0, s>>>(*mc, B, T, inputs, seed, z0, qn, rn, states, emissions);
+    LAUNCH_OK();
+    return BF_OK;
+  }
+};
+}  // namespace
+
+extern "C" int bf_model_eval(const bf_model_desc* model, int32_t what, int64_t n, const float* x, const float* aux, float u,
+                             float* out, void* stream) {
+  ModelConst mc;
+  int rc = build_model_const(model, &mc);
+  if (rc) return rc;
+  if (what < 0 || what > 5) return fail(BF_EINVAL, "what=%d out of range", what);
+  if (n < 1 || n > (int64_t)1 << 30 || !x || !out) return fail(BF_EINVAL, "bad n or NULL pointer");
+  if (what == 5 && !aux) return fail(BF_EINVAL, "log-prob needs y in aux");
+  EvalRun fn{&mc, what, (int)n, x, aux, u, out, (cudaStream_t)stream};
+  rc = bf_dispatch_model(mc, fn);
+  if (rc == -3) return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", mc.model_id, mc.dx, mc.dy);
+  return rc;
+}
+
+extern "C" int bf_ssm_sample(const bf_model_desc* model, int32_t B, int32_t T, const float* inputs, uint64_t seed,
+                             const float* z0, const float* q_noise, const float* r_noise, float* states, float* emissions,
+                             void* stream) {
+  ModelConst mc;
+  int rc = build_model_const(model, &mc);
+  if (rc) return rc;
+  if (B < 1 || T < 1 || !states || !emissions) return fail(BF_EINVAL, "bad B/T or NULL output");
+  SampleRun fn{&mc, B, T, inputs, seed, z0, q_noise, r_noise, states, emissions, (cudaStream_t)stream};
+  rc = bf_dispatch_model(mc, fn);
+  if (rc == -3) return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", mc.model_id, mc.dx, mc.dy);
+  return rc;
+}

@@ -1,0 +1,316 @@
+// gsf_kernels.cuh -- Gaussian-sum (mixture of EKFs) filter, persistent over time (sm_100a).
+//
+// Restates gaussfiltax/inference.py:333-365 (`_step` of gaussian_sum_filter): per component
+// `_condition_on` (:72-105) on the carried prediction, the max-shifted evidence reweighting across the
+// M components (:347-350), then `_predict` (:51-70).  One CTA per independent trial, one thread per
+// mixture component; a component's weight, mean and covariance stay in that thread's registers for all
+// T steps, so the only per-step HBM traffic is the requested outputs.  The only cross-component coupling
+// (one max and one sum per step) is a warp-shuffle + shared-memory CTA reduction.
+//
+// Arithmetic mirrors the reference, including its quirks:
+//   K  = solve(S + 1e-6 [every element], H P)^T          utils.py:256-259 psd_solve, LU with partial pivoting
+//   P+ = P - (K S) K^T with the UN-jittered S            inference.py:101
+//   ll = MVN(h(m), S).log_prob(y), Cholesky of the un-jittered S   inference.py:104 (TFP)
+//   no re-symmetrisation of P+.
+// All registered models have additive emission noise (H_r = I, so H_r R H_r^T = R) and a constant F_q,
+// so F_q Q F_q^T is computed once per CTA.
+#pragma once
+#include "common.cuh"
+#include "models.cuh"
+
+struct GsfArgs {
+  int M, T, resume, emissions_per_trial;
+  const float* emissions; const float* inputs;
+  const float* init_means; const float* init_covs; const float* init_weights;
+  float* carry_w; float* carry_m; float* carry_P;       // handle-owned carry [B,M], [B,M,DX], [B,M,DX,DX]
+  float* out_weights; float* out_means; float* out_covs; float* out_pred_means; float* out_pred_covs;
+  float* out_loglik; float* out_mix_mean;
+};
+
+// C[RxC] = A[RxK] @ B[KxC]
+template <int R, int K, int C>
+__device__ __forceinline__ void mm(const float* A, const float* B, float* Cm) {
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) s += A[i * K + k] * B[k * C + j];
+      Cm[i * C + j] = s;
+    }
+}
+// C[RxC] = A[RxK] @ B[CxK]^T
+template <int R, int K, int C>
+__device__ __forceinline__ void mmt(const float* A, const float* B, float* Cm) {
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) s += A[i * K + k] * B[j * K + k];
+      Cm[i * C + j] = s;
+    }
+}
+
+// Solve A X = B in place (B <- X) by Gaussian elimination with partial pivoting, A [NxN], B [NxC].
+// Row swaps are predicated so every index stays compile-time (registers, no local memory).
+template <int N, int C>
+__device__ __forceinline__ void lu_solve(float* A, float* B) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    int p = k;
+    float best = fabsf(A[k * N + k]);
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) {
+      float v = fabsf(A[r * N + k]);
+      if (v > best) { best = v; p = r; }
+    }
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) {
+      const bool sw = (p == r);
+#pragma unroll
+      for (int c = 0; c < N; ++c) { float a0 = A[k * N + c], a1 = A[r * N + c]; A[k * N + c] = sw ? a1 : a0; A[r * N + c] = sw ? a0 : a1; }
+#pragma unroll
+      for (int c = 0; c < C; ++c) { float b0 = B[k * C + c], b1 = B[r * C + c]; B[k * C + c] = sw ? b1 : b0; B[r * C + c] = sw ? b0 : b1; }
+    }
+    const float piv = A[k * N + k];
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) {
+      const float l = A[r * N + k] / piv;
+#pragma unroll
+      for (int c = k + 1; c < N; ++c) A[r * N + c] -= l * A[k * N + c];
+#pragma unroll
+      for (int c = 0; c < C; ++c) B[r * C + c] -= l * B[k * C + c];
+    }
+  }
+#pragma unroll
+  for (int k = N - 1; k >= 0; --k) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float s = B[k * C + c];
+#pragma unroll
+      for (int j = k + 1; j < N; ++j) s -= A[k * N + j] * B[j * C + c];
+      B[k * C + c] = s / A[k * N + k];
+    }
+  }
+}
+
+// log N(y; yhat, S) with TFP's formula (Cholesky, forward substitution)
+template <int N>
+__device__ __forceinline__ float mvn_logpdf_chol(const float* S, const float* d) {
+  float L[N * N];
+  float logdet = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      float s = S[i * N + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[i * N + k] * L[j * N + k];
+      if (i == j) { L[i * N + i] = sqrtf(s); logdet += logf(L[i * N + i]); }
+      else L[i * N + j] = s / L[j * N + j];
+    }
+  }
+  float ss = 0.0f, z[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float s = d[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) s -= L[i * N + j] * z[j];
+    z[i] = s / L[i * N + i];
+    ss += z[i] * z[i];
+  }
+  return -0.5f * ss - logdet - 0.5f * (float)N * 1.8378770664093453f;
+}
+
+// one component: `_condition_on` (inference.py:72-105).  m,P in/out; returns ll.
+template <class Mo>
+__device__ __forceinline__ float ekf_condition(float* m, float* P, const float* y, float u, const ModelConst& mc) {
+  constexpr int DX = Mo::DX, DY = Mo::DY;
+  float H[DY * DX], HP[DY * DX], S[DY * DY], Sj[DY * DY], X[DY * DX];
+  Mo::Hx(m, mc.r0, u, mc, H);
+  mm<DY, DX, DX>(H, P, HP);                         // H_x @ P
+  mmt<DY, DX, DY>(HP, H, S);                        // (H_x P) H_x^T
+#pragma unroll
+  for (int i = 0; i < DY; ++i)
+#pragma unroll
+    for (int j = 0; j < DY; ++j) {
+      S[i * DY + j] = mc.R[i * DY + j] + S[i * DY + j];      // H_r R H_r^T + H_x P H_x^T  (:99), H_r = I
+      Sj[i * DY + j] = S[i * DY + j] + 1e-6f;                // psd_solve jitter on EVERY element
+    }
+#pragma unroll
+  for (int i = 0; i < DY * DX; ++i) X[i] = HP[i];
+  lu_solve<DY, DX>(Sj, X);                          // X = solve(S', H P);  K = X^T   (:100)
+  float KS[DX * DY];                                // K @ S
+#pragma unroll
+  for (int i = 0; i < DX; ++i)
+#pragma unroll
+    for (int j = 0; j < DY; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < DY; ++k) s += X[k * DX + i] * S[k * DY + j];
+      KS[i * DY + j] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < DX; ++i)                      // P - (K S) K^T           (:101)
+#pragma unroll
+    for (int j = 0; j < DX; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < DY; ++k) s += KS[i * DY + k] * X[k * DX + j];
+      P[i * DX + j] -= s;
+    }
+  float yhat[DY], d[DY];
+  Mo::h(m, mc.r0, u, mc, yhat);
+#pragma unroll
+  for (int i = 0; i < DY; ++i) d[i] = y[i] - yhat[i];
+#pragma unroll
+  for (int i = 0; i < DX; ++i) {                    // m + K (y - h(m))        (:102)
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DY; ++k) s += X[k * DX + i] * d[k];
+    m[i] += s;
+  }
+  return mvn_logpdf_chol<DY>(S, d);                 // (:103-104)
+}
+
+// one component: `_predict` (inference.py:51-70).  GQG = F_q Q F_q^T (constant F_q).
+template <class Mo>
+__device__ __forceinline__ void ekf_predict(float* m, float* P, float u, const ModelConst& mc, const float* GQG) {
+  constexpr int DX = Mo::DX;
+  float F[DX * DX], FP[DX * DX], mn[DX];
+  Mo::Fx(m, mc.q0, u, mc, F);
+  Mo::f(m, mc.q0, u, mc, mn);
+  mm<DX, DX, DX>(F, P, FP);
+#pragma unroll
+  for (int i = 0; i < DX; ++i)
+#pragma unroll
+    for (int j = 0; j < DX; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < DX; ++k) s += FP[i * DX + k] * F[j * DX + k];
+      P[i * DX + j] = s + GQG[i * DX + j];
+    }
+#pragma unroll
+  for (int i = 0; i < DX; ++i) m[i] = mn[i];
+}
+
+template <int K>
+__device__ __forceinline__ void store_vec(float* dst, const float* v) {
+  if constexpr (K % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < K / 4; ++k) reinterpret_cast<float4*>(dst)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  } else if constexpr (K % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < K / 2; ++k) reinterpret_cast<float2*>(dst)[k] = make_float2(v[2 * k], v[2 * k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) dst[k] = v[k];
+  }
+}
+
+template <class Mo>
+__global__ void k_gsf(const __grid_constant__ ModelConst mc, const __grid_constant__ GsfArgs a) {
+  constexpr int DX = Mo::DX, DQ = Mo::DQ, DY = Mo::DY;
+  __shared__ float s_red[32 * (1 + BF_MAXD)];
+  __shared__ float s_gqg[BF_MAXD * BF_MAXD];
+  const int M = a.M, T = a.T, b = blockIdx.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+  const bool active = tid < M;
+  const size_t bm = (size_t)b * M + (active ? tid : 0);
+
+  if (tid == 0) {                     // F_q Q F_q^T, F_q constant for every registered model
+    float x0[DX], Fq[DX * DQ], FQ[DX * DQ];
+#pragma unroll
+    for (int i = 0; i < DX; ++i) x0[i] = mc.m0[i];
+    Mo::Fq(x0, mc.q0, 0.0f, mc, Fq);
+    mm<DX, DQ, DQ>(Fq, mc.Q, FQ);
+    float G[DX * DX];
+    mmt<DX, DQ, DX>(FQ, Fq, G);
+#pragma unroll
+    for (int i = 0; i < DX * DX; ++i) s_gqg[i] = G[i];
+  }
+  __syncthreads();
+  float GQG[DX * DX];
+#pragma unroll
+  for (int i = 0; i < DX * DX; ++i) GQG[i] = s_gqg[i];
+
+  // carry: (weights, pred_means, pred_covs)   inference.py:367-369
+  float w, m[DX], P[DX * DX];
+  if (a.resume) {
+    w = active ? a.carry_w[bm] : 0.0f;
+#pragma unroll
+    for (int i = 0; i < DX; ++i) m[i] = a.carry_m[bm * DX + i];
+#pragma unroll
+    for (int i = 0; i < DX * DX; ++i) P[i] = a.carry_P[bm * DX * DX + i];
+  } else {
+    w = active ? (a.init_weights ? a.init_weights[bm] : 1.0f / (float)M) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < DX; ++i) m[i] = a.init_means[bm * DX + i];
+#pragma unroll
+    for (int i = 0; i < DX * DX; ++i) P[i] = a.init_covs ? a.init_covs[bm * DX * DX + i] : mc.P0[i];
+  }
+
+  for (int t = 0; t < T; ++t) {
+    const float* yp = a.emissions + ((size_t)(a.emissions_per_trial ? b : 0) * T + t) * DY;
+    float y[DY];
+#pragma unroll
+    for (int k = 0; k < DY; ++k) y[k] = yp[k];
+    const float u = a.inputs ? a.inputs[t] : 0.0f;
+    const size_t btm = ((size_t)b * T + t) * M + (active ? tid : 0);
+
+    float ll = ekf_condition<Mo>(m, P, y, u, mc);
+    if (!active) ll = -INFINITY;
+    if (active) {
+      if (a.out_means) store_vec<DX>(a.out_means + btm * DX, m);
+      if (a.out_covs) store_vec<DX * DX>(a.out_covs + btm * DX * DX, P);
+    }
+    // lls -= max ; w = exp(lls) * w ; w /= sum(w)       (inference.py:347-350)
+    float mx = warp_max(ll);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = warp_max(lane < nwarps ? s_red[lane] : -INFINITY);
+    float e = active ? expf(ll - mx) * w : 0.0f;
+    float z = warp_sum(e);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = z;
+    __syncthreads();
+    const float Z = warp_sum(lane < nwarps ? s_red[lane] : 0.0f);
+    w = e / Z;
+    if (active && a.out_weights) a.out_weights[btm] = w;
+    if (tid == 0 && a.out_loglik) a.out_loglik[(size_t)b * T + t] = mx + logf(Z);
+    if (a.out_mix_mean) {
+      float v[DX];
+#pragma unroll
+      for (int k = 0; k < DX; ++k) v[k] = warp_sum(active ? w * m[k] : 0.0f);
+      __syncthreads();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < DX; ++k) s_red[warp * DX + k] = v[k];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < DX; ++k) v[k] = warp_sum(lane < nwarps ? s_red[lane * DX + k] : 0.0f);
+      if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < DX; ++k) a.out_mix_mean[((size_t)b * T + t) * DX + k] = v[k];
+      }
+    }
+    __syncthreads();                  // s_red reuse in the next step
+
+    ekf_predict<Mo>(m, P, u, mc, GQG);
+    if (active) {
+      if (a.out_pred_means) store_vec<DX>(a.out_pred_means + btm * DX, m);
+      if (a.out_pred_covs) store_vec<DX * DX>(a.out_pred_covs + btm * DX * DX, P);
+    }
+  }
+  if (active) {
+    a.carry_w[bm] = w;
+#pragma unroll
+    for (int i = 0; i < DX; ++i) a.carry_m[bm * DX + i] = m[i];
+#pragma unroll
+    for (int i = 0; i < DX * DX; ++i) a.carry_P[bm * DX * DX + i] = P[i];
+  }
+}

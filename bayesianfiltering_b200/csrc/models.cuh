@@ -1,0 +1,254 @@
+// models.cuh -- compiled model registry: f(x,q,u), h(x,r,u) and their analytic Jacobians as
+// __device__ functors templated into the filter kernels.  The reference takes arbitrary Python
+// callables (gaussfiltax/models.py:46-50) and differentiates them with jacfwd (inference.py:327-329);
+// a kernel cannot, so the models its drivers define are compiled in.  Sources of each definition are
+// listed in oracle/models.py, which restates the same functions in NumPy and is what these are tested
+// against (values at rtol 1e-5, Jacobians also against float64 finite differences).
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// UNGM / "stochastic growth model":  f = a x + b x/(1+x^2) + c u + q ;  h = d x + e x^2 + r
+// theta = [a b c d e]     (Experiment_TSP_2023.ipynb cell 2: f3, g3)
+struct UngmModel {
+  static constexpr int DX = 1, DQ = 1, DY = 1, DR = 1;
+  __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
+    float xx = x[0];
+    o[0] = c.theta[0] * xx + c.theta[1] * xx / (1.0f + xx * xx) + c.theta[2] * u + q[0];
+  }
+  __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
+    o[0] = c.theta[3] * x[0] + c.theta[4] * x[0] * x[0] + r[0];
+  }
+  __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+    float x2 = x[0] * x[0], den = 1.0f + x2;
+    J[0] = c.theta[0] + c.theta[1] * (1.0f - x2) / (den * den);
+  }
+  __device__ __forceinline__ static void Fq(const float* x, const float* q, float u, const ModelConst& c, float* J) { J[0] = 1.0f; }
+  __device__ __forceinline__ static void Hx(const float* x, const float* r, float u, const ModelConst& c, float* J) {
+    J[0] = c.theta[3] + 2.0f * c.theta[4] * x[0];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Manoeuvring bearings-only tracking (BOT_Experiment_script.py:27-47).  theta = [dt acc omega_scale]
+template <int DY_>
+struct BotModel {
+  static constexpr int DX = 4, DQ = 2, DY = DY_, DR = DY_;
+
+  struct Turn { float s, om, sn, cs, A, B; };
+  __device__ __forceinline__ static Turn turn(const float* x, const ModelConst& c) {
+    Turn t;
+    t.s = sqrtf(x[1] * x[1] + x[3] * x[3]);
+    t.om = c.theta[2] * c.theta[1] / t.s;
+    sincosf(c.theta[0] * t.om, &t.sn, &t.cs);
+    t.A = t.sn / t.om;
+    t.B = (1.0f - t.cs) / t.om;
+    return t;
+  }
+  __device__ __forceinline__ static void coef(float u, float& c0, float& c1, float& c2) {
+    c0 = 0.5f * (u - 1.0f) * (u - 2.0f); c1 = -u * (u - 2.0f); c2 = 0.5f * u * (u - 1.0f);
+  }
+  __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
+    float c0, c1, c2; coef(u, c0, c1, c2);
+    const float T = c.theta[0];
+    Turn t = turn(x, c);
+    // FCT(x,+acc) x and FCT(x,-acc) x share sin/cos: Omega -> -Omega flips sn and B only
+    float p0 = x[0] + t.A * x[1], p2 = x[2] + t.A * x[3];
+    float ct1[4] = {p0 - t.B * x[3], t.cs * x[1] - t.sn * x[3], p2 + t.B * x[1], t.sn * x[1] + t.cs * x[3]};
+    float ct2[4] = {p0 + t.B * x[3], t.cs * x[1] + t.sn * x[3], p2 - t.B * x[1], -t.sn * x[1] + t.cs * x[3]};
+    float cv[4] = {x[0] + T * x[1], x[1], x[2] + T * x[3], x[3]};
+    float gq[4] = {0.5f * q[0], q[0], 0.5f * q[1], q[1]};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = c0 * cv[i] + c1 * ct1[i] + c2 * ct2[i] + gq[i];
+  }
+  __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
+    o[0] = atan2f(x[2], x[0]) + r[0];
+    if (DY == 2) o[1] = sqrtf(x[0] * x[0] + x[2] * x[2]) + r[1];
+  }
+  // d(FCT(x,a) x)/dx for a = +acc (sgn=+1) or -acc (sgn=-1), accumulated into J with weight cw
+  __device__ __forceinline__ static void fct_jac(const float* x, const Turn& t, float T, float sgn, float cw, float* J) {
+    const float om = sgn * t.om, sn = sgn * t.sn, cs = t.cs, A = t.A, B = sgn * t.B;
+    const float dA = (T * cs * om - sn) / (om * om);
+    const float dB = (T * sn * om - (1.0f - cs)) / (om * om);
+    const float dsn = T * cs, dcs = -T * sn;
+    const float v[4] = {dA * x[1] - dB * x[3], dcs * x[1] - dsn * x[3], dB * x[1] + dA * x[3], dsn * x[1] + dcs * x[3]};
+    const float s2 = t.s * t.s;
+    const float g1 = -om * x[1] / s2, g3 = -om * x[3] / s2;
+    const float M[16] = {1.0f, A, 0.0f, -B, 0.0f, cs, 0.0f, -sn, 0.0f, B, 1.0f, A, 0.0f, sn, 0.0f, cs};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float e = M[i * 4 + j];
+        if (j == 1) e += v[i] * g1;
+        if (j == 3) e += v[i] * g3;
+        J[i * 4 + j] += cw * e;
+      }
+    }
+  }
+  __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+    float c0, c1, c2; coef(u, c0, c1, c2);
+    const float T = c.theta[0];
+    const float CV[16] = {1.0f, T, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f, T, 0.0f, 0.0f, 0.0f, 1.0f};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) J[i] = c0 * CV[i];
+    Turn t = turn(x, c);
+    fct_jac(x, t, T, 1.0f, c1, J);
+    fct_jac(x, t, T, -1.0f, c2, J);
+  }
+  __device__ __forceinline__ static void Fq(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+    const float G[8] = {0.5f, 0.0f, 1.0f, 0.0f, 0.0f, 0.5f, 0.0f, 1.0f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) J[i] = G[i];
+  }
+  __device__ __forceinline__ static void Hx(const float* x, const float* r, float u, const ModelConst& c, float* J) {
+    const float d2 = x[0] * x[0] + x[2] * x[2];
+    J[0] = -x[2] / d2; J[1] = 0.0f; J[2] = x[0] / d2; J[3] = 0.0f;
+    if (DY == 2) {
+      const float rg = sqrtf(d2);
+      J[4] = x[0] / rg; J[5] = 0.0f; J[6] = x[2] / rg; J[7] = 0.0f;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Lorenz-63, Euler step; h = c x.x + r.  theta = [sigma rho beta dt c]
+struct L63Model {
+  static constexpr int DX = 3, DQ = 3, DY = 1, DR = 1;
+  __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
+    const float sg = c.theta[0], rho = c.theta[1], be = c.theta[2], dt = c.theta[3];
+    o[0] = dt * sg * (x[1] - x[0]) + x[0] + q[0];
+    o[1] = dt * (x[0] * rho - x[1] - x[0] * x[2]) + x[1] + q[1];
+    o[2] = dt * (x[0] * x[1] - be * x[2]) + x[2] + q[2];
+  }
+  __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
+    o[0] = c.theta[4] * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) + r[0];
+  }
+  __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+    const float sg = c.theta[0], rho = c.theta[1], be = c.theta[2], dt = c.theta[3];
+    J[0] = 1.0f - dt * sg; J[1] = dt * sg; J[2] = 0.0f;
+    J[3] = dt * (rho - x[2]); J[4] = 1.0f - dt; J[5] = -dt * x[0];
+    J[6] = dt * x[1]; J[7] = dt * x[0]; J[8] = 1.0f - dt * be;
+  }
+  __device__ __forceinline__ static void Fq(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) J[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+  }
+  __device__ __forceinline__ static void Hx(const float* x, const float* r, float u, const ModelConst& c, float* J) {
+    const float k = 2.0f * c.theta[4];
+    J[0] = k * x[0]; J[1] = k * x[1]; J[2] = k * x[2];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Linear-Gaussian: f = A x + q, h = H x + r.  theta = [A (DX*DX) | H (DY*DX)], row-major
+template <int DX_, int DY_>
+struct LgModel {
+  static constexpr int DX = DX_, DQ = DX_, DY = DY_, DR = DY_;
+  __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
+#pragma unroll
+    for (int i = 0; i < DX; ++i) {
+      float a = 0.0f;
+#pragma unroll
+      for (int j = 0; j < DX; ++j) a += c.theta[i * DX + j] * x[j];
+      o[i] = a + q[i];
+    }
+  }
+  __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
+#pragma unroll
+    for (int i = 0; i < DY; ++i) {
+      float a = 0.0f;
+#pragma unroll
+      for (int j = 0; j < DX; ++j) a += c.theta[DX * DX + i * DX + j] * x[j];
+      o[i] = a + r[i];
+    }
+  }
+  __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+#pragma unroll
+    for (int i = 0; i < DX * DX; ++i) J[i] = c.theta[i];
+  }
+  __device__ __forceinline__ static void Fq(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+#pragma unroll
+    for (int i = 0; i < DX * DX; ++i) J[i] = (i % (DX + 1) == 0) ? 1.0f : 0.0f;
+  }
+  __device__ __forceinline__ static void Hx(const float* x, const float* r, float u, const ModelConst& c, float* J) {
+#pragma unroll
+    for (int i = 0; i < DY * DX; ++i) J[i] = c.theta[DX * DX + i];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// ICASSP toy: f = sin(w x) + q (element-wise), h = c x.x + r.  theta = [w c]
+template <int DX_>
+struct Sin1dModel {
+  static constexpr int DX = DX_, DQ = DX_, DY = 1, DR = 1;
+  __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
+#pragma unroll
+    for (int i = 0; i < DX; ++i) o[i] = sinf(c.theta[0] * x[i]) + q[i];
+  }
+  __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
+    float a = 0.0f;
+#pragma unroll
+    for (int i = 0; i < DX; ++i) a += x[i] * x[i];
+    o[0] = c.theta[1] * a + r[0];
+  }
+  __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+#pragma unroll
+    for (int i = 0; i < DX * DX; ++i) J[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < DX; ++i) J[i * DX + i] = c.theta[0] * cosf(c.theta[0] * x[i]);
+  }
+  __device__ __forceinline__ static void Fq(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+#pragma unroll
+    for (int i = 0; i < DX * DX; ++i) J[i] = (i % (DX + 1) == 0) ? 1.0f : 0.0f;
+  }
+  __device__ __forceinline__ static void Hx(const float* x, const float* r, float u, const ModelConst& c, float* J) {
+#pragma unroll
+    for (int i = 0; i < DX; ++i) J[i] = 2.0f * c.theta[1] * x[i];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// MVN(loc = h(x, r0, u), covariance_matrix = R).log_prob(y) -- the `*lp` callables of the reference's
+// drivers (e.g. BOT_Experiment_script.py:45) with TFP's formula: z = L^-1 (y - loc) by forward
+// substitution, -0.5 z.z - sum(log diag L) - 0.5 k log(2 pi).
+template <class M>
+__device__ __forceinline__ float emission_log_prob(const float* x, const float* y, float u, const ModelConst& c) {
+  float loc[M::DY];
+  M::h(x, c.r0, u, c, loc);
+  float z[M::DY];
+  float ss = 0.0f;
+#pragma unroll
+  for (int i = 0; i < M::DY; ++i) {
+    float d = y[i] - loc[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) d -= c.LR[i * M::DR + j] * z[j];
+    z[i] = d / c.LR[i * M::DR + i];
+    ss += z[i] * z[i];
+  }
+  return -0.5f * ss + c.lp_const;
+}
+
+// Dispatch a generic lambda-like functor over the registry.  F must provide `template<class M> int run()`.
+#define BF_DISPATCH_LG(F, dxv, dyv)                                  \
+  if (mc.dx == dxv && mc.dy == dyv) return F.template run<LgModel<dxv, dyv>>();
+
+template <class F>
+int bf_dispatch_model(const ModelConst& mc, F& fn) {
+  switch (mc.model_id) {
+    case 1: return fn.template run<UngmModel>();
+    case 2: if (mc.dy == 1) return fn.template run<BotModel<1>>();
+            if (mc.dy == 2) return fn.template run<BotModel<2>>();
+            return -3;
+    case 3: return fn.template run<L63Model>();
+    case 5:
+      BF_DISPATCH_LG(fn, 1, 1) BF_DISPATCH_LG(fn, 2, 1) BF_DISPATCH_LG(fn, 2, 2) BF_DISPATCH_LG(fn, 3, 1)
+      BF_DISPATCH_LG(fn, 3, 3) BF_DISPATCH_LG(fn, 4, 2) BF_DISPATCH_LG(fn, 4, 4) BF_DISPATCH_LG(fn, 8, 8)
+      return -3;
+    case 6: if (mc.dx == 1) return fn.template run<Sin1dModel<1>>();
+            if (mc.dx == 2) return fn.template run<Sin1dModel<2>>();
+            if (mc.dx == 3) return fn.template run<Sin1dModel<3>>();
+            return -3;
+    default: return -3;
+  }
+}

@@ -1,0 +1,299 @@
+"""Thin owners of libbfilt handles.  Two calling modes per engine:
+
+  * device mode: torch CUDA tensors in, torch CUDA tensors out, work enqueued on torch's current stream,
+    no synchronisation (`run`);
+  * host mode: NumPy arrays in, NumPy arrays out through the `*_run_host` C entry points, which do the
+    H2D / D2H copies themselves (`run_host`) -- this is the end-to-end path bench.py times.
+
+Buffers are time-major ([B,T,N,..] / [B,T,M,..]); `inference.py` returns the reference's [N,T,..] views.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_RESAMPLERS = {"multinomial": _lib.RESAMPLE_MULTINOMIAL, "systematic": _lib.RESAMPLE_SYSTEMATIC}
+_PATHS = {"auto": _lib.PATH_AUTO, "resident": _lib.PATH_RESIDENT, "streamed": _lib.PATH_STREAMED}
+
+PF_OUTPUTS = {
+    # name: (io field, per-(trial,step) shape as a function of (N, dx), dtype)
+    "particles": ("out_particles", lambda N, dx: (N, dx), np.float32),
+    "weights": ("out_weights", lambda N, dx: (N,), np.float32),
+    "propagated": ("out_propagated", lambda N, dx: (N, dx), np.float32),
+    "norm_weights": ("out_norm_weights", lambda N, dx: (N,), np.float32),
+    "ancestors": ("out_ancestors", lambda N, dx: (N,), np.int32),
+    "means": ("out_mean", lambda N, dx: (dx,), np.float32),
+    "log_likelihood": ("out_loglik", lambda N, dx: (), np.float32),
+    "ess": ("out_ess", lambda N, dx: (), np.float32),
+    "resampled": ("out_resampled", lambda N, dx: (), np.int32),
+}
+PF_FINALS = {
+    "final_particles": ("final_particles", lambda N, dx: (N, dx)),
+    "final_weights": ("final_weights", lambda N, dx: (N,)),
+}
+GSF_OUTPUTS = {
+    "weights": ("out_weights", lambda M, dx: (M,)),
+    "means": ("out_means", lambda M, dx: (M, dx)),
+    "covariances": ("out_covs", lambda M, dx: (M, dx, dx)),
+    "predicted_means": ("out_pred_means", lambda M, dx: (M, dx)),
+    "predicted_covariances": ("out_pred_covs", lambda M, dx: (M, dx, dx)),
+    "log_likelihood": ("out_loglik", lambda M, dx: ()),
+    "mixture_mean": ("out_mix_mean", lambda M, dx: (dx,)),
+}
+
+
+def _default_device():
+    import os
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def _np32(a, shape, name):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    if a.size != int(np.prod(shape)):
+        raise ValueError(f"{name} has {a.size} elements, expected shape {tuple(shape)}")
+    return a.reshape(shape)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+class ParticleFilterEngine:
+    """Owns a bf_pf_handle: N particles x B independent trials of one registry model."""
+
+    def __init__(self, host_model, num_particles, num_trials=1, ess_threshold=0.5, resampler="multinomial",
+                 path="auto", seed=0, device=None):
+        self.lib = _lib.load()
+        self.hm = host_model
+        self.N, self.B = int(num_particles), int(num_trials)
+        self.dx, self.dq, self.dy = host_model.dx, host_model.dq, host_model.dy
+        self.resampler = resampler
+        self.device = _default_device() if device is None else int(device)
+        cfg = _lib.PfConfig(self.N, self.B, float(ess_threshold), _RESAMPLERS[resampler], _PATHS[path],
+                            int(seed) & 0xFFFFFFFFFFFFFFFF, self.device, 0)
+        self.h = C.c_void_p()
+        _lib.check(self.lib.bf_pf_create(C.byref(host_model.desc), C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.bf_pf_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def launches(self):
+        n = C.c_int64()
+        _lib.check(self.lib.bf_pf_kernel_launches(self.h, C.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------ shapes of the inputs
+    def _in_shapes(self, T, per_trial):
+        B, N = self.B, self.N
+        return dict(emissions=((B, T, self.dy) if per_trial else (T, self.dy)), inputs=(T,),
+                    init_particles=(B, N, self.dx), init_weights=(B, N), noise=(T, B, N, self.dq),
+                    resample_u=((T, B) if self.resampler == "systematic" else (T, B, N)))
+
+    def _io(self, T, per_trial, t_offset, resume, ins, outs):
+        io = _lib.PfIO()
+        io.T, io.t_offset, io.resume, io.emissions_per_trial = int(T), int(t_offset), int(bool(resume)), int(bool(per_trial))
+        for k, v in ins.items():
+            setattr(io, k, _ptr(v))
+        for k, v in outs.items():
+            setattr(io, k, _ptr(v))
+        return io
+
+    def run_host(self, emissions, inputs=None, init_particles=None, init_weights=None, noise=None, resample_u=None,
+                 outputs=("weights", "particles"), t_offset=0, resume=False):
+        """NumPy in / NumPy out.  Copies happen inside bf_pf_run_host; returns after the device has finished."""
+        em = np.asarray(emissions, dtype=np.float32)
+        per_trial = em.ndim == 3
+        T = em.shape[-2] if em.ndim >= 2 else em.shape[0]
+        shp = self._in_shapes(T, per_trial)
+        ins = dict(emissions=_np32(em, shp["emissions"], "emissions"), inputs=_np32(inputs, shp["inputs"], "inputs"),
+                   init_particles=_np32(init_particles, shp["init_particles"], "init_particles"),
+                   init_weights=_np32(init_weights, shp["init_weights"], "init_weights"),
+                   noise=_np32(noise, shp["noise"], "noise"), resample_u=_np32(resample_u, shp["resample_u"], "resample_u"))
+        res, outs = {}, {}
+        for name in outputs:
+            if name in PF_OUTPUTS:
+                field, shape, dt = PF_OUTPUTS[name]
+                res[name] = np.empty((self.B, T) + shape(self.N, self.dx), dtype=dt)
+            elif name in PF_FINALS:
+                field, shape = PF_FINALS[name]
+                res[name] = np.empty((self.B,) + shape(self.N, self.dx), dtype=np.float32)
+            else:
+                raise ValueError(f"unknown particle-filter output {name!r}")
+            outs[field] = res[name]
+        io = self._io(T, per_trial, t_offset, resume, ins, outs)
+        _lib.check(self.lib.bf_pf_run_host(self.h, C.byref(io)))
+        return res
+
+    def run(self, emissions, inputs=None, init_particles=None, init_weights=None, noise=None, resample_u=None,
+            outputs=("weights", "particles"), t_offset=0, resume=False, out_buffers=None):
+        """torch CUDA tensors in / out, enqueued on torch's current stream, no synchronisation."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        f32 = lambda a, shape, name: None if a is None else self._t32(a, shape, name, dev)
+        em = emissions
+        per_trial = em.dim() == 3
+        T = em.shape[-2]
+        shp = self._in_shapes(T, per_trial)
+        ins = dict(emissions=f32(em, shp["emissions"], "emissions"), inputs=f32(inputs, shp["inputs"], "inputs"),
+                   init_particles=f32(init_particles, shp["init_particles"], "init_particles"),
+                   init_weights=f32(init_weights, shp["init_weights"], "init_weights"),
+                   noise=f32(noise, shp["noise"], "noise"), resample_u=f32(resample_u, shp["resample_u"], "resample_u"))
+        res, outs = {}, {}
+        for name in outputs:
+            if name in PF_OUTPUTS:
+                field, shape, dt = PF_OUTPUTS[name]
+                full = (self.B, T) + shape(self.N, self.dx)
+                tdt = torch.int32 if dt is np.int32 else torch.float32
+            elif name in PF_FINALS:
+                field, shape = PF_FINALS[name]
+                full = (self.B,) + shape(self.N, self.dx)
+                tdt = torch.float32
+            else:
+                raise ValueError(f"unknown particle-filter output {name!r}")
+            if out_buffers is not None and name in out_buffers:
+                buf = out_buffers[name]
+                if tuple(buf.shape) != full or buf.dtype != tdt or not buf.is_contiguous():
+                    raise ValueError(f"out_buffers[{name!r}] must be a contiguous {tdt} tensor of shape {full}")
+            else:
+                buf = torch.empty(full, dtype=tdt, device=dev)
+            res[name] = buf
+            outs[field] = buf
+        io = self._io(T, per_trial, t_offset, resume, ins, outs)
+        self._keep = (ins, outs)
+        _lib.check(self.lib.bf_pf_run(self.h, C.byref(io), torch.cuda.current_stream(dev).cuda_stream))
+        return res
+
+    @staticmethod
+    def _t32(a, shape, name, dev):
+        import torch
+        if not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(np.asarray(a, dtype=np.float32))
+        a = a.to(device=dev, dtype=torch.float32).contiguous()
+        if a.numel() != int(np.prod(shape)):
+            raise ValueError(f"{name} has {a.numel()} elements, expected shape {tuple(shape)}")
+        return a.view(shape)
+
+
+class GaussianSumFilterEngine:
+    """Owns a bf_gsf_handle: M components x B independent trials of one registry model."""
+
+    def __init__(self, host_model, num_components, num_trials=1, device=None):
+        self.lib = _lib.load()
+        self.hm = host_model
+        self.M, self.B = int(num_components), int(num_trials)
+        self.dx, self.dy = host_model.dx, host_model.dy
+        self.device = _default_device() if device is None else int(device)
+        cfg = _lib.GsfConfig(self.M, self.B, self.device, 0)
+        self.h = C.c_void_p()
+        _lib.check(self.lib.bf_gsf_create(C.byref(host_model.desc), C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.bf_gsf_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def launches(self):
+        n = C.c_int64()
+        _lib.check(self.lib.bf_gsf_kernel_launches(self.h, C.byref(n)))
+        return n.value
+
+    def _in_shapes(self, T, per_trial):
+        B, M, dx = self.B, self.M, self.dx
+        return dict(emissions=((B, T, self.dy) if per_trial else (T, self.dy)), inputs=(T,), init_means=(B, M, dx),
+                    init_covs=(B, M, dx, dx), init_weights=(B, M))
+
+    def _io(self, T, per_trial, resume, ins, outs):
+        io = _lib.GsfIO()
+        io.T, io.resume, io.emissions_per_trial = int(T), int(bool(resume)), int(bool(per_trial))
+        for k, v in ins.items():
+            setattr(io, k, _ptr(v))
+        for k, v in outs.items():
+            setattr(io, k, _ptr(v))
+        return io
+
+    def run_host(self, emissions, inputs=None, init_means=None, init_covs=None, init_weights=None,
+                 outputs=("weights", "means", "covariances", "predicted_means", "predicted_covariances"), resume=False):
+        em = np.asarray(emissions, dtype=np.float32)
+        per_trial = em.ndim == 3
+        T = em.shape[-2]
+        shp = self._in_shapes(T, per_trial)
+        ins = {k: _np32(v, shp[k], k) for k, v in dict(emissions=em, inputs=inputs, init_means=init_means,
+                                                        init_covs=init_covs, init_weights=init_weights).items()}
+        res, outs = {}, {}
+        for name in outputs:
+            if name not in GSF_OUTPUTS:
+                raise ValueError(f"unknown Gaussian-sum-filter output {name!r}")
+            field, shape = GSF_OUTPUTS[name]
+            res[name] = np.empty((self.B, T) + shape(self.M, self.dx), dtype=np.float32)
+            outs[field] = res[name]
+        io = self._io(T, per_trial, resume, ins, outs)
+        _lib.check(self.lib.bf_gsf_run_host(self.h, C.byref(io)))
+        return res
+
+    def run(self, emissions, inputs=None, init_means=None, init_covs=None, init_weights=None,
+            outputs=("weights", "means", "covariances", "predicted_means", "predicted_covariances"), resume=False,
+            out_buffers=None):
+        import torch
+        dev = torch.device("cuda", self.device)
+        per_trial = emissions.dim() == 3
+        T = emissions.shape[-2]
+        shp = self._in_shapes(T, per_trial)
+        t32 = ParticleFilterEngine._t32
+        ins = {k: (None if v is None else t32(v, shp[k], k, dev))
+               for k, v in dict(emissions=emissions, inputs=inputs, init_means=init_means, init_covs=init_covs,
+                                init_weights=init_weights).items()}
+        res, outs = {}, {}
+        for name in outputs:
+            if name not in GSF_OUTPUTS:
+                raise ValueError(f"unknown Gaussian-sum-filter output {name!r}")
+            field, shape = GSF_OUTPUTS[name]
+            full = (self.B, T) + shape(self.M, self.dx)
+            if out_buffers is not None and name in out_buffers:
+                buf = out_buffers[name]
+                if tuple(buf.shape) != full or buf.dtype != torch.float32 or not buf.is_contiguous():
+                    raise ValueError(f"out_buffers[{name!r}] must be a contiguous float32 tensor of shape {full}")
+            else:
+                buf = torch.empty(full, dtype=torch.float32, device=dev)
+            res[name] = buf
+            outs[field] = buf
+        io = self._io(T, per_trial, resume, ins, outs)
+        self._keep = (ins, outs)
+        _lib.check(self.lib.bf_gsf_run(self.h, C.byref(io), torch.cuda.current_stream(dev).cuda_stream))
+        return res
+
+
+def cumsum_canonical(w):
+    """cumsum in lax.associative_scan order on the GPU (torch CUDA tensor in/out); bit-exact vs the oracle."""
+    import torch
+    lib = _lib.load()
+    w = w.contiguous().float()
+    out = torch.empty_like(w)
+    _lib.check(lib.bf_cumsum(w.data_ptr(), out.data_ptr(), w.numel(), torch.cuda.current_stream(w.device).cuda_stream))
+    return out
+
+
+def resample_ancestors(w, u, resampler="multinomial"):
+    """Ancestor indices of jax.random.choice(p=w) for supplied uniforms (torch CUDA tensors)."""
+    import torch
+    lib = _lib.load()
+    w = w.contiguous().float()
+    u = u.contiguous().float().reshape(-1)
+    if resampler == "multinomial" and u.numel() != w.numel():
+        raise ValueError("multinomial resampling needs one uniform per particle")
+    anc = torch.empty(w.numel(), dtype=torch.int32, device=w.device)
+    _lib.check(lib.bf_resample(w.data_ptr(), u.data_ptr(), anc.data_ptr(), w.numel(), _RESAMPLERS[resampler],
+                               torch.cuda.current_stream(w.device).cuda_stream))
+    return anc

@@ -1,0 +1,172 @@
+/* bfilt.h -- C ABI of libbfilt.so: B200 (sm_100a) kernels for the gaussfiltax filtering hot path.
+ *
+ * The reference (kostastsa/BayesianFiltering, package `gaussfiltax`) is pure Python/JAX and has no
+ * FFI of its own; the boundary these entry points replace is the body of its two filter functions:
+ *
+ *   bf_pf_*   <->  gaussfiltax/inference.py:1302-1380  bootstrap_particle_filter (lax.scan of _step,
+ *                  :1330-1366) + gaussfiltax/utils.py:207-214 _resample + models.py:82-84
+ *   bf_gsf_*  <->  gaussfiltax/inference.py:303-377   gaussian_sum_filter (lax.scan of _step, :333-365)
+ *                  + _condition_on :72-105, _predict :51-70, utils.py:256-259 psd_solve
+ *   bf_resample / bf_cumsum  <->  jax.random.choice(p=w) as called at utils.py:210
+ *                  (cumsum in lax.associative_scan order, fixed-bisection searchsorted)
+ *
+ * Plain pointers and sizes only.  Unless an entry point's name ends in `_host`, every data pointer is
+ * a DEVICE pointer owned by the caller, all work is enqueued on the caller's stream, and nothing
+ * synchronises the device.  `*_host` variants take HOST pointers, do the H2D/D2H copies themselves and
+ * return after the stream has drained.  All entry points return 0 or a negative bf_status; the message
+ * of the last failure on the calling thread is bf_last_error().
+ *
+ * Python callables cannot run inside a kernel, so models come from a compiled registry
+ * (bf_model_id); the arrays of the reference's ParamsNLSSM / ParamsBPF travel in bf_model_desc.
+ */
+#ifndef BFILT_H
+#define BFILT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_ABI_VERSION 1
+
+typedef enum bf_status {
+  BF_OK = 0, BF_EINVAL = -1, BF_ECUDA = -2, BF_ENOMODEL = -3, BF_ENOMEM = -4, BF_ECOMM = -5
+} bf_status;
+
+/* compiled model registry; theta layouts are documented in csrc/models.cuh and oracle/models.py */
+typedef enum bf_model_id {
+  BF_MODEL_UNGM = 1,  /* dx=dq=dy=1           theta = a b c d e                       */
+  BF_MODEL_BOT = 2,   /* dx=4 dq=2 dy=1|2     theta = dt acc omega_scale              */
+  BF_MODEL_L63 = 3,   /* dx=dq=3 dy=1         theta = sigma rho beta dt c             */
+  BF_MODEL_L96 = 4,   /* dx=dq=d dy=d/2       theta = F dt c1 c2                      */
+  BF_MODEL_LG = 5,    /* dx=dq<=8 dy=dr<=8    theta = A[dx*dx] H[dy*dx] (row-major)   */
+  BF_MODEL_SIN1D = 6  /* dx=dq<=3 dy=1        theta = w c                             */
+} bf_model_id;
+
+typedef enum bf_resampler { BF_RESAMPLE_MULTINOMIAL = 0, BF_RESAMPLE_SYSTEMATIC = 1 } bf_resampler;
+typedef enum bf_pf_path { BF_PATH_AUTO = 0, BF_PATH_RESIDENT = 1, BF_PATH_STREAMED = 2 } bf_pf_path;
+
+/* The array fields of ParamsNLSSM / ParamsBPF (gaussfiltax/models.py:26-84).  HOST pointers, fp32,
+ * row-major, copied at create time. */
+typedef struct bf_model_desc {
+  int32_t model_id;
+  int32_t dx, dq, dy, dr;
+  int32_t n_theta;
+  const float* theta;
+  const float* q0;   /* [dq]     dynamics_noise_bias        */
+  const float* Q;    /* [dq,dq]  dynamics_noise_covariance  */
+  const float* r0;   /* [dr]     emission_noise_bias        */
+  const float* R;    /* [dr,dr]  emission_noise_covariance  */
+  const float* m0;   /* [dx]     initial_mean               */
+  const float* P0;   /* [dx,dx]  initial_covariance         */
+} bf_model_desc;
+
+/* ---------------------------------------------------------------- bootstrap particle filter */
+typedef struct bf_pf_s* bf_pf_handle;
+
+typedef struct bf_pf_config {
+  int64_t num_particles;     /* N per trial (per rank when world > 1)                          */
+  int32_t num_trials;        /* B independent filters                                          */
+  float ess_threshold;       /* resample when 1/sum(w^2) < ess_threshold*N  (inference.py:1356) */
+  int32_t resampler;         /* bf_resampler                                                   */
+  int32_t path;              /* bf_pf_path: RESIDENT = one CTA per trial, state in shared memory;
+                                STREAMED = multi-kernel pipeline over HBM                      */
+  uint64_t seed;             /* Philox key for every random input that is not supplied          */
+  int32_t device;            /* CUDA device ordinal                                             */
+  int32_t reserved;
+} bf_pf_config;
+
+typedef struct bf_pf_io {
+  int32_t T;                    /* steps in this call                                               */
+  int32_t t_offset;             /* global index of the first step (Philox counters, chunked runs)   */
+  int32_t resume;               /* 0: start from init_* ; 1: continue from the handle's carry        */
+  int32_t emissions_per_trial;  /* 0: emissions is [T,dy] shared by all trials ; 1: [B,T,dy]         */
+  const float* emissions;
+  const float* inputs;          /* [T] or NULL (zeros, inference.py:23)                              */
+  const float* init_particles;  /* [B,N,dx] or NULL (drawn from N(m0,P0) with Philox)                */
+  const float* init_weights;    /* [B,N] or NULL (1/N, inference.py:1371)                            */
+  const float* noise;           /* [T,B,N,dq] coloured process noise q0+L_Q z, or NULL (Philox)      */
+  const float* resample_u;      /* multinomial [T,B,N], systematic [T,B]; or NULL (Philox)           */
+  /* outputs, each may be NULL.  Time-major; the Python layer returns [N,T,...] views. */
+  float* out_particles;         /* [B,T,N,dx] post-resample (inference.py:1359-1362)                */
+  float* out_weights;           /* [B,T,N]    post-resample                                          */
+  float* out_propagated;        /* [B,T,N,dx] pre-resample particles                                 */
+  float* out_norm_weights;      /* [B,T,N]    pre-resample normalised weights                        */
+  int32_t* out_ancestors;       /* [B,T,N]    identity on steps that did not resample                */
+  float* out_mean;              /* [B,T,dx]   sum_i w_i x_i before resampling                        */
+  float* out_loglik;            /* [B,T]      log p(y_t | y_1:t-1) estimate                          */
+  float* out_ess;               /* [B,T]                                                             */
+  int32_t* out_resampled;       /* [B,T]      1 if the step resampled                                */
+  float* final_particles;       /* [B,N,dx]   carry after the last step                              */
+  float* final_weights;         /* [B,N]                                                             */
+} bf_pf_io;
+
+int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg, bf_pf_handle* out);
+int bf_pf_run(bf_pf_handle h, const bf_pf_io* io, void* cuda_stream);
+int bf_pf_step(bf_pf_handle h, const bf_pf_io* io, void* cuda_stream); /* bf_pf_run with T forced to 1 */
+int bf_pf_run_host(bf_pf_handle h, const bf_pf_io* host_io);
+int bf_pf_kernel_launches(bf_pf_handle h, int64_t* out);   /* launches enqueued so far by this handle */
+int bf_pf_destroy(bf_pf_handle h);
+
+/* ---------------------------------------------------------------- Gaussian-sum (EKF) filter */
+typedef struct bf_gsf_s* bf_gsf_handle;
+
+typedef struct bf_gsf_config {
+  int32_t num_components;   /* M */
+  int32_t num_trials;       /* B */
+  int32_t device;
+  int32_t reserved;
+} bf_gsf_config;
+
+typedef struct bf_gsf_io {
+  int32_t T;
+  int32_t resume;               /* 0: start from init_* ; 1: continue from the handle's carry */
+  int32_t emissions_per_trial;  /* 0: [T,dy] shared ; 1: [B,T,dy] */
+  int32_t reserved;
+  const float* emissions;
+  const float* inputs;          /* [T] or NULL */
+  const float* init_means;      /* [B,M,dx]  (reference draws MVN(m0,P0), inference.py:367) */
+  const float* init_covs;       /* [B,M,dx,dx] or NULL (P0 replicated, inference.py:368)    */
+  const float* init_weights;    /* [B,M] or NULL (1/M, inference.py:369)                    */
+  /* outputs, each may be NULL; time-major, the Python layer returns [M,T,...] views */
+  float* out_weights;           /* [B,T,M]        */
+  float* out_means;             /* [B,T,M,dx]     */
+  float* out_covs;              /* [B,T,M,dx,dx]  */
+  float* out_pred_means;        /* [B,T,M,dx]     */
+  float* out_pred_covs;         /* [B,T,M,dx,dx]  */
+  float* out_loglik;            /* [B,T]          */
+  float* out_mix_mean;          /* [B,T,dx]  sum_m w_m mu_m (posterior mean of the mixture) */
+} bf_gsf_io;
+
+int bf_gsf_create(const bf_model_desc* model, const bf_gsf_config* cfg, bf_gsf_handle* out);
+int bf_gsf_run(bf_gsf_handle h, const bf_gsf_io* io, void* cuda_stream);
+int bf_gsf_run_host(bf_gsf_handle h, const bf_gsf_io* host_io);
+int bf_gsf_kernel_launches(bf_gsf_handle h, int64_t* out);
+int bf_gsf_destroy(bf_gsf_handle h);
+
+/* ---------------------------------------------------------------- stand-alone resampler pieces */
+/* cdf[i] = inclusive prefix sum of w in lax.associative_scan order; bit-exact vs oracle/scan.py. */
+int bf_cumsum(const float* w, float* cdf, int64_t n, void* cuda_stream);
+/* anc[i] for supplied uniforms: multinomial u[n], systematic u[1]; bit-exact vs oracle/scan.py. */
+int bf_resample(const float* w, const float* u, int32_t* anc, int64_t n, int32_t resampler, void* cuda_stream);
+
+/* ---------------------------------------------------------------- model evaluation + data generator */
+/* Evaluate a registry model on n states (DEVICE pointers).  what: 0 f(x,q,u) -> [n,dx] (aux = q [n,dq] or NULL=q0);
+ * 1 h(x,r,u) -> [n,dy] (aux = r [n,dr] or NULL=r0); 2 dF/dx [n,dx,dx]; 3 dF/dq [n,dx,dq]; 4 dH/dx [n,dy,dx];
+ * 5 emission log-prob of one y (aux = y [dy]) -> [n].  Replaces calling the Python f/h/jacfwd(f)
+ * (gaussfiltax/inference.py:327-329) on host arrays. */
+int bf_model_eval(const bf_model_desc* model, int32_t what, int64_t n, const float* x, const float* aux, float u,
+                  float* out, void* cuda_stream);
+/* NonlinearSSM.sample (gaussfiltax/models.py:240-289) for B independent trials (DEVICE pointers):
+ * states [B,T,dx], emissions [B,T,dy].  z0 [B,dx], q_noise [B,T,dq] (row t=0 unused), r_noise [B,T,dr]
+ * are already-coloured draws, or NULL to draw them with Philox(seed). */
+int bf_ssm_sample(const bf_model_desc* model, int32_t B, int32_t T, const float* inputs, uint64_t seed,
+                  const float* z0, const float* q_noise, const float* r_noise, float* states, float* emissions,
+                  void* cuda_stream);
+
+const char* bf_last_error(void);
+int bf_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFILT_H */

@@ -1,0 +1,69 @@
+"""CPU tier: the C-ABI library loads and exports every symbol include/bfilt.h declares; argument validation
+that needs no GPU behaves as the header says.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bayesianfiltering_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "bfilt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bf_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 17
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in bfilt.h but not exported by libbfilt.so"
+        assert name in bound, f"{name} declared in bfilt.h but not bound in _lib.SYMBOLS"
+    assert lib.bf_abi_version() == 1
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "bfilt.h")).read()
+    assert "torch" not in src.lower() and "at::" not in src and "#include <cuda" not in src
+
+
+def _desc(**kw):
+    from bayesianfiltering_b200 import zoo
+    return zoo.ungm().host_model(**kw)
+
+
+def test_create_rejects_bad_arguments_without_touching_the_gpu():
+    lib = _lib.load()
+    hm = _desc()
+    h = C.c_void_p()
+    cfg = _lib.PfConfig(0, 1, 0.5, 0, 0, 0, 0, 0)                 # N = 0
+    assert lib.bf_pf_create(C.byref(hm.desc), C.byref(cfg), C.byref(h)) == _lib.BF_EINVAL
+    assert b"num_particles" in lib.bf_last_error()
+    cfg = _lib.PfConfig(100, 1, 0.5, 7, 0, 0, 0, 0)               # unknown resampler
+    assert lib.bf_pf_create(C.byref(hm.desc), C.byref(cfg), C.byref(h)) == _lib.BF_EINVAL
+    bad = _lib.HostModel(99, 1, 1, 1, 1, [0.0], [0], [[1]], [0], [[1]], [0], [[1]])
+    cfg = _lib.PfConfig(100, 1, 0.5, 0, 0, 0, 0, 0)
+    assert lib.bf_pf_create(C.byref(bad.desc), C.byref(cfg), C.byref(h)) == _lib.BF_ENOMODEL
+    gcfg = _lib.GsfConfig(5000, 1, 0, 0)                          # M > 1024
+    assert lib.bf_gsf_create(C.byref(hm.desc), C.byref(gcfg), C.byref(h)) == _lib.BF_EINVAL
+    with pytest.raises(ValueError):
+        _lib.check(_lib.BF_EINVAL)
+
+
+def test_wrong_theta_length_is_rejected():
+    lib = _lib.load()
+    bad = _lib.HostModel(_lib.MODEL_UNGM, 1, 1, 1, 1, [0.5, 25.0], [0], [[1]], [0], [[1]], [0], [[1]])
+    h = C.c_void_p()
+    cfg = _lib.PfConfig(100, 1, 0.5, 0, 0, 0, 0, 0)
+    assert lib.bf_pf_create(C.byref(bad.desc), C.byref(cfg), C.byref(h)) == _lib.BF_EINVAL

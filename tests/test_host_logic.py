@@ -1,0 +1,80 @@
+"""CPU tier: host-side mirror of the reference's call surface (no GPU, no kernels)."""
+import inspect
+
+import numpy as np
+import pytest
+
+from bayesianfiltering_b200 import containers, inference, models, zoo
+from bayesianfiltering_b200.random import PRNGKey, key_to_seed, split
+
+
+def test_param_containers_have_the_reference_fields():
+    # gaussfiltax/models.py:43-50 and :73-80
+    base = ("initial_mean", "initial_covariance", "dynamics_function", "dynamics_noise_bias",
+            "dynamics_noise_covariance", "emission_function", "emission_noise_bias", "emission_noise_covariance")
+    assert models.ParamsNLSSM._fields == base
+    assert models.ParamsBPF._fields == base + ("emission_distribution_log_prob",)
+    assert hasattr(models.ParamsBPF, "sample_dynamics_distribution")
+    # inference.py:35-39
+    assert inference.PosteriorGaussianSumFiltered._fields == ("weights", "means", "covariances", "predicted_means",
+                                                              "predicted_covariances")
+    assert containers.GaussianComponent._fields == ("mean", "covariance", "weight")
+    assert containers.GaussianSum._fields == ("means", "covariances", "weights")
+
+
+def test_entry_point_signatures_match_the_reference():
+    # inference.py:1302-1309
+    p = list(inspect.signature(inference.bootstrap_particle_filter).parameters.values())
+    assert [q.name for q in p[:6]] == ["params", "emissions", "num_particles", "key", "inputs", "ess_threshold"]
+    assert p[5].default == 0.5 and p[4].default is None
+    assert all(q.kind is inspect.Parameter.KEYWORD_ONLY for q in p[6:])
+    # inference.py:303-309
+    g = list(inspect.signature(inference.gaussian_sum_filter).parameters.values())
+    assert [q.name for q in g[:5]] == ["params", "emissions", "num_components", "num_iter", "inputs"]
+    assert g[2].default == 1 and g[3].default == 1 and g[4].default is None
+    assert all(q.kind is inspect.Parameter.KEYWORD_ONLY for q in g[5:])
+    s = inspect.signature(models.NonlinearSSM.__init__)
+    assert list(s.parameters)[1:6] == ["state_dim", "state_noise_dim", "emission_dim", "emission_noise_dim", "input_dim"]
+
+
+def test_untagged_callables_raise_no_fallback():
+    f = lambda x, q, u: x + q
+    p = models.ParamsNLSSM(np.zeros(1), np.eye(1), f, np.zeros(1), np.eye(1), f, np.zeros(1), np.eye(1))
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        inference.gaussian_sum_filter(p, np.zeros((3, 1), np.float32), 2)
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        inference.bootstrap_particle_filter(p, np.zeros((3, 1), np.float32), 10)
+
+
+def test_mixed_registry_models_raise():
+    a, b = zoo.ungm(), zoo.ungm()
+    p = models.ParamsNLSSM(np.zeros(1), np.eye(1), a.dynamics_function, np.zeros(1), np.eye(1), b.emission_function,
+                           np.zeros(1), np.eye(1))
+    with pytest.raises(ValueError):
+        zoo.resolve(p)
+
+
+def test_host_model_arrays_and_shape_checks():
+    m = zoo.bot(emission_dim=2)
+    hm = m.host_model(Q=1e-5 * np.eye(2), R=25e-6 * np.eye(2), m0=[-0.05, 0.001, 0.7, -0.05], P0=np.diag([0.1, 0.005, 0.1, 0.01]))
+    assert (hm.dx, hm.dq, hm.dy, hm.dr) == (4, 2, 2, 2) and hm.desc.n_theta == 3
+    with pytest.raises(ValueError):
+        m.host_model(Q=np.eye(3))
+    with pytest.raises(ValueError):
+        zoo.bot(emission_dim=3)
+
+
+def test_keys():
+    k = PRNGKey(7)
+    assert k.dtype == np.uint32 and k.shape == (2,) and key_to_seed(k) == 7
+    s = split(k, 3)
+    assert s.shape == (3, 2) and len({key_to_seed(x) for x in s}) == 3
+    assert key_to_seed(None) == 0 and key_to_seed(5) == 5
+
+
+def test_time_varying_params_are_rejected_loudly():
+    m = zoo.ungm()
+    p = models.ParamsNLSSM(np.zeros(1), np.eye(1), m.dynamics_function, np.zeros(1), np.ones((5, 1, 1)),
+                           m.emission_function, np.zeros(1), np.eye(1))
+    with pytest.raises(NotImplementedError):
+        zoo.host_model_from_params(p)

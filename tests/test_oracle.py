@@ -1,0 +1,125 @@
+"""CPU tier: the oracle against independent known answers (the reference ships no golden vectors --
+SURVEY.md section 4 -- so these pins are ours) and against the committed fixtures in tests/golden/."""
+import os
+
+import numpy as np
+import pytest
+import scipy.stats
+
+from oracle import gsf as ogsf, models as om, pf as opf, scan as oscan
+from tests.parity_cases import ALL_CASES, case
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 31, 33, 100, 1000, 1024, 4097])
+def test_cumsum_recursive_equals_closed_form(n):
+    rng = np.random.default_rng(n)
+    x = rng.random(n).astype(np.float32)
+    x /= x.sum(dtype=np.float32)
+    a = oscan.cumsum_associative(x)
+    assert np.array_equal(a, oscan.cumsum_closed_form(x))
+    np.testing.assert_allclose(a, np.cumsum(x.astype(np.float64)), rtol=0, atol=4e-7)
+
+
+def test_cumsum_differs_from_sequential_in_last_bits():
+    rng = np.random.default_rng(0)
+    x = rng.random(4097).astype(np.float32); x /= x.sum(dtype=np.float32)
+    assert not np.array_equal(oscan.cumsum_associative(x), np.cumsum(x))   # the order matters: that is the point
+
+
+def test_bisect_equals_numpy_on_sorted():
+    rng = np.random.default_rng(1)
+    for n in [1, 2, 5, 64, 1000, 4097]:
+        c = np.sort(rng.random(n).astype(np.float32))
+        r = np.concatenate([rng.random(3000).astype(np.float32), c[: min(n, 50)], [0.0, 1.0]]).astype(np.float32)
+        assert np.array_equal(oscan.searchsorted_bisect(c, r), np.searchsorted(c, r, "left"))
+
+
+def test_resample_invariants():
+    rng = np.random.default_rng(2)
+    n = 3000
+    w = rng.random(n).astype(np.float32) ** 4
+    w[::7] = 0.0
+    w /= w.sum(dtype=np.float32)
+    a = oscan.resample_ancestors(w, rng.random(n, dtype=np.float32), "multinomial")
+    assert a.min() >= 0 and a.max() < n
+    assert not np.any(w[a] == 0.0)                      # zero-weight particles are never selected (side='left')
+    s = oscan.resample_ancestors(w, np.float32(0.37), "systematic")
+    assert np.all(np.diff(s) >= 0)                      # sorted positions -> monotone ancestors
+    counts = np.bincount(s, minlength=n)
+    assert counts.sum() == n and np.all(np.abs(counts - n * w.astype(np.float64)) < 1.0 + 1e-3 * n * w)
+
+
+def test_mvn_log_prob_against_scipy():
+    rng = np.random.default_rng(3)
+    for k in (1, 2, 5):
+        A = rng.normal(size=(k, k)); cov = A @ A.T + k * np.eye(k)
+        loc = rng.normal(size=(7, k)); y = rng.normal(size=k)
+        ref = np.array([scipy.stats.multivariate_normal(l, cov).logpdf(y) for l in loc])
+        np.testing.assert_allclose(om.mvn_log_prob(loc, cov, y), ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_jacobians_against_finite_differences(name):
+    c = case(name)
+    m = c.omodel
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(6, m.dx)) + 0.5
+    q = np.zeros((6, m.dq)); r = np.zeros((6, m.dr))
+    for u in (0.0, 1.0, 2.0, 0.3):
+        np.testing.assert_allclose(m.Fx(x, q, u), om.numerical_jacobian(lambda z: m.f(z, q, u), x), rtol=2e-6, atol=2e-7)
+        np.testing.assert_allclose(m.Hx(x, r, u), om.numerical_jacobian(lambda z: m.h(z, r, u), x), rtol=2e-6, atol=2e-7)
+        np.testing.assert_allclose(m.Fq(x, q, u), om.numerical_jacobian(lambda z: m.f(x, z, u), q), rtol=2e-6, atol=2e-7)
+
+
+def test_gsf_single_component_is_the_kalman_filter():
+    """Linear-Gaussian model: gaussian_sum_filter(M=1) == closed-form KF up to the reference's psd_solve
+    jitter (utils.py:258 adds 1e-6 to every element of S)."""
+    c = case("lg42")
+    T = 60
+    _, ys = c.simulate(T, 5)
+    km, kP, kll = ogsf.kalman_filter_exact(c.omodel.A, c.omodel.H, c.Q, c.R, c.m0, c.P0, ys)
+    o = ogsf.gaussian_sum_filter(c.omodel, ys.astype(np.float64), None, c.m0[None].astype(np.float64), c.P0, c.Q, c.q0, c.R, c.r0)
+    np.testing.assert_allclose(o["means"][0], km, rtol=0, atol=5e-5)
+    np.testing.assert_allclose(o["covariances"][0], kP, rtol=0, atol=5e-5)
+    np.testing.assert_allclose(o["loglik_inc"], kll, rtol=0, atol=5e-5)
+    assert abs(o["weights"] - 1.0).max() == 0.0
+
+
+def test_pf_loglik_converges_to_kalman():
+    """Config 5 in miniature: BPF marginal log-likelihood -> exact KF log-likelihood as N grows."""
+    c = case("lg3")
+    T = 25
+    _, ys = c.simulate(T, 6)
+    _, _, kll = ogsf.kalman_filter_exact(c.omodel.A, c.omodel.H, c.Q, c.R, c.m0, c.P0, ys)
+    errs = []
+    for N in (200, 20000):
+        x0, noise, ru = c.pf_randomness(T, N, 7)
+        o = opf.bootstrap_particle_filter(c.omodel, ys, None, x0, noise, ru, c.r0, c.R, 0.5, keep_trajectory=False)
+        errs.append(abs(o["marginal_loglik"] - kll.sum()))
+    assert errs[1] < 0.5 and errs[1] < errs[0] + 0.2
+
+
+def test_pf_outputs_shapes_and_invariants():
+    c = case("ungm")
+    T, N = 12, 300
+    _, ys = c.simulate(T, 8)
+    x0, noise, ru = c.pf_randomness(T, N, 9)
+    o = opf.bootstrap_particle_filter(c.omodel, ys, c.inputs(T), x0, noise, ru, c.r0, c.R, 0.5)
+    assert o["weights"].shape == (N, T) and o["particles"].shape == (N, T, 1)       # inference.py:1378
+    np.testing.assert_allclose(o["weights"].sum(axis=0), 1.0, atol=1e-5)
+    assert o["resampled"].sum() > 0
+
+
+@pytest.mark.parametrize("fname", sorted(f for f in os.listdir(GOLD) if f.endswith(".npz")) if os.path.isdir(GOLD) else [])
+def test_oracle_reproduces_committed_golden(fname):
+    """tests/golden/*.npz were written by tests/golden/make_golden.py from this oracle; they freeze it."""
+    from tests.golden.make_golden import regenerate
+    g = np.load(os.path.join(GOLD, fname))
+    fresh = regenerate(fname[:-4])
+    for k in g.files:
+        if g[k].dtype.kind == "f":
+            np.testing.assert_allclose(fresh[k], g[k], rtol=1e-6, atol=1e-7, err_msg=f"{fname}:{k}")
+        else:
+            assert np.array_equal(fresh[k], g[k]), f"{fname}:{k}"
