@@ -1,0 +1,293 @@
+"""GPU tier: bootstrap particle filter (bf_pf_* through the C ABI) against the oracle's restatement of
+gaussfiltax/inference.py:1302-1380.
+
+Contract (BASELINE.json north_star): ancestor indices BIT-EXACT given identical normalised weights and the
+same uniforms; particles / weights / log-likelihood within relative 1e-5 (fp32) at the scale of the field.
+The maps are nonlinear (UNGM's slope reaches 25), so one-ulp differences between CUDA's fused multiply-adds
+and NumPy grow along a trajectory; the 1e-5 bar is therefore checked per step with the kernel's own previous
+state as the oracle's input (`_stepwise`), and whole trajectories are compared at 1e-5 on the models that do
+not amplify rounding (linear-Gaussian) and at a looser, stated tolerance elsewhere.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gsf as ogsf, pf as opf, scan as oscan
+from tests.parity_cases import case, close, close_cond
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ALL_OUT = ("weights", "particles", "propagated", "norm_weights", "ancestors", "means", "log_likelihood", "ess",
+           "resampled", "final_particles", "final_weights")
+
+
+def _engine(c, N, B=1, thr=0.5, res="multinomial", path="auto", seed=0):
+    from bayesianfiltering_b200.engine import ParticleFilterEngine
+    return ParticleFilterEngine(c.host_model(), N, B, thr, res, path, seed, 0)
+
+
+def _stepwise(c, out, ys, u, x0, noise, ru, thr, res, b=0, B=1):
+    """Every step of the kernel's trajectory re-derived by the oracle from the kernel's previous state."""
+    T = ys.shape[0]
+    N = x0.shape[0]
+    x, w = x0, np.full(N, np.float32(1.0) / np.float32(N), np.float32)
+    n_res = 0
+    for t in range(T):
+        ut = 0.0 if u is None else u[t]
+        o = opf.pf_step(c.omodel, x, w, ys[t], ut, noise[t], ru[t], c.r0, c.R, thr, res)
+        f8 = lambda v: np.asarray(v, dtype=np.float64)
+        o8 = opf.pf_step(c.omodel, f8(x), f8(w), f8(ys[t]), ut, f8(noise[t]), ru[t], c.r0, c.R, thr, res)
+        close(out["propagated"][b, t], o["propagated"], what=f"propagated t={t}")
+        # normalised weights and the by-products, from the kernel's own previous state
+        close_cond(out["norm_weights"][b, t], o["norm_weights"], o8["norm_weights"], what=f"norm_weights t={t}")
+        # the increment is max + log(sum): its rounding is set by the size of the per-particle log-likelihoods
+        ll_scale = max(1.0, abs(float(np.max(o["lls"]))), abs(float(o["loglik_inc"])))
+        ll_tol = 1e-5 * ll_scale + 8 * abs(float(o["loglik_inc"]) - float(o8["loglik_inc"]))
+        assert abs(float(out["log_likelihood"][b, t]) - float(o["loglik_inc"])) <= ll_tol, f"loglik t={t}"
+        close_cond(out["ess"][b, t], o["ess"], o8["ess"], rtol=2e-5, what=f"ess t={t}")
+        close_cond(out["means"][b, t], o["mean"], o8["mean"], rtol=2e-5, what=f"mean t={t}")
+        flag = bool(out["resampled"][b, t])
+        margin = abs(float(o["ess"]) - thr * N) / (thr * N)
+        if margin > 1e-4:
+            assert flag == o["resampled"], f"resample decision differs at t={t}"
+        if flag:
+            n_res += 1
+            # BIT-EXACT ancestors given the kernel's own normalised weights and the supplied uniforms
+            anc = oscan.resample_ancestors(out["norm_weights"][b, t], ru[t], res)
+            assert np.array_equal(out["ancestors"][b, t], anc), f"ancestors differ at t={t}"
+            assert np.array_equal(out["particles"][b, t], out["propagated"][b, t][anc]), f"gather differs at t={t}"
+            assert np.all(out["weights"][b, t] == np.float32(1.0) / np.float32(N))
+        else:
+            assert np.array_equal(out["ancestors"][b, t], np.arange(N))
+            assert np.array_equal(out["particles"][b, t], out["propagated"][b, t])
+            assert np.array_equal(out["weights"][b, t], out["norm_weights"][b, t])
+        x, w = out["particles"][b, t], out["weights"][b, t]
+    assert np.array_equal(out["final_particles"][b], x) and np.array_equal(out["final_weights"][b], w)
+    return n_res
+
+
+@pytest.mark.parametrize("path", ["resident", "streamed"])
+@pytest.mark.parametrize("name,T,N,thr,res", [
+    ("ungm", 40, 1000, 0.5, "multinomial"),        # BASELINE config 1 shape (N=1000), multinomial = the reference
+    ("ungm", 30, 777, 0.5, "systematic"),          # north_star's systematic grid, ragged N
+    ("bot2", 30, 1500, 1.0, "multinomial"),        # BOT_Experiment_script.py:151: resample every step
+    ("bot1", 20, 600, 0.5, "systematic"),
+    ("l63", 25, 900, 0.5, "multinomial"),
+    ("lg3", 25, 640, 0.5, "multinomial"),
+    ("lg8", 20, 512, 0.7, "multinomial"),          # config 5 model
+    ("lg42", 20, 500, 0.5, "systematic"),
+    ("sin1d", 25, 1000, 0.5, "multinomial"),
+    ("sin3d", 20, 300, 0.5, "multinomial"),
+])
+def test_pf_stepwise_parity(name, T, N, thr, res, path):
+    c = case(name)
+    _, ys = c.simulate(T, 7)
+    u = c.inputs(T)
+    x0, noise, ru = c.pf_randomness(T, N, 8, res)
+    eng = _engine(c, N, 1, thr, res, path)
+    out = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=ALL_OUT)
+    n_res = _stepwise(c, out, ys, u, x0, noise, ru, thr, res)
+    assert n_res > 0, "case never resampled: it does not exercise the scan/search/gather"
+    eng.close()
+
+
+@pytest.mark.parametrize("path", ["resident", "streamed"])
+@pytest.mark.parametrize("gold", ["pf_ungm", "pf_bot2", "pf_ungm_sys", "pf_lg3"])
+def test_pf_golden_fixtures(gold, path):
+    """Whole trajectories against the committed oracle outputs (tests/golden/make_golden.py)."""
+    from tests.golden.make_golden import PF_CASES
+    cname, T, N, thr, res = PF_CASES[gold]
+    g = np.load(os.path.join(GOLD, gold + ".npz"))
+    c = case(cname)
+    u = g["inputs"] if "inputs" in g.files else None
+    eng = _engine(c, N, 1, thr, res, path)
+    out = eng.run_host(g["emissions"], inputs=u, init_particles=g["x0"], noise=g["noise"], resample_u=g["res_u"],
+                       outputs=ALL_OUT)
+    eng.close()
+    assert np.array_equal(out["resampled"][0], g["resampled"])
+    # linear-Gaussian: no error growth -> the north_star tolerance on the whole trajectory
+    tol = 1e-5 if cname.startswith("lg") else 2e-3
+    close(out["log_likelihood"][0], g["loglik_inc"], rtol=tol, atol_scale=tol, what="loglik")
+    close(out["ess"][0], g["ess"], rtol=10 * tol, atol_scale=10 * tol, what="ess")
+    close(out["means"][0], g["means"], rtol=10 * tol, atol_scale=10 * tol, what="means")
+    # reference axis order: weights [N,T], particles [N,T,dx]  (inference.py:1378)
+    W = np.swapaxes(out["weights"][0], 0, 1)
+    X = np.swapaxes(out["particles"][0], 0, 1)
+    bad = ~np.isclose(X, g["particles"], rtol=tol, atol=tol * np.abs(g["particles"]).max())
+    assert bad.mean() < (0.0 if cname.startswith("lg") else 0.01) + 1e-12, f"{bad.mean():.4f} of particle entries differ"
+    badw = ~np.isclose(W, g["weights"], rtol=10 * tol, atol=10 * tol * np.abs(g["weights"]).max())
+    assert badw.mean() < (0.0 if cname.startswith("lg") else 0.01) + 1e-12
+
+
+def test_reference_entry_point_shapes_and_axis_order():
+    """bootstrap_particle_filter(params, emissions, num_particles, key, inputs, ess_threshold) returns the
+    reference's dict: weights [N,T], particles [N,T,dx] (inference.py:1359-1362, 1378)."""
+    from bayesianfiltering_b200 import inference as gf
+    from bayesianfiltering_b200.random import PRNGKey
+    c = case("bot2")
+    T, N = 12, 300
+    _, ys = c.simulate(T, 1)
+    u = c.inputs(T)
+    x0, noise, ru = c.pf_randomness(T, N, 2)
+    post = gf.bootstrap_particle_filter(c.params_bpf(), ys, N, PRNGKey(0), u, 1.0, noise=noise, resample_uniforms=ru,
+                                        init_particles=x0)
+    assert set(post) == {"weights", "particles"}
+    assert post["weights"].shape == (N, T) and post["particles"].shape == (N, T, 4)
+    ref = opf.bootstrap_particle_filter(c.omodel, ys, u, x0, noise, ru, c.r0, c.R, 1.0)
+    # point estimate as the driver computes it (BOT_Experiment_script.py:152)
+    est = np.einsum("ijk,ij->jk", post["particles"], post["weights"])
+    est_ref = np.einsum("ijk,ij->jk", ref["particles"], ref["weights"])
+    close(est, est_ref, rtol=1e-3, atol_scale=1e-3)
+    # Philox mode (no supplied randomness): same key -> same result, different key -> different
+    a = gf.bootstrap_particle_filter(c.params_bpf(), ys, N, PRNGKey(3), u, 1.0)
+    b = gf.bootstrap_particle_filter(c.params_bpf(), ys, N, PRNGKey(3), u, 1.0)
+    d = gf.bootstrap_particle_filter(c.params_bpf(), ys, N, PRNGKey(4), u, 1.0)
+    assert np.array_equal(a["particles"], b["particles"]) and not np.array_equal(a["particles"], d["particles"])
+    np.testing.assert_allclose(a["weights"].sum(axis=0), 1.0, rtol=1e-5)
+
+
+@pytest.mark.parametrize("path", ["resident", "streamed"])
+def test_resident_and_streamed_agree_and_chunked_resume_is_exact(path):
+    """The carry (weights, particles) is an explicit state: a run split in time equals the unsplit run bit for
+    bit (SURVEY section 5 checkpoint/resume)."""
+    c = case("lg42")
+    T, N = 24, 700
+    _, ys = c.simulate(T, 3)
+    x0, noise, ru = c.pf_randomness(T, N, 4)
+    outs = ("weights", "particles", "log_likelihood", "ancestors")
+    e1 = _engine(c, N, 1, 0.6, "multinomial", path)
+    full = e1.run_host(ys, init_particles=x0, noise=noise, resample_u=ru, outputs=outs)
+    e1.close()
+    e2 = _engine(c, N, 1, 0.6, "multinomial", path)
+    k = 9
+    a = e2.run_host(ys[:k], init_particles=x0, noise=noise[:k], resample_u=ru[:k], outputs=outs)
+    b = e2.run_host(ys[k:], noise=noise[k:], resample_u=ru[k:], outputs=outs, t_offset=k, resume=True)
+    e2.close()
+    for name in outs:
+        assert np.array_equal(np.concatenate([a[name], b[name]], axis=1), full[name]), name
+    other = _engine(c, N, 1, 0.6, "multinomial", "streamed" if path == "resident" else "resident")
+    o = other.run_host(ys, init_particles=x0, noise=noise, resample_u=ru, outputs=outs)
+    other.close()
+    assert np.array_equal(o["ancestors"], full["ancestors"])
+    close(o["particles"], full["particles"])
+    close(o["log_likelihood"], full["log_likelihood"])
+
+
+@pytest.mark.parametrize("path", ["resident", "streamed"])
+def test_trial_batch_equals_loop_over_trials(path):
+    """num_trials=B is the reference drivers' `for i in range(Nsim)` loop (BOT_Experiment_script.py:89)."""
+    c = case("ungm")
+    T, N, B = 15, 400, 3
+    ys = np.stack([c.simulate(T, 10 + b)[1] for b in range(B)])
+    u = c.inputs(T)
+    rnd = [c.pf_randomness(T, N, 20 + b) for b in range(B)]
+    x0 = np.stack([r[0] for r in rnd]); noise = np.stack([r[1] for r in rnd], axis=1); ru = np.stack([r[2] for r in rnd], axis=1)
+    eng = _engine(c, N, B, 0.5, "multinomial", path)
+    out = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=ALL_OUT)
+    eng.close()
+    for b in range(B):
+        one = _engine(c, N, 1, 0.5, "multinomial", path)
+        o = one.run_host(ys[b], inputs=u, init_particles=x0[b], noise=noise[:, b], resample_u=ru[:, b], outputs=ALL_OUT)
+        one.close()
+        for k in ALL_OUT:
+            assert np.array_equal(o[k][0], out[k][b]), (k, b)
+    _stepwise(c, out, ys[1], u, x0[1], noise[:, 1], ru[:, 1], 0.5, "multinomial", b=1, B=B)
+
+
+def test_device_tensor_mode_matches_host_mode():
+    import torch
+    c = case("bot2")
+    T, N = 10, 5000
+    _, ys = c.simulate(T, 5)
+    u = c.inputs(T)
+    x0, noise, ru = c.pf_randomness(T, N, 6)
+    eng = _engine(c, N, 1, 1.0, "multinomial", "streamed")
+    host = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=("particles", "ancestors"))
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dev = eng.run(cu(ys), inputs=cu(u), init_particles=cu(x0[None]), noise=cu(noise[:, None]), resample_u=cu(ru[:, None]),
+                  outputs=("particles", "ancestors"))
+    torch.cuda.synchronize()
+    assert eng.launches() > 0
+    for k in host:
+        assert np.array_equal(dev[k].cpu().numpy(), host[k]), k
+    eng.close()
+
+
+@pytest.mark.parametrize("N", [1, 2, 33])
+def test_tiny_particle_counts(N):
+    c = case("ungm")
+    T = 6
+    _, ys = c.simulate(T, 1)
+    u = c.inputs(T)
+    x0, noise, ru = c.pf_randomness(T, N, 2)
+    for path in ("resident", "streamed"):
+        eng = _engine(c, N, 1, 1.1, "multinomial", path)       # thr > 1: resample at every step
+        out = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=ALL_OUT)
+        _stepwise(c, out, ys, u, x0, noise, ru, 1.1, "multinomial")
+        eng.close()
+
+
+def test_errors_are_loud():
+    from bayesianfiltering_b200.engine import ParticleFilterEngine
+    c = case("ungm")
+    with pytest.raises(ValueError):
+        ParticleFilterEngine(c.host_model(), 0, 1)
+    with pytest.raises(ValueError):
+        ParticleFilterEngine(c.host_model(), 1 << 20, 1, path="resident")       # does not fit shared memory
+    eng = _engine(c, 64)
+    with pytest.raises(ValueError):
+        eng.run_host(np.zeros((4, 1), np.float32), resume=True)                 # no carry yet
+    with pytest.raises(ValueError):
+        eng.run_host(np.zeros((4, 1), np.float32), noise=np.zeros((3, 64, 1), np.float32))
+    eng.close()
+
+
+def test_philox_pf_loglik_converges_to_exact_kalman():
+    """BASELINE config 5: BPF on a linear-Gaussian SSM (d=8) against the exact Kalman-filter log-likelihood.
+    The PF estimate of log Z is consistent; its spread shrinks as N grows."""
+    c = case("lg8")
+    T = 30
+    _, ys = c.simulate(T, 9)
+    A, H = c.omodel.A, c.omodel.H
+    _, _, ll = ogsf.kalman_filter_exact(A, H, c.Q, c.R, c.m0, c.P0, ys)
+    exact = ll.sum()
+    errs = {}
+    for N, path in ((1 << 10, "resident"), (1 << 14, "streamed"), (1 << 18, "streamed")):
+        vals = []
+        for seed in range(3):
+            eng = _engine(c, N, 1, 0.5, "systematic", path, seed=100 + seed)
+            out = eng.run_host(ys, outputs=("log_likelihood",))
+            vals.append(out["log_likelihood"][0].astype(np.float64).sum())
+            eng.close()
+        errs[N] = np.mean(np.abs(np.array(vals) - exact))
+    # d=8, T=30: the estimator's spread is O(1) at N=2^18 and shrinks like N^-1/2
+    assert errs[1 << 18] < 1.5, errs
+    assert errs[1 << 18] < errs[1 << 14] < errs[1 << 10], errs
+
+
+def test_large_streamed_properties_2pow22():
+    """Size-independent properties at a large N (the oracle is too slow for whole trajectories there):
+    weights sum to one, ancestors in range and non-decreasing for systematic positions, every gathered particle is
+    a propagated one, the log-likelihood of a batch equals the sum of its two halves' runs (chunked resume)."""
+    c = case("bot2")
+    T, N = 4, 1 << 22
+    _, ys = c.simulate(T, 2)
+    u = c.inputs(T)
+    ru = np.random.default_rng(3).random(T, dtype=np.float32)
+    eng = _engine(c, N, 1, 1.0, "systematic", "streamed", seed=5)
+    out = eng.run_host(ys, inputs=u, resample_u=ru,
+                       outputs=("norm_weights", "ancestors", "particles", "propagated", "log_likelihood", "ess"))
+    eng.close()
+    for t in range(T):
+        w = out["norm_weights"][0, t].astype(np.float64)
+        assert abs(w.sum() - 1.0) < 1e-4
+        a = out["ancestors"][0, t]
+        assert a.min() >= 0 and a.max() < N
+        assert np.all(np.diff(a) >= -1)            # monotone up to last-bit cdf wiggles
+        assert np.array_equal(out["particles"][0, t], out["propagated"][0, t][a])
+        close(out["ess"][0, t], 1.0 / np.sum(w * w), rtol=1e-4, atol_scale=1e-4)
+    # full-size steps against the oracle (vectorised NumPy, seconds): bit-exact ancestors
+    for t in (0, T - 1):
+        anc = oscan.resample_ancestors(out["norm_weights"][0, t], ru[t], "systematic")
+        assert np.array_equal(out["ancestors"][0, t], anc)
