@@ -58,6 +58,7 @@ SYMBOLS = [
     ("bf_pf_step", C.c_int, [C.c_void_p, C.POINTER(PfIO), C.c_void_p]),
     ("bf_pf_run_host", C.c_int, [C.c_void_p, C.POINTER(PfIO)]),
     ("bf_pf_kernel_launches", C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    ("bf_pf_phase_times", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),
     ("bf_pf_destroy", C.c_int, [C.c_void_p]),
     ("bf_gsf_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(GsfConfig), C.POINTER(C.c_void_p)]),
     ("bf_gsf_run", C.c_int, [C.c_void_p, C.POINTER(GsfIO), C.c_void_p]),

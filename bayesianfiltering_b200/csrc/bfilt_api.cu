@@ -15,6 +15,7 @@
 #include "scan.cuh"
 #include "pf_kernels.cuh"
 #include "pf_resident.cuh"
+#include "pf_fused.cuh"
 #include "gsf_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------ errors
@@ -91,7 +92,7 @@ static int build_model_const(const bf_model_desc* d, ModelConst* mc) {
   chol32(mc->R, d->dr, mc->LR);
   chol32(mc->P0, d->dx, mc->LP0);
   float logdet = 0.0f;
-  for (int i = 0; i < d->dr; ++i) logdet += logf(mc->LR[i * d->dr + i]);
+  for (int i = 0; i < d->dr; ++i) { logdet += logf(mc->LR[i * d->dr + i]); mc->iLR[i] = 1.0f / mc->LR[i * d->dr + i]; }
   mc->lp_const = -logdet - 0.5f * (float)d->dy * 1.8378770664093453f;
   if (mc->model_id == BF_MODEL_LG) {
     bool ok = false;
@@ -129,8 +130,8 @@ struct bf_pf_s {
   bool have_carry;
   DevBuf carry_x, carry_w, carry_uniform, carry_stats;
   // streamed scratch
-  DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats;
-  int ntiles, grid_prop;
+  DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats, phase_ns;
+  int ntiles;
   // host-call staging
   DevBuf hbuf[24];
 };
@@ -170,17 +171,16 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
     bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the carry failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (h->path == BF_PATH_STREAMED) {
-    h->ntiles = (int)(((int64_t)h->N + 1 + PF_TILE - 1) / PF_TILE);
-    h->grid_prop = (int)std::min<int64_t>(((int64_t)h->N + PF_PROP_THREADS - 1) / PF_PROP_THREADS, (int64_t)h->nsm * 8);
-    const size_t npad = (size_t)h->ntiles * PF_TILE;
+    constexpr int FT = PF_FUSED_WARPS * 128;
+    h->ntiles = (int)(((int64_t)h->N + 1 + FT - 1) / FT);
+    const size_t npad = (size_t)h->ntiles * FT;
     if (h->xa.ensure((size_t)h->N * h->mc.dx * 4) || h->xb.ensure((size_t)h->N * h->mc.dx * 4) || h->LL.ensure(npad * 4) ||
-        h->E.ensure(npad * 4) || h->anc.ensure((size_t)h->N * 4) || h->tilesum.ensure((size_t)h->ntiles * 4) ||
-        h->Etile.ensure(((size_t)h->ntiles + 1) * 4) || h->partials.ensure((size_t)h->grid_prop * sizeof(PfPartial)) ||
-        h->counter.ensure(64)) {
+        h->E.ensure(npad * 4) || h->tilesum.ensure((size_t)h->ntiles * 4) || h->Etile.ensure(((size_t)h->ntiles + 1) * 4)) {
       bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the streamed scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    cudaMemset(h->counter.p, 0, 64);
     cudaMemset(h->LL.p, 0, npad * 4);
+    if (h->phase_ns.ensure(8 * sizeof(unsigned long long))) { bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc failed"); }
+    cudaMemset(h->phase_ns.p, 0, 8 * sizeof(unsigned long long));
   }
   *out = h;
   return BF_OK;
@@ -189,10 +189,22 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
 extern "C" int bf_pf_destroy(bf_pf_handle h) {
   if (!h) return BF_OK;
   DevBuf* all[] = {&h->carry_x, &h->carry_w, &h->carry_uniform, &h->carry_stats, &h->xa, &h->xb, &h->LL, &h->E, &h->anc,
-                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats};
+                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns};
   for (DevBuf* b : all) b->release();
   for (DevBuf& b : h->hbuf) b.release();
   delete h;
+  return BF_OK;
+}
+
+extern "C" int bf_pf_phase_times(bf_pf_handle h, double* out_ms, int32_t reset) {
+  if (!h || !out_ms) return fail(BF_EINVAL, "NULL argument");
+  for (int i = 0; i < 5; ++i) out_ms[i] = 0.0;
+  if (h->path != BF_PATH_STREAMED) return BF_OK;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  unsigned long long ns[5];
+  CUDA_OK(cudaMemcpy(ns, h->phase_ns.p, sizeof ns, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 5; ++i) out_ms[i] = (double)ns[i] * 1e-6;
+  if (reset) CUDA_OK(cudaMemset(h->phase_ns.p, 0, sizeof ns));
   return BF_OK;
 }
 
@@ -228,78 +240,70 @@ struct PfRun {
     return BF_OK;
   }
 
+  // large-N path: one persistent cooperative kernel per trial runs all T steps (pf_fused.cuh)
   template <class M> int streamed() {
     constexpr int DX = M::DX, DQ = M::DQ, DY = M::DY;
+    constexpr int NW = PF_FUSED_WARPS, TILE = NW * 128;
     const int N = h->N, B = h->B, T = io->T;
-    const size_t nst = (size_t)(T + 1);
-    CUDA_OK(h->stats.ensure(nst * sizeof(StepStats)));
-    StepStats* stats = h->stats.as<StepStats>();
+    auto kern = k_pf_fused<M, NW>;
+    const int ntiles = h->ntiles;
+    const int nchunk = (ntiles + 1 + TILE - 1) / TILE;
+    const size_t smem = (size_t)(nchunk + 1 + NW + 8) * sizeof(float);
+    int per_sm = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
+    if (per_sm < 1) return fail(BF_ECUDA, "fused particle-filter kernel does not fit on an SM");
+    int grid = std::min(per_sm * h->nsm, ntiles);
+    const int tpc = (ntiles + grid - 1) / grid;
+    grid = (ntiles + tpc - 1) / tpc;
+    CUDA_OK(h->partials.ensure((size_t)2 * grid * sizeof(PfPartial)));
     const int grid_s = (int)std::min<int64_t>(((int64_t)N + 255) / 256, (int64_t)h->nsm * 8);
-    const int nchunk = (h->ntiles + 1 + PF_TILE - 1) / PF_TILE;
-    const size_t scan_smem = (size_t)(nchunk + 1 + PF_TILE_WARPS + 8) * sizeof(float);
+    int log2n = -1;
+    if ((N & (N - 1)) == 0) { log2n = 0; while ((1 << log2n) < N) ++log2n; }
     for (int b = 0; b < B; ++b) {
       float* cx = h->carry_x.as<float>() + (size_t)b * N * DX;
       float* cw = h->carry_w.as<float>() + (size_t)b * N;
-      StepStats* cst = h->carry_stats.as<StepStats>() + b;
-      const float* x_prev;
-      if (io->resume) {
-        x_prev = cx;
-        CUDA_OK(cudaMemcpyAsync(stats, cst, sizeof(StepStats), cudaMemcpyDeviceToDevice, s));
-      } else {
-        if (io->init_particles) x_prev = io->init_particles + (size_t)b * N * DX;
-        else {
-          k_init_particles<DX><<<grid_s, 256, 0, s>>>(h->mc, cx, N, h->cfg.seed, b);
-          LAUNCH_OK(); h->launches++;
-          x_prev = cx;
-        }
-        if (io->init_weights) CUDA_OK(cudaMemcpyAsync(cw, io->init_weights + (size_t)b * N, (size_t)N * 4, cudaMemcpyDeviceToDevice, s));
-        k_init_stats<<<1, 1, 0, s>>>(stats, io->init_weights ? 0 : 1);
+      PfFusedArgs a;
+      memset(&a, 0, sizeof a);
+      a.N = N; a.T = T; a.t_offset = io->t_offset; a.trial = b; a.B = B;
+      a.resume = io->resume; a.w_uniform0 = io->init_weights ? 0 : 1; a.resampler = h->cfg.resampler;
+      a.ntiles = ntiles; a.tiles_per_cta = tpc; a.log2n = log2n;
+      a.ess_threshold = h->cfg.ess_threshold; a.seed = h->cfg.seed;
+      a.emissions = io->emissions + (size_t)(io->emissions_per_trial ? b : 0) * T * DY;
+      a.inputs = io->inputs;
+      if (io->resume) a.x_init = cx;
+      else if (io->init_particles) a.x_init = io->init_particles + (size_t)b * N * DX;
+      else {
+        k_init_particles<DX><<<grid_s, 256, 0, s>>>(h->mc, cx, N, h->cfg.seed, b);
         LAUNCH_OK(); h->launches++;
+        a.x_init = cx;
       }
-      float* bufs[2] = {h->xa.as<float>(), h->xb.as<float>()};
-      for (int t = 0; t < T; ++t) {
-        const size_t bt = (size_t)b * T + t;
-        PfStepArgs a;
-        a.N = N; a.t = t; a.t_global = t + io->t_offset; a.trial = b; a.ess_threshold = h->cfg.ess_threshold;
-        a.resampler = h->cfg.resampler; a.seed = h->cfg.seed;
-        a.y = io->emissions + ((size_t)(io->emissions_per_trial ? b : 0) * T + t) * DY;
-        a.u_in = io->inputs ? io->inputs + t : nullptr;
-        a.x_prev = x_prev; a.x_cur = bufs[t & 1];
-        a.W = cw; a.LL = h->LL.as<float>(); a.E = h->E.as<float>(); a.anc = h->anc.as<int>();
-        a.tilesum = h->tilesum.as<float>(); a.Etile = h->Etile.as<float>();
-        a.partials = h->partials.as<PfPartial>(); a.counter = h->counter.as<unsigned int>();
-        a.prev = stats + t; a.cur = stats + t + 1;
-        a.noise = io->noise ? io->noise + ((size_t)t * B + b) * N * DQ : nullptr;
-        a.res_u = io->resample_u ? (h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC ? io->resample_u + (size_t)t * B + b
-                                                                               : io->resample_u + ((size_t)t * B + b) * N)
-                                 : nullptr;
-        a.out_particles = io->out_particles ? io->out_particles + bt * N * DX : nullptr;
-        a.out_weights = io->out_weights ? io->out_weights + bt * N : nullptr;
-        a.out_propagated = io->out_propagated ? io->out_propagated + bt * N * DX : nullptr;
-        a.out_norm_weights = io->out_norm_weights ? io->out_norm_weights + bt * N : nullptr;
-        a.out_ancestors = io->out_ancestors ? io->out_ancestors + bt * N : nullptr;
-        a.out_mean = io->out_mean ? io->out_mean + bt * DX : nullptr;
-        a.out_loglik = io->out_loglik ? io->out_loglik + bt : nullptr;
-        a.out_ess = io->out_ess ? io->out_ess + bt : nullptr;
-        a.out_resampled = io->out_resampled ? io->out_resampled + bt : nullptr;
-
-        k_propagate<M><<<h->grid_prop, PF_PROP_THREADS, 0, s>>>(h->mc, a);
-        k_weights<<<h->ntiles, PF_TILE_WARPS * 32, 0, s>>>(a);
-        k_scan_tiles<<<1, PF_TILE_WARPS * 32, scan_smem, s>>>(a.tilesum, a.Etile, h->ntiles, a.cur);
-        k_downsweep<<<h->ntiles, PF_TILE_WARPS * 32, 0, s>>>(a);
-        k_search<<<grid_s, 256, 0, s>>>(a);
-        h->launches += 5;
-        if (a.out_particles) { k_emit<DX><<<grid_s, 256, 0, s>>>(a.x_cur, a.anc, a.cur, N, a.out_particles); h->launches++; }
-        LAUNCH_OK();
-        x_prev = a.x_cur;
-      }
-      k_finalize<DX><<<grid_s, 256, 0, s>>>(x_prev, h->anc.as<int>(), stats + T, N, cx, cw,
-                                           io->final_particles ? io->final_particles + (size_t)b * N * DX : nullptr,
-                                           io->final_weights ? io->final_weights + (size_t)b * N : nullptr);
-      LAUNCH_OK(); h->launches++;
-      CUDA_OK(cudaMemcpyAsync(cst, stats + T, sizeof(StepStats), cudaMemcpyDeviceToDevice, s));
-      k_clear_gather<<<1, 1, 0, s>>>(cst);
-      LAUNCH_OK(); h->launches++;
+      if (!io->resume && io->init_weights)
+        CUDA_OK(cudaMemcpyAsync(cw, io->init_weights + (size_t)b * N, (size_t)N * 4, cudaMemcpyDeviceToDevice, s));
+      a.xbuf0 = h->xa.as<float>(); a.xbuf1 = h->xb.as<float>();
+      a.W = cw; a.LL = h->LL.as<float>(); a.E = h->E.as<float>();
+      a.tilesum = h->tilesum.as<float>(); a.Etile = h->Etile.as<float>();
+      a.partials = h->partials.as<PfPartial>();
+      a.carry_stats = h->carry_stats.as<StepStats>() + b;
+      a.noise = io->noise ? io->noise + (size_t)b * N * DQ : nullptr;
+      a.res_u = io->resample_u ? (h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC ? io->resample_u + b : io->resample_u + (size_t)b * N)
+                               : nullptr;
+      const size_t bt = (size_t)b * T;
+      a.out_particles = io->out_particles ? io->out_particles + bt * N * DX : nullptr;
+      a.out_weights = io->out_weights ? io->out_weights + bt * N : nullptr;
+      a.out_propagated = io->out_propagated ? io->out_propagated + bt * N * DX : nullptr;
+      a.out_norm_weights = io->out_norm_weights ? io->out_norm_weights + bt * N : nullptr;
+      a.out_ancestors = io->out_ancestors ? io->out_ancestors + bt * N : nullptr;
+      a.out_mean = io->out_mean ? io->out_mean + bt * DX : nullptr;
+      a.out_loglik = io->out_loglik ? io->out_loglik + bt : nullptr;
+      a.out_ess = io->out_ess ? io->out_ess + bt : nullptr;
+      a.out_resampled = io->out_resampled ? io->out_resampled + bt : nullptr;
+      a.carry_x = cx;
+      a.final_particles = io->final_particles ? io->final_particles + (size_t)b * N * DX : nullptr;
+      a.final_weights = io->final_weights ? io->final_weights + (size_t)b * N : nullptr;
+      a.phase_ns = h->phase_ns.as<unsigned long long>();
+      void* params[] = {(void*)&h->mc, (void*)&a};
+      CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, s));
+      h->launches++;
     }
     return BF_OK;
   }

@@ -19,6 +19,7 @@ struct ModelConst {
   float LQ[BF_MAXD * BF_MAXD];    // chol(Q), row-major dq x dq
   float LR[BF_MAXD * BF_MAXD];    // chol(R), row-major dr x dr
   float LP0[BF_MAXD * BF_MAXD];   // chol(P0)
+  float iLR[BF_MAXD];             // 1 / diag(LR)
   float lp_const;                 // -sum(log diag LR) - 0.5*dy*log(2 pi)
 };
 

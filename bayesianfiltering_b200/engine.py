@@ -93,6 +93,12 @@ class ParticleFilterEngine:
         _lib.check(self.lib.bf_pf_kernel_launches(self.h, C.byref(n)))
         return n.value
 
+    def phase_times(self, reset=True):
+        """Streamed path: ms spent in (propagate+search, stats+weights, tile-sum scan, cdf, final gather)."""
+        out = (C.c_double * 5)()
+        _lib.check(self.lib.bf_pf_phase_times(self.h, out, int(bool(reset))))
+        return dict(zip(("propagate_search", "stats_weights", "scan_tiles", "cdf", "final_gather"), list(out)))
+
     # ------------------------------------------------------------------ shapes of the inputs
     def _in_shapes(self, T, per_trial):
         B, N = self.B, self.N

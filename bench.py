@@ -202,6 +202,7 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     l0 = eng.launches()
+    eng.phase_times(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -212,6 +213,7 @@ def run_ours(args):
     ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
     launches = eng.launches() - l0
+    phases = {k: v * 1e3 / (args.steps * T) for k, v in eng.phase_times().items()}     # us per time step
     ll = bufs["log_likelihood"].double().sum().item()
     if not np.isfinite(ll):
         raise SystemExit(f"benchmark produced a non-finite log-likelihood ({ll})")
@@ -290,7 +292,8 @@ def run_ours(args):
                            "step": "one whole filter run = N*T particle-steps"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
-                             "kernel": "streamed step pipeline"},
+                             "kernel": "k_pf_fused (persistent cooperative kernel, all T steps in one launch)",
+                             "phase_us_per_time_step": phases},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "gsf": gsf}
         print(json.dumps(line), flush=True)
     if world > 1:

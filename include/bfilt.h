@@ -105,6 +105,10 @@ int bf_pf_run(bf_pf_handle h, const bf_pf_io* io, void* cuda_stream);
 int bf_pf_step(bf_pf_handle h, const bf_pf_io* io, void* cuda_stream); /* bf_pf_run with T forced to 1 */
 int bf_pf_run_host(bf_pf_handle h, const bf_pf_io* host_io);
 int bf_pf_kernel_launches(bf_pf_handle h, int64_t* out);   /* launches enqueued so far by this handle */
+/* Streamed path only: wall time (ms, device globaltimer as seen by CTA 0) accumulated in the phases of the
+ * persistent kernel since the last reset -- [0] propagate+ancestor search, [1] statistics+weights+tile sums,
+ * [2] scan of the tile sums, [3] in-tile scan -> cdf, [4] final gather.  Synchronises the device. */
+int bf_pf_phase_times(bf_pf_handle h, double* out_ms5, int32_t reset);
 int bf_pf_destroy(bf_pf_handle h);
 
 /* ---------------------------------------------------------------- Gaussian-sum (EKF) filter */
