@@ -130,7 +130,7 @@ struct bf_pf_s {
   bool have_carry;
   DevBuf carry_x, carry_w, carry_uniform, carry_stats;
   // streamed scratch
-  DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats, phase_ns;
+  DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats, phase_ns, V;
   int ntiles;
   // host-call staging
   DevBuf hbuf[24];
@@ -175,7 +175,8 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
     h->ntiles = (int)(((int64_t)h->N + 1 + FT - 1) / FT);
     const size_t npad = (size_t)h->ntiles * FT;
     if (h->xa.ensure((size_t)h->N * h->mc.dx * 4) || h->xb.ensure((size_t)h->N * h->mc.dx * 4) || h->LL.ensure(npad * 4) ||
-        h->E.ensure(npad * 4) || h->tilesum.ensure((size_t)h->ntiles * 4) || h->Etile.ensure(((size_t)h->ntiles + 1) * 4)) {
+        h->E.ensure(npad * 4) || h->tilesum.ensure((size_t)h->ntiles * 4) || h->Etile.ensure(((size_t)h->ntiles + 1) * 4) ||
+        h->V.ensure(((size_t)h->ntiles + 4) * 4)) {
       bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the streamed scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     cudaMemset(h->LL.p, 0, npad * 4);
@@ -189,7 +190,7 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
 extern "C" int bf_pf_destroy(bf_pf_handle h) {
   if (!h) return BF_OK;
   DevBuf* all[] = {&h->carry_x, &h->carry_w, &h->carry_uniform, &h->carry_stats, &h->xa, &h->xb, &h->LL, &h->E, &h->anc,
-                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns};
+                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V};
   for (DevBuf* b : all) b->release();
   for (DevBuf& b : h->hbuf) b.release();
   delete h;
@@ -248,13 +249,27 @@ struct PfRun {
     auto kern = k_pf_fused<M, NW>;
     const int ntiles = h->ntiles;
     const int nchunk = (ntiles + 1 + TILE - 1) / TILE;
-    const size_t smem = (size_t)(nchunk + 1 + NW + 8) * sizeof(float);
-    int per_sm = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
-    if (per_sm < 1) return fail(BF_ECUDA, "fused particle-filter kernel does not fit on an SM");
-    int grid = std::min(per_sm * h->nsm, ntiles);
-    const int tpc = (ntiles + grid - 1) / grid;
-    grid = (ntiles + tpc - 1) / tpc;
+    // shared memory depends on tiles_per_cta, which depends on the grid, which depends on shared memory: iterate
+    int grid = 1, tpc = ntiles;
+    size_t smem = 0;
+    auto smem_for = [&](int t) { return (size_t)((3 * NW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, nchunk + 1 + NW + 8) + 8) * sizeof(float); };
+    for (int round = 0; round < 3; ++round) {
+      smem = smem_for(round == 0 ? 64 : tpc);
+      if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
+      if (per_sm < 1) return fail(BF_ECUDA, "fused particle-filter kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+      grid = std::min(per_sm * h->nsm, ntiles);
+      tpc = (ntiles + grid - 1) / grid;
+      grid = (ntiles + tpc - 1) / tpc;
+    }
+    smem = smem_for(tpc);
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      int per_sm = 0;                   // a cooperative grid must be co-resident
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
+      if (grid > per_sm * h->nsm) return fail(BF_ECUDA, "cooperative grid of %d CTAs does not fit (%d per SM)", grid, per_sm);
+    }
     CUDA_OK(h->partials.ensure((size_t)2 * grid * sizeof(PfPartial)));
     const int grid_s = (int)std::min<int64_t>(((int64_t)N + 255) / 256, (int64_t)h->nsm * 8);
     int log2n = -1;
@@ -282,6 +297,8 @@ struct PfRun {
       a.xbuf0 = h->xa.as<float>(); a.xbuf1 = h->xb.as<float>();
       a.W = cw; a.LL = h->LL.as<float>(); a.E = h->E.as<float>();
       a.tilesum = h->tilesum.as<float>(); a.Etile = h->Etile.as<float>();
+      a.V = h->V.as<float>(); a.total = h->V.as<float>() + ntiles + 1;
+      a.use_tau = (log2n >= 3) ? 1 : 0;
       a.partials = h->partials.as<PfPartial>();
       a.carry_stats = h->carry_stats.as<StepStats>() + b;
       a.noise = io->noise ? io->noise + (size_t)b * N * DQ : nullptr;

@@ -29,6 +29,17 @@ struct UngmModel {
   }
 };
 
+// sin and cos to ~1 ulp: minimax polynomials (Cephes sinf/cosf kernels) for |x| <= pi/4, libm otherwise.
+__device__ __forceinline__ void sincos_small(float x, float* sn, float* cs) {
+  if (fabsf(x) <= 0.78539816f) {
+    const float z = x * x;
+    *sn = x + x * z * (-1.6666654611e-1f + z * (8.3321608736e-3f + z * -1.9515295891e-4f));
+    *cs = 1.0f - 0.5f * z + z * z * (4.166664568298827e-2f + z * (-1.388731625493765e-3f + z * 2.443315711809948e-5f));
+  } else {
+    sincosf(x, sn, cs);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Manoeuvring bearings-only tracking (BOT_Experiment_script.py:27-47).  theta = [dt acc omega_scale]
 template <int DY_>
@@ -44,7 +55,7 @@ struct BotModel {
     const float k = c.theta[2] * c.theta[1];
     t.s = v2 * rs;
     t.om = k * rs;
-    sincosf(c.theta[0] * t.om, &t.sn, &t.cs);
+    sincos_small(c.theta[0] * t.om, &t.sn, &t.cs);
     const float iom = t.s * (1.0f / k);                 // k is uniform: the reciprocal is hoisted
     t.A = t.sn * iom;
     t.B = (1.0f - t.cs) * iom;

@@ -1,8 +1,10 @@
 // pf_fused.cuh -- bootstrap particle filter, large-N path: ONE persistent cooperative kernel runs all T
 // steps of gaussfiltax/inference.py:1330-1366 with the particle state streamed through HBM (sm_100a).
 //
-// Grid = every co-resident CTA of the device (cooperative launch), tiles of NWARPS*128 consecutive particles
-// are owned by the same CTA (and the same 4 particles by the same thread) in every phase, so a step is
+// Grid = every co-resident CTA of the device (cooperative launch).  A CTA owns a contiguous range of tiles
+// (NWARPS*128 particles, the unit of the canonical summation tree); inside it every WARP owns a contiguous run
+// of chunks (128 particles, 4 per lane) and works through them on its own -- the same 4 particles belong to the
+// same thread in every phase, and no phase has a CTA barrier inside its loop.  A step is
 //
 //   A  ancestor of slot i from the PREVIOUS step's cdf (the resampling gather is fused into the propagate:
 //      x = X[t-1][a_i], never materialised), x~ = f(x, q, u), ll = log p(y | x~), CTA partial of the online
@@ -13,14 +15,23 @@
 //      resampling: canonical tree sum of each tile of w                                      -- grid sync --
 //   C1 CTA 0: canonical exclusive scan of the tile sums                                      -- grid sync --
 //   C2 w again (recomputed from ll, bit-identical), canonical exclusive scan inside each tile -> E[0..N]
-//      (cdf[j] = E[j+1], lax.associative_scan order: oracle/scan.py)                         -- grid sync --
+//      (cdf[j] = E[j+1], lax.associative_scan order: oracle/scan.py); for power-of-two N the cdf is stored
+//      as its EFFECTIVE THRESHOLDS tau (see below)                                           -- grid sync --
 //
 // and after the last step one more gather materialises the carry.  HBM traffic of a resampling step with
 // in-kernel Philox noise, per particle: A read x 4DX + write x~ 4DX + write ll 4 (+ cdf probes, cached);
 // B read ll 4; C2 read ll 4 + write E 4  ->  8 DX + 16 bytes (48 B for DX = 4).
 //
-// The ancestor search is jnp.searchsorted's fixed bisection (oracle/scan.py searchsorted_bisect), the probe
-// sequence is part of the contract because the tree-ordered fp32 cdf is not monotone in its last bit.
+// The ancestor search is jnp.searchsorted's fixed bisection (oracle/scan.py searchsorted_bisect); its probe
+// sequence is part of the contract because the tree-ordered fp32 cdf is not monotone in its last bit.  Running
+// it literally costs 25 dependent loads per particle at N = 2^24 and was half of phase A.  Instead, for
+// N = 2^k, phase C2 stores tau_j = the monotone thresholds with  bisect(cdf, r) == lower_bound(tau, r)  for every
+// r (oracle/scan.py effective_thresholds_pow2: walking down the bisection tree, tau = min(v, .) under a left
+// turn and max(v, .) under a right turn of the probe value v): the same 4 bytes per particle, after which ANY
+// lower-bound search returns the reference's ancestors bit for bit.  Systematic positions are sorted and a
+// warp's chunks are consecutive, so a warp stages the next few hundred bytes of tau (starting at its previous
+// answer) in shared memory and every lane searches that window; multinomial positions bisect tau in global
+// memory.  Other N keep the literal bisection on E.
 #pragma once
 #include <cooperative_groups.h>
 #include "pf_kernels.cuh"
@@ -28,6 +39,7 @@
 namespace cg = cooperative_groups;
 
 #define PF_FUSED_WARPS 16                   // 512 threads, 2 CTAs per SM, tiles of 2048 particles
+#define PF_FUSED_WINCAP 512                 // floats of tau a warp stages in shared memory for one chunk of 128 slots
 
 struct PfFusedArgs {
   int N, T, t_offset, trial, B;
@@ -41,7 +53,10 @@ struct PfFusedArgs {
   float* xbuf0; float* xbuf1;                // [N,DX] ping-pong
   float* W;                                  // [N] carried weights (valid when the carry is not uniform)
   float* LL;                                 // [ntiles*TILE]
-  float* E;                                  // [ntiles*TILE] exclusive canonical cdf, E[N] = total
+  float* E;                                  // [ntiles*TILE] exclusive canonical cdf, E[N] = total; or tau[N] (use_tau)
+  float* V;                                  // [ntiles] w[k*TILE]: cdf[k*TILE] = Etile[k] + V[k] are the probes above a tile
+  float* total;                              // [1] canonical total (= E[N])
+  int use_tau;                               // N = 2^k >= 8: E holds the effective thresholds tau
   float* tilesum;                            // [ntiles]
   float* Etile;                              // [ntiles+1]
   PfPartial* partials;                       // [2*gridDim.x]
@@ -113,6 +128,103 @@ __device__ __forceinline__ void bisect4_left_exclusive_pow2(const float* ex, int
   anc[3] = (int)min(low3 + ((r[3] <= v3) ? 0u : 1u), nm1);
 }
 
+// fixed bisection / lower bound of ONE query on the monotone thresholds tau[0..2^log2n); result in [0, n]
+__device__ __forceinline__ int lower_bound_tau_pow2(const float* tau, int log2n, float r) {
+  unsigned low = 0;
+  for (unsigned s = 1u << (log2n - 1); s != 0; s >>= 1)
+    if (!(r <= tau[low + s])) low += s;
+  return (int)(low + ((r <= tau[low]) ? 0u : 1u));
+}
+
+// number of entries of win[p0..wn) that are < r (NaN r counts every entry, like the bisection's "go right")
+__device__ __forceinline__ int lower_bound_window(const float* win, int p0, int wn, float r) {
+  int pos = p0, len = wn - p0;
+  while (len > 0) {
+    const int half = len >> 1;
+    if (!(r <= win[pos + half])) { pos += half + 1; len -= half + 1; } else len = half;
+  }
+  return pos;
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// Canonical tree sum of one warp-chunk (128 consecutive leaves, 4 per lane); every lane returns it.
+__device__ __forceinline__ float chunk_tree_sum(const float v[4]) {
+  float x = __fadd_rn(__fadd_rn(v[0], v[1]), __fadd_rn(v[2], v[3]));
+#pragma unroll
+  for (int j = 0; j < 5; ++j) x = __fadd_rn(x, __shfl_xor_sync(BF_FULL, x, 1 << j));
+  return x;
+}
+
+// Exclusive canonical scan of one warp-chunk inside its tile, barrier-free: the tree sums of the tile's NWARPS
+// chunks (s_wsum) were left in shared memory by phase B.  Same additions in the same order as
+// tile_exclusive_scan (scan.cuh).  wpos = position of this chunk in the tile.
+// With TAU it also turns the chunk's cdf into its effective thresholds: the bisection tree over the boundaries
+// j of the tile is walked from the tile's node down; the probe value of a node with middle m is cdf[m] = E[m+1]:
+//   across chunks (half-width >= 128 leaves): E(chunk start) + v[first leaf of that chunk] (s_v0) -> lane l of every warp
+//   inside a chunk (half-width 64 .. 4)     : e[1] of the lane that owns leaf m                    -> one shuffle per level
+//   inside a thread (half-width 2, 1)       : e[3], e[2] and the next thread's e[0].
+// (lo, hi) is the clamp interval the levels ABOVE the tile impose; ncap = min(TILE, N) (a power of two).
+template <int NWARPS, bool TAU>
+__device__ __forceinline__ void chunk_scan(const float v[4], int wpos, const float* s_wsum, const float* s_v0, float e_tile,
+                                           float e_next_tile, float lo, float hi, int ncap, float e[4], float tau[4]) {
+  const int lane = threadIdx.x & 31;
+  const float s01 = __fadd_rn(v[0], v[1]);
+  const float s23 = __fadd_rn(v[2], v[3]);
+  float x = __fadd_rn(s01, s23);
+  float recv[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    recv[j] = __shfl_xor_sync(BF_FULL, x, 1 << j);
+    x = __fadd_rn(x, recv[j]);
+  }
+  constexpr int LW = Log2<NWARPS>::v;
+  float y = (lane < NWARPS) ? s_wsum[lane] : 0.0f;
+  float rw[LW > 0 ? LW : 1];
+#pragma unroll
+  for (int j = 0; j < LW; ++j) {
+    rw[j] = __shfl_xor_sync(BF_FULL, y, 1 << j);
+    y = __fadd_rn(y, rw[j]);
+  }
+  float ew = e_tile;                       // lane l: E(first leaf of chunk l)
+#pragma unroll
+  for (int j = LW - 1; j >= 0; --j)
+    if ((lane >> j) & 1) ew = __fadd_rn(ew, rw[j]);
+  float E = __shfl_sync(BF_FULL, ew, wpos);
+#pragma unroll
+  for (int j = 4; j >= 0; --j)
+    if ((lane >> j) & 1) E = __fadd_rn(E, recv[j]);
+  e[0] = E;
+  e[1] = __fadd_rn(E, v[0]);
+  const float e23 = __fadd_rn(E, s01);
+  e[2] = e23;
+  e[3] = __fadd_rn(e23, v[2]);
+  if (!TAU) return;
+  const float cw = __fadd_rn(ew, (lane < NWARPS) ? s_v0[lane] : 0.0f);     // lane l: cdf[first boundary of chunk l]
+#pragma unroll
+  for (int swd = NWARPS / 2; swd >= 1; swd >>= 1) {            // nodes spanning 2*swd chunks
+    const int midw = (wpos & ~(2 * swd - 1)) + swd;
+    const float c = clampf(__shfl_sync(BF_FULL, cw, midw & 31), lo, hi);
+    if (2 * swd * 128 <= ncap) { if (wpos < midw) hi = c; else lo = c; }
+  }
+#pragma unroll
+  for (int sl = 16; sl >= 1; sl >>= 1) {                       // nodes spanning 2*sl lanes
+    const int midl = (lane & ~(2 * sl - 1)) + sl;
+    const float c = clampf(__shfl_sync(BF_FULL, e[1], midl), lo, hi);
+    if (2 * sl * 4 <= ncap) { if (lane < midl) hi = c; else lo = c; }
+  }
+  float nxt = __shfl_down_sync(BF_FULL, e[0], 1);              // E of the next thread's first leaf
+  const float nxtw = (wpos + 1 < NWARPS) ? __shfl_sync(BF_FULL, ew, (wpos + 1) & 31) : e_next_tile;
+  if (lane == 31) nxt = nxtw;
+  const float c2 = clampf(e[3], lo, hi);                       // node (j0, j0+4), middle j0+2
+  const float c1 = clampf(e[2], lo, c2);                       // node (j0, j0+2), middle j0+1
+  const float c3 = clampf(nxt, c2, hi);                        // node (j0+2, j0+4), middle j0+3
+  tau[0] = clampf(e[1], lo, c1);
+  tau[1] = clampf(e[2], c1, c2);
+  tau[2] = clampf(e[3], c2, c3);
+  tau[3] = clampf(nxt, c3, hi);
+}
+
 template <int DX>
 __device__ __forceinline__ void load_state_cg(const float* base, size_t i, float* x) {
   if constexpr (DX % 4 == 0) {
@@ -133,52 +245,116 @@ template <class M, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 2048 / (NWARPS * 32) > 2 ? 2 : 2048 / (NWARPS * 32))
 k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFusedArgs a) {
   constexpr int DX = M::DX, DQ = M::DQ, DY = M::DY;
-  constexpr int NT = NWARPS * 32, TILE = NWARPS * 128;
+  constexpr int NT = NWARPS * 32, TILE = NWARPS * 128, WINCAP = PF_FUSED_WINCAP;
   cg::grid_group grid = cg::this_grid();
-  extern __shared__ float s_dyn[];                    // scan scratch of CTA 0 (phase C1)
-  __shared__ float s_warp[2][NWARPS];
+  // dynamic shared memory (words): [NWARPS*tpc] chunk tree sums | [NWARPS*tpc] first weight of each chunk |
+  // [2*tpc] clamp interval of each tile | [NWARPS*tpc+2] tau window starts | [NWARPS*WINCAP] tau windows (phase A),
+  // aliased by CTA 0's scan scratch (C1)
+  extern __shared__ __align__(16) float s_dyn[];
+  const int tpc = a.tiles_per_cta;
+  float* s_wsum = s_dyn;
+  float* s_v0 = s_wsum + NWARPS * tpc;
+  float* s_meta_f = s_v0 + NWARPS * tpc;
+  int* s_lo = reinterpret_cast<int*>(s_meta_f + 2 * tpc);       // [NWARPS*tpc + 2] tau window start of each chunk
+  float* s_win = reinterpret_cast<float*>(s_lo + NWARPS * tpc + 2);
   __shared__ PfPartial s_part[NWARPS];
   __shared__ StepStats s_stats;
+  __shared__ int s_ctr[4];                            // chunk queues of phases A / B / C2
 
   const int N = a.N, T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
-  const int tile0 = blockIdx.x * a.tiles_per_cta;
-  const int tile1 = min(tile0 + a.tiles_per_cta, a.ntiles);
+  const int tile0 = blockIdx.x * tpc;
+  const int tile1 = min(tile0 + tpc, a.ntiles);
+  // chunks (128 consecutive particles) of this CTA: chunk q starts at particle cta_base + 128 q; warps take them
+  // from a shared queue (the SM's warp arbiter favours some warps: a static split leaves the others as a tail)
+  const int nchunk_cta = NWARPS * (tile1 - tile0);
+  const int cta_base = tile0 * TILE;
+  const int nchunk_valid = max(0, min(nchunk_cta, (N - cta_base + 127) / 128));
+  auto next_chunk = [&](int which) -> int {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(&s_ctr[which], 1);
+    return __shfl_sync(BF_FULL, q, 0);
+  };
+  if (tid < 4) s_ctr[tid] = 0;
+  __syncthreads();
   const float invN = 1.0f / (float)N;
   const int levels = bisect_levels(N);
+  const bool use_tau = a.use_tau != 0;
+  const bool use_win = use_tau && a.resampler == 1;      // sorted positions: windowed search
+  // (i + u) / 2^k is an exact scaling: multiplying by 2^-k gives the same bits as the oracle's division
+  const float invn_pow2 = (a.log2n >= 0) ? __int_as_float((127 - a.log2n) << 23) : 0.0f;
 
   bool w_uni = a.resume ? (a.carry_stats->w_uniform != 0) : (a.w_uniform0 != 0);
   bool gather = false;                                // the carry entering the call is materialised
   const float* x_prev = a.x_init;
-  int sw = 0;                                         // s_warp double-buffer index
+  float res_total = 0.0f, res_u0 = 0.0f;              // of the resampling being gathered
 
-  // ancestors of the 4 slots base..base+3 for the resampling done at (local) step ts
-  auto ancestors4 = [&](int base, int ts, int anc[4]) {
-    const float total = a.E[N];
-    float u[4];
-    if (a.resampler == 1) {
-      const float u0 = a.res_u ? a.res_u[(size_t)ts * a.B]
-                               : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, 0ull);
-      u[0] = u[1] = u[2] = u[3] = u0;
-    } else if (a.res_u) {
-      const float* p = a.res_u + (size_t)ts * a.B * N;
+  auto position = [&](int slot, float u) -> float {
+    if (a.log2n >= 0)
+      return (a.resampler == 1) ? __fmul_rn(res_total, __fmul_rn(__fadd_rn((float)slot, u), invn_pow2))
+                                : __fmul_rn(res_total, __fsub_rn(1.0f, u));
+    return resample_position(a.resampler, res_total, u, slot, N);
+  };
+
+  // Once per phase that gathers: total and the systematic uniform.  ts = local step whose resampling is gathered.
+  auto begin_gather = [&](int ts) {
+    res_total = __ldcg(a.total);
+    if (a.resampler == 1)
+      res_u0 = a.res_u ? a.res_u[(size_t)ts * a.B]
+                       : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, 0ull);
+    if (!use_win) return;
+    // Sorted positions: every answer of chunk q lies in [lower_bound(first slot of q), lower_bound(first slot of q+1)].
+    // One bisection per chunk, all of them in flight together (one latency per step instead of one per chunk).
+    for (int q = tid; q <= nchunk_valid; q += NT) {
+      const int slot = (q < nchunk_valid) ? cta_base + 128 * q : min(cta_base + 128 * nchunk_cta, N) - 1;
+      s_lo[q] = (nchunk_valid > 0) ? lower_bound_tau_pow2(a.E, a.log2n, position(slot, res_u0)) : 0;
+    }
+    __syncthreads();
+  };
+
+  // Ancestors of the 4 slots base..base+3 of the chunk starting at cbase.  Warp-synchronous (all lanes call it).
+  auto ancestors4 = [&](int ts, int q, int base, int nv, int anc[4]) {
+    float u[4] = {res_u0, res_u0, res_u0, res_u0};
+    if (a.resampler != 1 && nv > 0) {
+      if (a.res_u) {
+        const float* p = a.res_u + (size_t)ts * a.B * N;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = (base + k < N) ? p[base + k] : 0.0f;
-    } else {
-      philox_quad_uniforms(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, (uint32_t)(base >> 2), u);
+        for (int k = 0; k < 4; ++k) u[k] = (k < nv) ? p[base + k] : 0.0f;
+      } else {
+        philox_quad_uniforms(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, (uint32_t)(base >> 2), u);
+      }
     }
     float r[4];
-    if (a.log2n >= 0) {
-      // (i + u) / 2^k is an exact scaling: multiplying by 2^-k gives the same bits as the oracle's division
-      const float invn = __int_as_float((127 - a.log2n) << 23);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        r[k] = (a.resampler == 1) ? __fmul_rn(total, __fmul_rn(__fadd_rn((float)(base + k), u[k]), invn))
-                                  : __fmul_rn(total, __fsub_rn(1.0f, u[k]));
-      bisect4_left_exclusive_pow2(a.E, a.log2n, r, anc);
+    for (int k = 0; k < 4; ++k) r[k] = position(base + k, u[k]);
+    if (use_win) {
+      const float* tau = a.E;
+      const int lo = s_lo[q], wn = s_lo[q + 1] - lo;             // warp-uniform
+      if (wn <= WINCAP) {
+        float* win = s_win + warp * WINCAP;
+        for (int i = lane; i < wn; i += 32) win[i] = tau[lo + i];
+        __syncwarp();
+        // a lane's four answers lie between its first answer and the next lane's first answer
+        int p = lower_bound_window(win, 0, wn, r[0]);
+        int pn = __shfl_down_sync(BF_FULL, p, 1);
+        if (lane == 31) pn = wn;
+        anc[0] = min(lo + p, N - 1);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          p = lower_bound_window(win, p, pn, r[k]);
+          anc[k] = min(lo + p, N - 1);
+        }
+        __syncwarp();                                  // the window is overwritten by this warp's next chunk
+      } else if (nv > 0) {                             // window larger than the cap (very uneven weights): rare
+#pragma unroll
+        for (int k = 0; k < 4; ++k) anc[k] = min(lower_bound_tau_pow2(tau, a.log2n, r[k]), N - 1);
+      }
+      return;
+    }
+    if (nv <= 0) return;
+    if (use_tau) {
+      bisect4_left_exclusive_pow2(a.E - 1, a.log2n, r, anc);       // ex[j+1] == tau[j]
     } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) r[k] = resample_position(a.resampler, total, u[k], base + k, N);
 #pragma unroll
       for (int k = 0; k < 4; ++k) anc[k] = fused_bisect_left_exclusive(a.E, N, levels, r[k]);
     }
@@ -198,13 +374,16 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     for (int k = 0; k < DY; ++k) y[k] = a.emissions[(size_t)t * DY + k];
 
     // ------------------------------------------------------------------ phase A
+    if (gather) begin_gather(t - 1);
     OnlineAcc<DX> acc; acc.init();
-    for (int tile = tile0; tile < tile1; ++tile) {
-      const int base = tile * TILE + tid * 4;
-      if (base >= N) continue;                         // no barrier inside this loop
-      const int nv = min(4, N - base);
+    for (int q = next_chunk(0); q < nchunk_valid; q = next_chunk(0)) {
+      const int base = cta_base + 128 * q + lane * 4;
+      const int nv = max(0, min(4, N - base));
       int anc[4] = {base, base + 1, base + 2, base + 3};
-      if (gather) ancestors4(base, t - 1, anc);
+#ifndef BF_EXP_NOSEARCH
+      if (gather) ancestors4(t - 1, q, base, nv, anc);
+#endif
+      if (nv <= 0) continue;
       if (t > 0 && a.out_ancestors) {
         int* o = a.out_ancestors + (size_t)(t - 1) * N + base;
 #pragma unroll
@@ -217,23 +396,28 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       for (int k = 0; k < 4; ++k) {
         if (k < nv) {
           const int i = base + k;
-          float x[DX], q[DQ], xt[DX];
+          float x[DX], qn[DQ], xt[DX];
+#ifdef BF_EXP_NOGATHER
+          load_state_cg<DX>(x_prev, (size_t)i, x);
+          if (anc[k] == -12345) x[0] += 1.0f;
+#else
           load_state_cg<DX>(x_prev, (size_t)anc[k], x);
+#endif
           if (t > 0 && a.out_particles) store_state<DX>(a.out_particles + (size_t)(t - 1) * N * DX, (size_t)i, x);
           if (a.noise) {
             const float* np_ = a.noise + (size_t)t * a.B * N * DQ + (size_t)i * DQ;
 #pragma unroll
-            for (int c = 0; c < DQ; ++c) q[c] = np_[c];
+            for (int c = 0; c < DQ; ++c) qn[c] = np_[c];
           } else {
 #pragma unroll
             for (int r = 0; r < DQ; ++r) {             // q = q0 + L_Q z  (models.py:83, TFP MVN sample)
               float s = mc.q0[r];
 #pragma unroll
               for (int c = 0; c <= r; ++c) s += mc.LQ[r * DQ + c] * z[k][c];
-              q[r] = s;
+              qn[r] = s;
             }
           }
-          M::f(x, q, u_in, mc, xt);
+          M::f(x, qn, u_in, mc, xt);
           store_state<DX>(x_cur, (size_t)i, xt);
           if (a.out_propagated) store_state<DX>(a.out_propagated + (size_t)t * N * DX, (size_t)i, xt);
           const float ll = emission_log_prob<M>(xt, y, u_in, mc);
@@ -249,6 +433,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #pragma unroll
       for (int k = 0; k < DX; ++k) s_part[warp].sx[k] = acc.sx[k];
     }
+    if (tid == 0) { s_ctr[1] = 0; s_ctr[2] = 0; }      // queues of phases B and C2 (nobody is in them now)
     __syncthreads();
     if (warp == 0) {
       acc.init();
@@ -265,6 +450,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     lap(0);
 
     // ------------------------------------------------------------------ phase B
+    if (tid == 0) s_ctr[0] = 0;                        // queue of the next phase A / the final gather
     acc.init();
     for (int b = tid; b < G; b += NT) {               // same order in every CTA: bit-identical stats
       const PfPartial* p = &a.partials[(size_t)(t & 1) * G + b];
@@ -310,9 +496,8 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     const float mx = s_stats.mx, rZ = 1.0f / s_stats.Z;
     const bool flag = s_stats.flag != 0;
 
-    // normalised weights of this thread's 4 leaves in `tile`, exactly as inference.py:1350-1353
-    auto weights4 = [&](int tile, float v[4]) {
-      const int base = tile * TILE + tid * 4;
+    // normalised weights of the 4 leaves base..base+3: (exp(ll - max) * w_prev) / sum   (inference.py:1350-1353)
+    auto weights4 = [&](int base, float v[4]) {
       const float4 l4 = *reinterpret_cast<const float4*>(a.LL + base);
       const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
@@ -322,10 +507,10 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
     };
 
-    for (int tile = tile0; tile < tile1; ++tile) {
-      const int base = tile * TILE + tid * 4;
+    for (int q = next_chunk(1); q < nchunk_cta; q = next_chunk(1)) {
+      const int base = cta_base + 128 * q + lane * 4;
       float v[4];
-      weights4(tile, v);
+      weights4(base, v);
       if (a.out_norm_weights) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) if (base + k < N) a.out_norm_weights[(size_t)t * N + base + k] = v[k];
@@ -341,28 +526,69 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #pragma unroll
           for (int k = 0; k < 4; ++k) if (base + k < N) a.out_weights[(size_t)t * N + base + k] = invN;
         }
-        const float ts = tile_tree_sum<NWARPS>(v, s_warp[sw]);
-        sw ^= 1;
-        if (tid == 0) a.tilesum[tile] = ts;
+        *reinterpret_cast<float4*>(a.E + base) = make_float4(v[0], v[1], v[2], v[3]);   // for phase C2 (same thread)
+        const float cs = chunk_tree_sum(v);
+        if (lane == 0) { s_wsum[q] = cs; s_v0[q] = v[0]; }
       }
     }
     x_prev = x_cur;
     if (!flag) { w_uni = false; gather = false; lap(1); continue; }     // grid-uniform branch
+    __syncthreads();
+    for (int i = tid; i < tile1 - tile0; i += NT) {   // tile sums: the top log2(NWARPS) levels of the tile's tree
+      float y16[NWARPS];
+#pragma unroll
+      for (int k = 0; k < NWARPS; ++k) y16[k] = s_wsum[i * NWARPS + k];
+#pragma unroll
+      for (int w = NWARPS / 2; w >= 1; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) y16[k] = __fadd_rn(y16[2 * k], y16[2 * k + 1]);
+      a.tilesum[tile0 + i] = y16[0];
+      a.V[tile0 + i] = s_v0[i * NWARPS];
+    }
     grid.sync();
     lap(1);
 
     // ------------------------------------------------------------------ phase C1 (CTA 0)
-    if (blockIdx.x == 0) cta_exclusive_scan<NWARPS>(a.tilesum, a.Etile, a.ntiles, s_dyn);
+    if (blockIdx.x == 0) cta_exclusive_scan<NWARPS>(a.tilesum, a.Etile, a.ntiles, s_win);
     grid.sync();
     lap(2);
 
     // ------------------------------------------------------------------ phase C2
-    for (int tile = tile0; tile < tile1; ++tile) {
-      float v[4], e[4];
-      weights4(tile, v);
-      tile_exclusive_scan<NWARPS>(v, __ldcg(&a.Etile[tile]), e, s_warp[sw]);
-      sw ^= 1;
-      *reinterpret_cast<float4*>(a.E + (size_t)tile * TILE + tid * 4) = make_float4(e[0], e[1], e[2], e[3]);
+    if (use_tau) {
+      // clamp interval of each owned tile from the bisection levels above it (half-widths N/2 .. TILE); the probe
+      // value of a node whose middle is the first boundary of tile m is cdf[m*TILE] = Etile[m] + w[m*TILE]
+      for (int i = tid; i < tile1 - tile0; i += NT) {
+        const int jt = (tile0 + i) * TILE;
+        float lo = -INFINITY, hi = INFINITY;
+        if (jt < N) {
+          for (int s = N >> 1; s >= TILE; s >>= 1) {
+            const int mid = (jt & ~(2 * s - 1)) + s, m = mid / TILE;
+            const float c = clampf(__fadd_rn(__ldcg(&a.Etile[m]), __ldcg(&a.V[m])), lo, hi);
+            if (jt < mid) hi = c; else lo = c;
+          }
+        }
+        s_meta_f[2 * i] = lo; s_meta_f[2 * i + 1] = hi;
+      }
+      __syncthreads();
+    }
+    for (int q = next_chunk(2); q < nchunk_cta; q = next_chunk(2)) {
+      const int tl = q / NWARPS, wpos = q % NWARPS, tile = tile0 + tl;
+      const int base = cta_base + 128 * q + lane * 4;
+      float e[4], tau[4];
+      const float4 w4 = *reinterpret_cast<const float4*>(a.E + base);      // the weights phase B left here
+      const float v[4] = {w4.x, w4.y, w4.z, w4.w};
+      float4 out;
+      if (use_tau) {
+        chunk_scan<NWARPS, true>(v, wpos, s_wsum + tl * NWARPS, s_v0 + tl * NWARPS, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]),
+                                 s_meta_f[2 * tl], s_meta_f[2 * tl + 1], min(TILE, N), e, tau);
+        out = make_float4(tau[0], tau[1], tau[2], tau[3]);
+      } else {
+        chunk_scan<NWARPS, false>(v, wpos, s_wsum + tl * NWARPS, s_v0 + tl * NWARPS, __ldcg(&a.Etile[tile]), 0.0f, 0.0f, 0.0f, 0, e, tau);
+        out = make_float4(e[0], e[1], e[2], e[3]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (base + k == N) *a.total = e[k];          // E[N], the canonical total
+      if (!use_tau || base < N) *reinterpret_cast<float4*>(a.E + base) = out;
     }
     grid.sync();
     lap(3);
@@ -370,12 +596,12 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   }
 
   // ------------------------------------------------------------------ materialise the carry
-  for (int tile = tile0; tile < tile1; ++tile) {
-    const int base = tile * TILE + tid * 4;
-    if (base >= N) continue;
-    const int nv = min(4, N - base);
+  if (gather) begin_gather(T - 1);
+  for (int q = next_chunk(0); q < nchunk_valid; q = next_chunk(0)) {
+    const int base = cta_base + 128 * q + lane * 4;
+    const int nv = max(0, min(4, N - base));
     int anc[4] = {base, base + 1, base + 2, base + 3};
-    if (gather) ancestors4(base, T - 1, anc);
+    if (gather) ancestors4(T - 1, q, base, nv, anc);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < nv) {

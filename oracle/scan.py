@@ -97,6 +97,32 @@ def searchsorted_bisect(cdf, r):
     return high.astype(np.int32)
 
 
+def effective_thresholds_pow2(cdf):
+    """Monotone thresholds tau with  searchsorted_bisect(cdf, r) == np.searchsorted(tau, r, 'left')  for EVERY r,
+    for len(cdf) = n = 2^k -- including cdfs that are not monotone (the tree-ordered fp32 cumsum is not).
+
+    Why: the fixed bisection F(r) is monotone in r whatever the array holds (two queries share their path until
+    the first node where the smaller goes left and the larger goes right), so it is a lower bound on SOME
+    monotone array.  Unrolling `F(r) <= j` down the bisection tree: at a node with probe value v = cdf[mid],
+        j <  mid :  F <= j  needs "go left"  (r <= v) AND the left subtree's condition   ->  tau_j = min(v, tau_j(left))
+        j >= mid :  F <= j  holds if "go left" OR the right subtree's condition          ->  tau_j = max(v, tau_j(right))
+    with tau_j = cdf[j] at the bottom.  The CUDA kernel stores tau instead of the cdf (same bytes) and can then
+    use ANY lower-bound search (windowed, galloping) and still return the reference's ancestors bit for bit.
+    O(n log n), test use only."""
+    cdf = np.asarray(cdf)
+    n = cdf.shape[0]
+    assert n >= 1 and (n & (n - 1)) == 0, "power-of-two length only"
+    j = np.arange(n)
+    tau = cdf.copy()
+    s = 1
+    while s < n:                                  # deepest ancestor first, the root last (outermost)
+        mid = (j // (2 * s)) * (2 * s) + s
+        v = cdf[mid]
+        tau = np.where(j < mid, np.minimum(v, tau), np.maximum(v, tau))
+        s *= 2
+    return tau
+
+
 def multinomial_positions(total, u):
     """r_i = p_cuml[-1] * (1 - u_i), u_i in [0,1)   (jax.random.choice, replace=True, p given)."""
     u = np.asarray(u)

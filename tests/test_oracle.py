@@ -36,6 +36,32 @@ def test_bisect_equals_numpy_on_sorted():
         assert np.array_equal(oscan.searchsorted_bisect(c, r), np.searchsorted(c, r, "left"))
 
 
+@pytest.mark.parametrize("kind", ["weights", "noisy", "garbage", "flat"])
+def test_fixed_bisection_is_a_lower_bound_on_effective_thresholds(kind):
+    """The identity the large-N CUDA path rests on: jnp.searchsorted's fixed bisection on ANY array equals
+    numpy's searchsorted on the monotone array oracle.scan.effective_thresholds_pow2 derives from it."""
+    rng = np.random.default_rng({"weights": 0, "noisy": 1, "garbage": 2, "flat": 3}[kind])
+    for n in [1, 2, 4, 8, 64, 512, 4096]:
+        if kind == "weights":
+            w = rng.random(n).astype(np.float32) ** 3; w /= w.sum(dtype=np.float32)
+            cdf = oscan.cumsum_associative(w)
+        elif kind == "noisy":
+            cdf = np.sort(rng.random(n).astype(np.float32))
+            idx = rng.integers(0, n, size=max(1, n // 4)); cdf[idx] += rng.normal(0, 0.02, size=idx.size).astype(np.float32)
+        elif kind == "garbage":
+            cdf = rng.random(n).astype(np.float32)
+        else:
+            w = np.zeros(n, np.float32); w[rng.integers(n)] = 1.0
+            cdf = oscan.cumsum_associative(w) + rng.integers(-2, 3, size=n).astype(np.float32) * np.float32(6e-8)
+        tau = oscan.effective_thresholds_pow2(cdf)
+        assert np.all(np.diff(tau) >= 0)
+        r = np.concatenate([rng.random(2000).astype(np.float32), cdf, np.nextafter(cdf, np.float32(2)),
+                            np.nextafter(cdf, np.float32(-1)), [np.float32(-1), np.float32(2)]]).astype(np.float32)
+        assert np.array_equal(oscan.searchsorted_bisect(cdf, r), np.searchsorted(tau, r, "left"))
+        if kind == "weights":
+            assert np.mean(tau == cdf) > 0.9          # a last-bit repair, not a different cdf
+
+
 def test_resample_invariants():
     rng = np.random.default_rng(2)
     n = 3000
