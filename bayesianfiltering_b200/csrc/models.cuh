@@ -40,6 +40,22 @@ __device__ __forceinline__ void sincos_small(float x, float* sn, float* cs) {
   }
 }
 
+// atan2 to ~2 ulp in ~28 instructions (libm's atan2f is ~52): one division, Cephes atanf's reduction at
+// tan(pi/8) and its degree-4 polynomial in t^2, then the quadrant.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const bool mid = mn > 0.41421356f * mx;               // atan(mn/mx) = pi/4 + atan((mn-mx)/(mn+mx))
+  const float num = mid ? mn - mx : mn, den = mid ? mn + mx : mx;
+  const float t = (den == 0.0f) ? 0.0f : __fdividef(num, den);
+  const float z = t * t;
+  const float p = ((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f;
+  float r = fmaf(p * z, t, t) + (mid ? 0.78539816339744831f : 0.0f);
+  if (ay > ax) r = 1.57079632679489662f - r;
+  if (x < 0.0f) r = 3.14159265358979324f - r;
+  return copysignf(r, y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Manoeuvring bearings-only tracking (BOT_Experiment_script.py:27-47).  theta = [dt acc omega_scale]
 template <int DY_>
@@ -67,6 +83,13 @@ struct BotModel {
   __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
     float c0, c1, c2; coef(u, c0, c1, c2);
     const float T = c.theta[0];
+    const float gq0 = 0.5f * q[0], gq2 = 0.5f * q[1];
+    // u = 0 (constant velocity): the two turn models enter with coefficient exactly 0 -- skip them unless the
+    // speed is 0, where the reference's 0 * NaN still poisons the result
+    if (c0 == 1.0f && c1 == 0.0f && c2 == 0.0f && (x[1] != 0.0f || x[3] != 0.0f)) {
+      o[0] = x[0] + T * x[1] + gq0; o[1] = x[1] + q[0]; o[2] = x[2] + T * x[3] + gq2; o[3] = x[3] + q[1];
+      return;
+    }
     Turn t = turn(x, c);
     // FCT(x,+acc) x and FCT(x,-acc) x share sin/cos: Omega -> -Omega flips sn and B only
     float p0 = x[0] + t.A * x[1], p2 = x[2] + t.A * x[3];
@@ -78,7 +101,7 @@ struct BotModel {
     for (int i = 0; i < 4; ++i) o[i] = c0 * cv[i] + c1 * ct1[i] + c2 * ct2[i] + gq[i];
   }
   __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
-    o[0] = atan2f(x[2], x[0]) + r[0];
+    o[0] = atan2_fast(x[2], x[0]) + r[0];
     if (DY == 2) o[1] = sqrtf(x[0] * x[0] + x[2] * x[2]) + r[1];
   }
   // d(FCT(x,a) x)/dx for a = +acc (sgn=+1) or -acc (sgn=-1), accumulated into J with weight cw

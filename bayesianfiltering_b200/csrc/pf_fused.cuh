@@ -275,11 +275,17 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (lane == 0) q = atomicAdd(&s_ctr[which], 1);
     return __shfl_sync(BF_FULL, q, 0);
   };
+  auto next_chunks4 = [&](int which) -> int {          // four consecutive chunks: their loads are issued together
+    int q = 0;
+    if (lane == 0) q = atomicAdd(&s_ctr[which], 4);
+    return __shfl_sync(BF_FULL, q, 0);
+  };
   if (tid < 4) s_ctr[tid] = 0;
   __syncthreads();
   const float invN = 1.0f / (float)N;
   const int levels = bisect_levels(N);
   const bool use_tau = a.use_tau != 0;
+  const bool w_vec = (reinterpret_cast<size_t>(a.W) & 15) == 0;     // carry of trial b starts at b*N floats
   const bool use_win = use_tau && a.resampler == 1;      // sorted positions: windowed search
   // (i + u) / 2^k is an exact scaling: multiplying by 2^-k gives the same bits as the oracle's division
   const float invn_pow2 = (a.log2n >= 0) ? __int_as_float((127 - a.log2n) << 23) : 0.0f;
@@ -496,43 +502,54 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     const float mx = s_stats.mx, rZ = 1.0f / s_stats.Z;
     const bool flag = s_stats.flag != 0;
 
-    // normalised weights of the 4 leaves base..base+3: (exp(ll - max) * w_prev) / sum   (inference.py:1350-1353)
-    auto weights4 = [&](int base, float v[4]) {
-      const float4 l4 = *reinterpret_cast<const float4*>(a.LL + base);
-      const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+    // normalised weights (exp(ll - max) * w_prev) / sum (inference.py:1350-1353), four chunks per turn so that four
+    // 512-byte loads per warp are in flight (one at a time left this phase latency-bound)
+    for (int qb = next_chunks4(1); qb < nchunk_cta; qb = next_chunks4(1)) {
+      float4 l4[4], wp4[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float wp = (base + k < N) ? (w_uni ? invN : a.W[base + k]) : 0.0f;
-        v[k] = (base + k < N) ? norm_weight_rcp(ll[k], wp, mx, rZ) : 0.0f;
-      }
-    };
-
-    for (int q = next_chunk(1); q < nchunk_cta; q = next_chunk(1)) {
-      const int base = cta_base + 128 * q + lane * 4;
-      float v[4];
-      weights4(base, v);
-      if (a.out_norm_weights) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (base + k < N) a.out_norm_weights[(size_t)t * N + base + k] = v[k];
-      }
-      if (!flag) {                       // identity branch of lax.cond (inference.py:1357): carry the weights
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (base + k < N) {
-          a.W[base + k] = v[k];
-          if (a.out_weights) a.out_weights[(size_t)t * N + base + k] = v[k];
+      for (int j = 0; j < 4; ++j) {
+        const int base = cta_base + 128 * (qb + j) + lane * 4;
+        l4[j] = *reinterpret_cast<const float4*>(a.LL + base);
+        wp4[j] = make_float4(invN, invN, invN, invN);
+        if (!w_uni && w_vec && base + 3 < N) wp4[j] = *reinterpret_cast<const float4*>(a.W + base);
+        else if (!w_uni) {
+          wp4[j].x = (base < N) ? a.W[base] : 0.0f; wp4[j].y = (base + 1 < N) ? a.W[base + 1] : 0.0f;
+          wp4[j].z = (base + 2 < N) ? a.W[base + 2] : 0.0f; wp4[j].w = (base + 3 < N) ? a.W[base + 3] : 0.0f;
         }
-      } else {
-        if (a.out_weights) {             // utils.py:212: weights = 1/N after resampling
+      }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) if (base + k < N) a.out_weights[(size_t)t * N + base + k] = invN;
+      for (int j = 0; j < 4; ++j) {
+        const int q = qb + j, base = cta_base + 128 * q + lane * 4;
+        const float ll[4] = {l4[j].x, l4[j].y, l4[j].z, l4[j].w}, wp[4] = {wp4[j].x, wp4[j].y, wp4[j].z, wp4[j].w};
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (base + k < N) ? norm_weight_rcp(ll[k], wp[k], mx, rZ) : 0.0f;
+        if (a.out_norm_weights) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (base + k < N) a.out_norm_weights[(size_t)t * N + base + k] = v[k];
         }
-        *reinterpret_cast<float4*>(a.E + base) = make_float4(v[0], v[1], v[2], v[3]);   // for phase C2 (same thread)
-        const float cs = chunk_tree_sum(v);
-        if (lane == 0) { s_wsum[q] = cs; s_v0[q] = v[0]; }
+        if (!flag) {                     // identity branch of lax.cond (inference.py:1357): carry the weights
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (base + k < N) {
+            a.W[base + k] = v[k];
+            if (a.out_weights) a.out_weights[(size_t)t * N + base + k] = v[k];
+          }
+        } else {
+          if (a.out_weights) {           // utils.py:212: weights = 1/N after resampling
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (base + k < N) a.out_weights[(size_t)t * N + base + k] = invN;
+          }
+          *reinterpret_cast<float4*>(a.E + base) = make_float4(v[0], v[1], v[2], v[3]);   // for phase C2
+          const float cs = chunk_tree_sum(v);
+          if (lane == 0) { s_wsum[q] = cs; s_v0[q] = v[0]; }
+        }
       }
     }
     x_prev = x_cur;
-    if (!flag) { w_uni = false; gather = false; lap(1); continue; }     // grid-uniform branch
+    if (!flag) {                         // grid-uniform branch: no grid sync, but chunks change hands between warps
+      __syncthreads();                   // W of this step is complete before any warp of the CTA starts the next step
+      w_uni = false; gather = false; lap(1); continue;
+    }
     __syncthreads();
     for (int i = tid; i < tile1 - tile0; i += NT) {   // tile sums: the top log2(NWARPS) levels of the tile's tree
       float y16[NWARPS];
@@ -571,24 +588,30 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
       __syncthreads();
     }
-    for (int q = next_chunk(2); q < nchunk_cta; q = next_chunk(2)) {
-      const int tl = q / NWARPS, wpos = q % NWARPS, tile = tile0 + tl;
-      const int base = cta_base + 128 * q + lane * 4;
-      float e[4], tau[4];
-      const float4 w4 = *reinterpret_cast<const float4*>(a.E + base);      // the weights phase B left here
-      const float v[4] = {w4.x, w4.y, w4.z, w4.w};
-      float4 out;
-      if (use_tau) {
-        chunk_scan<NWARPS, true>(v, wpos, s_wsum + tl * NWARPS, s_v0 + tl * NWARPS, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]),
-                                 s_meta_f[2 * tl], s_meta_f[2 * tl + 1], min(TILE, N), e, tau);
-        out = make_float4(tau[0], tau[1], tau[2], tau[3]);
-      } else {
-        chunk_scan<NWARPS, false>(v, wpos, s_wsum + tl * NWARPS, s_v0 + tl * NWARPS, __ldcg(&a.Etile[tile]), 0.0f, 0.0f, 0.0f, 0, e, tau);
-        out = make_float4(e[0], e[1], e[2], e[3]);
-      }
+    for (int qb = next_chunks4(2); qb < nchunk_cta; qb = next_chunks4(2)) {
+      float4 w4[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (base + k == N) *a.total = e[k];          // E[N], the canonical total
-      if (!use_tau || base < N) *reinterpret_cast<float4*>(a.E + base) = out;
+      for (int j = 0; j < 4; ++j)        // the weights phase B left here
+        w4[j] = *reinterpret_cast<const float4*>(a.E + cta_base + 128 * (qb + j) + lane * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = qb + j, tl = q / NWARPS, wpos = q % NWARPS, tile = tile0 + tl;
+        const int base = cta_base + 128 * q + lane * 4;
+        float e[4], tau[4];
+        const float v[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};
+        float4 out;
+        if (use_tau) {
+          chunk_scan<NWARPS, true>(v, wpos, s_wsum + tl * NWARPS, s_v0 + tl * NWARPS, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]),
+                                   s_meta_f[2 * tl], s_meta_f[2 * tl + 1], min(TILE, N), e, tau);
+          out = make_float4(tau[0], tau[1], tau[2], tau[3]);
+        } else {
+          chunk_scan<NWARPS, false>(v, wpos, s_wsum + tl * NWARPS, s_v0 + tl * NWARPS, __ldcg(&a.Etile[tile]), 0.0f, 0.0f, 0.0f, 0, e, tau);
+          out = make_float4(e[0], e[1], e[2], e[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (base + k == N) *a.total = e[k];          // E[N], the canonical total
+        if (!use_tau || base < N) *reinterpret_cast<float4*>(a.E + base) = out;
+      }
     }
     grid.sync();
     lap(3);

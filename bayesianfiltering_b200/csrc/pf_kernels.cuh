@@ -86,7 +86,9 @@ struct OnlineAcc {
   }
   __device__ __forceinline__ void add(float ll, float wprev, const float* x) {
     if (ll > m) rescale(ll);
-    float e = (ll == -INFINITY) ? 0.0f : expf(ll - m) * wprev;
+    // statistics only (sum, ESS, mean): the fast exponential's ~1e-7 relative error is far inside their 1e-5 bar;
+    // the weights themselves are computed with expf in norm_weight*
+    float e = (ll == -INFINITY) ? 0.0f : __expf(ll - m) * wprev;
     s += e; s2 += e * e;
 #pragma unroll
     for (int k = 0; k < DX; ++k) sx[k] += e * x[k];
