@@ -71,6 +71,7 @@ SYMBOLS = [
                                 C.c_void_p, C.c_void_p]),
     ("bf_ssm_sample", C.c_int, [C.POINTER(ModelDesc), C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("bf_trim_memory", C.c_int, [C.c_int32]),
     ("bf_last_error", C.c_char_p, []),
     ("bf_abi_version", C.c_int, []),
 ]

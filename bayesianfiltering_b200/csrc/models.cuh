@@ -40,17 +40,18 @@ __device__ __forceinline__ void sincos_small(float x, float* sn, float* cs) {
   }
 }
 
-// atan2 to ~2 ulp in ~28 instructions (libm's atan2f is ~52): one division, Cephes atanf's reduction at
+// atan2 to ~1 ulp in ~35 instructions (libm's atan2f is ~52): one division, Cephes atanf's reduction at
 // tan(pi/8) and its degree-4 polynomial in t^2, then the quadrant.
 __device__ __forceinline__ float atan2_fast(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
   const bool mid = mn > 0.41421356f * mx;               // atan(mn/mx) = pi/4 + atan((mn-mx)/(mn+mx))
   const float num = mid ? mn - mx : mn, den = mid ? mn + mx : mx;
-  const float t = (den == 0.0f) ? 0.0f : __fdividef(num, den);
+  const float t = (den == 0.0f) ? 0.0f : num / den;
   const float z = t * t;
   const float p = ((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f;
-  float r = fmaf(p * z, t, t) + (mid ? 0.78539816339744831f : 0.0f);
+  float r = fmaf(p * z, t, t);
+  if (mid) r = (r + -2.18556941e-8f) + 0.785398185253143310546875f;     // pi/4 as hi + lo
   if (ay > ax) r = 1.57079632679489662f - r;
   if (x < 0.0f) r = 3.14159265358979324f - r;
   return copysignf(r, y);

@@ -270,6 +270,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   const int nchunk_cta = NWARPS * (tile1 - tile0);
   const int cta_base = tile0 * TILE;
   const int nchunk_valid = max(0, min(nchunk_cta, (N - cta_base + 127) / 128));
+#ifdef BF_DYNAMIC_CHUNKS
   auto next_chunk = [&](int which) -> int {
     int q = 0;
     if (lane == 0) q = atomicAdd(&s_ctr[which], 1);
@@ -280,6 +281,13 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (lane == 0) q = atomicAdd(&s_ctr[which], 4);
     return __shfl_sync(BF_FULL, q, 0);
   };
+#else
+  // Static round-robin: warp w takes chunks w, w + NWARPS, ... -- the order in which a thread accumulates its
+  // statistics is then fixed, so a run is bit-reproducible (and a run split in time equals the unsplit run).
+  int turn[3] = {0, 0, 0};
+  auto next_chunk = [&](int which) -> int { return warp + NWARPS * turn[which]++; };
+  auto next_chunks4 = [&](int which) -> int { return 4 * (warp + NWARPS * turn[which]++); };
+#endif
   if (tid < 4) s_ctr[tid] = 0;
   __syncthreads();
   const float invN = 1.0f / (float)N;
@@ -440,6 +448,9 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       for (int k = 0; k < DX; ++k) s_part[warp].sx[k] = acc.sx[k];
     }
     if (tid == 0) { s_ctr[1] = 0; s_ctr[2] = 0; }      // queues of phases B and C2 (nobody is in them now)
+#ifndef BF_DYNAMIC_CHUNKS
+    turn[1] = 0; turn[2] = 0;
+#endif
     __syncthreads();
     if (warp == 0) {
       acc.init();
@@ -457,6 +468,9 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 
     // ------------------------------------------------------------------ phase B
     if (tid == 0) s_ctr[0] = 0;                        // queue of the next phase A / the final gather
+#ifndef BF_DYNAMIC_CHUNKS
+    turn[0] = 0;
+#endif
     acc.init();
     for (int b = tid; b < G; b += NT) {               // same order in every CTA: bit-identical stats
       const PfPartial* p = &a.partials[(size_t)(t & 1) * G + b];

@@ -167,6 +167,10 @@ int bf_ssm_sample(const bf_model_desc* model, int32_t B, int32_t T, const float*
                   const float* z0, const float* q_noise, const float* r_noise, float* states, float* emissions,
                   void* cuda_stream);
 
+/* Handles draw their device memory from the device's stream-ordered pool and leave it cached there when they are
+ * destroyed (creating a handle per call stays cheap).  This returns the cached memory to the driver. */
+int bf_trim_memory(int32_t device);
+
 const char* bf_last_error(void);
 int bf_abi_version(void);
 
