@@ -11,6 +11,7 @@ BF_OK, BF_EINVAL, BF_ECUDA, BF_ENOMODEL, BF_ENOMEM, BF_ECOMM = 0, -1, -2, -3, -4
 MODEL_UNGM, MODEL_BOT, MODEL_L63, MODEL_L96, MODEL_LG, MODEL_SIN1D = 1, 2, 3, 4, 5, 6
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 PATH_AUTO, PATH_RESIDENT, PATH_STREAMED = 0, 1, 2
+GSF_PREDICT_FIRST, GSF_NO_JITTER, GSF_COV_PLUS_P = 1, 2, 4
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)
@@ -39,7 +40,7 @@ class PfIO(C.Structure):
 
 
 class GsfConfig(C.Structure):
-    _fields_ = [("num_components", C.c_int32), ("num_trials", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("num_components", C.c_int32), ("num_trials", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32)]
 
 
 class GsfIO(C.Structure):

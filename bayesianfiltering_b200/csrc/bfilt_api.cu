@@ -485,6 +485,7 @@ struct GsfRun {
   template <class M> int run() {
     GsfArgs a;
     a.M = h->cfg.num_components; a.T = io->T; a.resume = io->resume; a.emissions_per_trial = io->emissions_per_trial;
+    a.flags = h->cfg.flags;
     a.emissions = io->emissions; a.inputs = io->inputs; a.init_means = io->init_means; a.init_covs = io->init_covs;
     a.init_weights = io->init_weights;
     a.carry_w = h->carry_w.as<float>(); a.carry_m = h->carry_m.as<float>(); a.carry_P = h->carry_P.as<float>();

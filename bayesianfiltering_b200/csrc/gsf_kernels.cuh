@@ -17,9 +17,10 @@
 #pragma once
 #include "common.cuh"
 #include "models.cuh"
+#include "../../include/bfilt.h"
 
 struct GsfArgs {
-  int M, T, resume, emissions_per_trial;
+  int M, T, resume, emissions_per_trial, flags;
   const float* emissions; const float* inputs;
   const float* init_means; const float* init_covs; const float* init_weights;
   float* carry_w; float* carry_m; float* carry_P;       // handle-owned carry [B,M], [B,M,DX], [B,M,DX,DX]
@@ -127,7 +128,7 @@ __device__ __forceinline__ float mvn_logpdf_chol(const float* S, const float* d)
 
 // one component: `_condition_on` (inference.py:72-105).  m,P in/out; returns ll.
 template <class Mo>
-__device__ __forceinline__ float ekf_condition(float* m, float* P, const float* y, float u, const ModelConst& mc) {
+__device__ __forceinline__ float ekf_condition(float* m, float* P, const float* y, float u, const ModelConst& mc, float jitter) {
   constexpr int DX = Mo::DX, DY = Mo::DY;
   float H[DY * DX], HP[DY * DX], S[DY * DY], Sj[DY * DY], X[DY * DX];
   Mo::Hx(m, mc.r0, u, mc, H);
@@ -138,7 +139,7 @@ __device__ __forceinline__ float ekf_condition(float* m, float* P, const float* 
 #pragma unroll
     for (int j = 0; j < DY; ++j) {
       S[i * DY + j] = mc.R[i * DY + j] + S[i * DY + j];      // H_r R H_r^T + H_x P H_x^T  (:99), H_r = I
-      Sj[i * DY + j] = S[i * DY + j] + 1e-6f;                // psd_solve jitter on EVERY element
+      Sj[i * DY + j] = S[i * DY + j] + jitter;               // psd_solve: + 1e-6 on EVERY element
     }
 #pragma unroll
   for (int i = 0; i < DY * DX; ++i) X[i] = HP[i];
@@ -177,8 +178,9 @@ __device__ __forceinline__ float ekf_condition(float* m, float* P, const float* 
 }
 
 // one component: `_predict` (inference.py:51-70).  GQG = F_q Q F_q^T (constant F_q).
+// cov_plus_p: the legacy gausssumfilt.GaussSumFilt adds the covariance itself instead of Q (gausssumfilt.py:59)
 template <class Mo>
-__device__ __forceinline__ void ekf_predict(float* m, float* P, float u, const ModelConst& mc, const float* GQG) {
+__device__ __forceinline__ void ekf_predict(float* m, float* P, float u, const ModelConst& mc, const float* GQG, bool cov_plus_p = false) {
   constexpr int DX = Mo::DX;
   float F[DX * DX], FP[DX * DX], mn[DX];
   Mo::Fx(m, mc.q0, u, mc, F);
@@ -191,7 +193,7 @@ __device__ __forceinline__ void ekf_predict(float* m, float* P, float u, const M
       float s = 0.0f;
 #pragma unroll
       for (int k = 0; k < DX; ++k) s += FP[i * DX + k] * F[j * DX + k];
-      P[i * DX + j] = s + GQG[i * DX + j];
+      P[i * DX + j] = s + (cov_plus_p ? P[i * DX + j] : GQG[i * DX + j]);
     }
 #pragma unroll
   for (int i = 0; i < DX; ++i) m[i] = mn[i];
@@ -253,6 +255,12 @@ __global__ void k_gsf(const __grid_constant__ ModelConst mc, const __grid_consta
     for (int i = 0; i < DX * DX; ++i) P[i] = a.init_covs ? a.init_covs[bm * DX * DX + i] : mc.P0[i];
   }
 
+  const float jitter = (a.flags & BF_GSF_NO_JITTER) ? 0.0f : 1e-6f;
+  const bool cov_plus_p = (a.flags & BF_GSF_COV_PLUS_P) != 0;
+  // legacy order (gausssumfilt.py:51-70): the carry entering the call holds FILTERED moments -> predict first,
+  // with the input of the first step
+  if ((a.flags & BF_GSF_PREDICT_FIRST) && !a.resume) ekf_predict<Mo>(m, P, a.inputs ? a.inputs[0] : 0.0f, mc, GQG, cov_plus_p);
+
   for (int t = 0; t < T; ++t) {
     const float* yp = a.emissions + ((size_t)(a.emissions_per_trial ? b : 0) * T + t) * DY;
     float y[DY];
@@ -261,7 +269,7 @@ __global__ void k_gsf(const __grid_constant__ ModelConst mc, const __grid_consta
     const float u = a.inputs ? a.inputs[t] : 0.0f;
     const size_t btm = ((size_t)b * T + t) * M + (active ? tid : 0);
 
-    float ll = ekf_condition<Mo>(m, P, y, u, mc);
+    float ll = ekf_condition<Mo>(m, P, y, u, mc, jitter);
     if (!active) ll = -INFINITY;
     if (active) {
       if (a.out_means) store_vec<DX>(a.out_means + btm * DX, m);
@@ -300,7 +308,7 @@ __global__ void k_gsf(const __grid_constant__ ModelConst mc, const __grid_consta
     }
     __syncthreads();                  // s_red reuse in the next step
 
-    ekf_predict<Mo>(m, P, u, mc, GQG);
+    ekf_predict<Mo>(m, P, u, mc, GQG, cov_plus_p);
     if (active) {
       if (a.out_pred_means) store_vec<DX>(a.out_pred_means + btm * DX, m);
       if (a.out_pred_covs) store_vec<DX * DX>(a.out_pred_covs + btm * DX * DX, P);

@@ -41,6 +41,9 @@ class RegisteredModel:
         self.dynamics_function = _Tagged(self, "f")
         self.emission_function = _Tagged(self, "h")
         self.emission_log_prob = _Tagged(self, "lp")
+        # single-argument faces for the legacy classes (gaussfilt.SSM(f=..., g=...)): f(x) = f(x, 0, 0), g(x) = h(x, 0, 0)
+        self.f = _Tagged(self, "f")
+        self.g = _Tagged(self, "h")
 
     # -- host-side description of a fully specified model (theta + the params' arrays)
     def host_model(self, q0=None, Q=None, r0=None, R=None, m0=None, P0=None):

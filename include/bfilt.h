@@ -114,11 +114,17 @@ int bf_pf_destroy(bf_pf_handle h);
 /* ---------------------------------------------------------------- Gaussian-sum (EKF) filter */
 typedef struct bf_gsf_s* bf_gsf_handle;
 
+/* flags: the legacy NumPy classes (gaussfiltax/gausssumfilt.py:30-78, gaussfilt.py:88-130, :325-361) run the same
+ * per-component EKF in a different order and with their own quirks */
+#define BF_GSF_PREDICT_FIRST 1    /* init_* are FILTERED moments: predict once before the first update (gausssumfilt.py:55-59) */
+#define BF_GSF_NO_JITTER 2        /* gain from S itself (legacy np.linalg.inv(Sy), :67), not S + 1e-6 (utils.py:258)           */
+#define BF_GSF_COV_PLUS_P 4       /* predict with cov + F cov F^T -- adds cov, never Q (gausssumfilt.py:59, sic)               */
+
 typedef struct bf_gsf_config {
   int32_t num_components;   /* M */
   int32_t num_trials;       /* B */
   int32_t device;
-  int32_t reserved;
+  int32_t flags;            /* BF_GSF_* ; 0 = gaussfiltax/inference.py:303-377 */
 } bf_gsf_config;
 
 typedef struct bf_gsf_io {
