@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbfilt.so")
+LIB_PATH = os.environ.get("BFILT_LIB", os.path.join(_HERE, "libbfilt.so"))
 
 BF_OK, BF_EINVAL, BF_ECUDA, BF_ENOMODEL, BF_ENOMEM, BF_ECOMM = 0, -1, -2, -3, -4, -5
 MODEL_UNGM, MODEL_BOT, MODEL_L63, MODEL_L96, MODEL_LG, MODEL_SIN1D = 1, 2, 3, 4, 5, 6

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -198,7 +199,7 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
     bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the carry failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (h->path == BF_PATH_STREAMED) {
-    constexpr int FT = PF_FUSED_WARPS * 128;
+    constexpr int FT = PF_FUSED_TILE_CHUNKS * 128;
     h->ntiles = (int)(((int64_t)h->N + 1 + FT - 1) / FT);
     const size_t npad = (size_t)h->ntiles * FT;
     if (h->xa.ensure((size_t)h->N * h->mc.dx * 4) || h->xb.ensure((size_t)h->N * h->mc.dx * 4) || h->LL.ensure(npad * 4) ||
@@ -273,15 +274,15 @@ struct PfRun {
   // large-N path: one persistent cooperative kernel per trial runs all T steps (pf_fused.cuh)
   template <class M> int streamed() {
     constexpr int DX = M::DX, DQ = M::DQ, DY = M::DY;
-    constexpr int NW = PF_FUSED_WARPS, TILE = NW * 128;
+    constexpr int NW = PF_FUSED_WARPS, TW = PF_FUSED_TILE_CHUNKS;
     const int N = h->N, B = h->B, T = io->T;
-    auto kern = k_pf_fused<M, NW>;
+    auto kern = k_pf_fused<M, NW, PF_FUSED_CTAS_PER_SM>;
     const int ntiles = h->ntiles;
-    const int nchunk = (ntiles + 1 + TILE - 1) / TILE;
+    const int nchunk = (ntiles + 1 + NW * 128 - 1) / (NW * 128);      // chunks of the one-CTA scan of the tile sums
     // shared memory depends on tiles_per_cta, which depends on the grid, which depends on shared memory: iterate
     int grid = 1, tpc = ntiles;
     size_t smem = 0;
-    auto smem_for = [&](int t) { return (size_t)((3 * NW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, nchunk + 1 + NW + 8) + 8) * sizeof(float); };
+    auto smem_for = [&](int t) { return (size_t)((3 * TW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, nchunk + 1 + NW + 8) + 8) * sizeof(float); };
     for (int round = 0; round < 3; ++round) {
       smem = smem_for(round == 0 ? 64 : tpc);
       if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -442,6 +443,7 @@ struct bf_gsf_s {
   bool have_carry;
   DevBuf carry_w, carry_m, carry_P;
   DevBuf hbuf[16];
+  int nsm;
 };
 
 extern "C" int bf_gsf_create(const bf_model_desc* model, const bf_gsf_config* cfg, bf_gsf_handle* out) {
@@ -456,6 +458,8 @@ extern "C" int bf_gsf_create(const bf_model_desc* model, const bf_gsf_config* cf
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { delete h; return fail(BF_ECUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e)); }
   if ((e = pool_setup(cfg->device)) != cudaSuccess) { delete h; return fail(BF_ECUDA, "memory pool setup: %s", cudaGetErrorString(e)); }
+  h->nsm = 148;
+  cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, cfg->device);
   const size_t bm = (size_t)cfg->num_trials * cfg->num_components, dx = h->mc.dx;
   if (h->carry_w.ensure(bm * 4) || h->carry_m.ensure(bm * dx * 4) || h->carry_P.ensure(bm * dx * dx * 4)) {
     bf_gsf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the carry failed");
@@ -492,8 +496,26 @@ struct GsfRun {
     a.out_weights = io->out_weights; a.out_means = io->out_means; a.out_covs = io->out_covs;
     a.out_pred_means = io->out_pred_means; a.out_pred_covs = io->out_pred_covs; a.out_loglik = io->out_loglik;
     a.out_mix_mean = io->out_mix_mean;
-    const int threads = std::max(32, ((a.M + 31) / 32) * 32);
-    k_gsf<M><<<h->cfg.num_trials, threads, 0, s>>>(h->mc, a);
+    // one warp per trial when the mixture fits CPL components per lane within the register budget
+    // (state words per lane: CPL * (1 + dx + dx^2)); else one CTA per trial, one thread per component
+    constexpr int DXm = M::DX, WORDS = 1 + DXm + DXm * DXm;
+    const int cpl = (a.M + 31) / 32;
+    const int B = h->cfg.num_trials, gridw = (B + 3) / 4;
+    // a warp per trial needs enough trials to fill the machine (B warps in flight); below that, one thread per
+    // component keeps more warps resident.  BF_GSF_KERNEL=cta|warp overrides (experiments).
+    const char* force = getenv("BF_GSF_KERNEL");
+    const bool want_warp = force ? (strcmp(force, "warp") == 0) : (B >= 16 * h->nsm);
+    if (!want_warp) {
+      const int threads = std::max(32, ((a.M + 31) / 32) * 32);
+      k_gsf<M><<<B, threads, 0, s>>>(h->mc, a);
+    } else if (cpl == 1 && WORDS <= 96) k_gsf_warp<M, 1><<<gridw, 128, 0, s>>>(h->mc, a, B);
+    else if (cpl == 2 && 2 * WORDS <= 64) k_gsf_warp<M, 2><<<gridw, 128, 0, s>>>(h->mc, a, B);
+    else if (cpl <= 4 && 4 * WORDS <= 48) k_gsf_warp<M, 4><<<gridw, 128, 0, s>>>(h->mc, a, B);
+    else if (cpl <= 8 && 8 * WORDS <= 32) k_gsf_warp<M, 8><<<gridw, 128, 0, s>>>(h->mc, a, B);
+    else {
+      const int threads = std::max(32, ((a.M + 31) / 32) * 32);
+      k_gsf<M><<<B, threads, 0, s>>>(h->mc, a);
+    }
     LAUNCH_OK();
     h->launches += 1;
     return BF_OK;

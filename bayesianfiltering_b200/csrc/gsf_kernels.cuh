@@ -101,7 +101,7 @@ __device__ __forceinline__ void lu_solve(float* A, float* B) {
 // log N(y; yhat, S) with TFP's formula (Cholesky, forward substitution)
 template <int N>
 __device__ __forceinline__ float mvn_logpdf_chol(const float* S, const float* d) {
-  float L[N * N];
+  float L[N * N], iL[N];
   float logdet = 0.0f;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -110,8 +110,9 @@ __device__ __forceinline__ float mvn_logpdf_chol(const float* S, const float* d)
       float s = S[i * N + j];
 #pragma unroll
       for (int k = 0; k < j; ++k) s -= L[i * N + k] * L[j * N + k];
-      if (i == j) { L[i * N + i] = sqrtf(s); logdet += logf(L[i * N + i]); }
-      else L[i * N + j] = s / L[j * N + j];
+      // pivot: L_ii = sqrt(s), 1/L_ii = rsqrt(s) (2 ulp), log L_ii = log(s)/2: no division, one log
+      if (i == j) { iL[i] = rsqrtf(s); L[i * N + i] = s * iL[i]; logdet += 0.5f * logf(s); }
+      else L[i * N + j] = s * iL[j];
     }
   }
   float ss = 0.0f, z[N];
@@ -120,7 +121,7 @@ __device__ __forceinline__ float mvn_logpdf_chol(const float* S, const float* d)
     float s = d[i];
 #pragma unroll
     for (int j = 0; j < i; ++j) s -= L[i * N + j] * z[j];
-    z[i] = s / L[i * N + i];
+    z[i] = s * iL[i];
     ss += z[i] * z[i];
   }
   return -0.5f * ss - logdet - 0.5f * (float)N * 1.8378770664093453f;
@@ -320,5 +321,124 @@ __global__ void k_gsf(const __grid_constant__ ModelConst mc, const __grid_consta
     for (int i = 0; i < DX; ++i) a.carry_m[bm * DX + i] = m[i];
 #pragma unroll
     for (int i = 0; i < DX * DX; ++i) a.carry_P[bm * DX * DX + i] = P[i];
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Same filter, ONE WARP per trial, CPL components per lane (component c = lane + 32 j).  For the small state
+// dimensions of the reference's experiments a component's (w, mean, cov) is a handful of registers, so a lane can
+// carry several: the max and the sum across the mixture are then plain warp shuffles (no shared memory, no CTA
+// barrier), amortised over CPL components, and the CPL independent EKFs give each thread instruction-level
+// parallelism.  A CTA = 4 warps = 4 trials.  Used when M <= 32 CPL fits the register budget (bfilt_api.cu).
+template <class Mo, int CPL>
+__global__ void __launch_bounds__(128)
+k_gsf_warp(const __grid_constant__ ModelConst mc, const __grid_constant__ GsfArgs a, int B) {
+  constexpr int DX = Mo::DX, DQ = Mo::DQ, DY = Mo::DY;
+  const int M = a.M, T = a.T, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= B) return;                                   // whole warp; no CTA-level barrier below
+
+  float GQG[DX * DX];                                   // F_q Q F_q^T, F_q constant for every registered model
+  {
+    float x0[DX], Fq[DX * DQ], FQ[DX * DQ];
+#pragma unroll
+    for (int i = 0; i < DX; ++i) x0[i] = mc.m0[i];
+    Mo::Fq(x0, mc.q0, 0.0f, mc, Fq);
+    mm<DX, DQ, DQ>(Fq, mc.Q, FQ);
+    mmt<DX, DQ, DX>(FQ, Fq, GQG);
+  }
+  const float jitter = (a.flags & BF_GSF_NO_JITTER) ? 0.0f : 1e-6f;
+  const bool cov_plus_p = (a.flags & BF_GSF_COV_PLUS_P) != 0;
+
+  float w[CPL], m[CPL][DX], P[CPL][DX * DX];
+  bool act[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    act[j] = c < M;
+    const size_t bm = (size_t)b * M + (act[j] ? c : 0);
+    if (a.resume) {
+      w[j] = act[j] ? a.carry_w[bm] : 0.0f;
+#pragma unroll
+      for (int i = 0; i < DX; ++i) m[j][i] = a.carry_m[bm * DX + i];
+#pragma unroll
+      for (int i = 0; i < DX * DX; ++i) P[j][i] = a.carry_P[bm * DX * DX + i];
+    } else {
+      w[j] = act[j] ? (a.init_weights ? a.init_weights[bm] : 1.0f / (float)M) : 0.0f;
+#pragma unroll
+      for (int i = 0; i < DX; ++i) m[j][i] = a.init_means[bm * DX + i];
+#pragma unroll
+      for (int i = 0; i < DX * DX; ++i) P[j][i] = a.init_covs ? a.init_covs[bm * DX * DX + i] : mc.P0[i];
+      if (a.flags & BF_GSF_PREDICT_FIRST) ekf_predict<Mo>(m[j], P[j], a.inputs ? a.inputs[0] : 0.0f, mc, GQG, cov_plus_p);
+    }
+  }
+
+  const float* yrow = a.emissions + (size_t)(a.emissions_per_trial ? b : 0) * T * DY;
+  for (int t = 0; t < T; ++t) {
+    float y[DY];
+#pragma unroll
+    for (int k = 0; k < DY; ++k) y[k] = yrow[(size_t)t * DY + k];
+    const float u = a.inputs ? a.inputs[t] : 0.0f;
+    const size_t bt = (size_t)b * T + t;
+
+    float ll[CPL], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      ll[j] = ekf_condition<Mo>(m[j], P[j], y, u, mc, jitter);
+      if (!act[j]) ll[j] = -INFINITY;
+      mx = fmaxf(mx, ll[j]);
+      if (act[j]) {
+        const size_t btm = bt * M + lane + 32 * j;
+        if (a.out_means) store_vec<DX>(a.out_means + btm * DX, m[j]);
+        if (a.out_covs) store_vec<DX * DX>(a.out_covs + btm * DX * DX, P[j]);
+      }
+    }
+    // lls -= max ; w = exp(lls) * w ; w /= sum(w)       (inference.py:347-350)
+    mx = warp_max(mx);
+    float z = 0.0f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { w[j] = act[j] ? expf(ll[j] - mx) * w[j] : 0.0f; z += w[j]; }
+    const float Z = warp_sum(z);
+    const float rZ = 1.0f / Z;
+    float mix[DX];
+#pragma unroll
+    for (int k = 0; k < DX; ++k) mix[k] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      w[j] = __fmul_rn(w[j], rZ);
+      if (act[j] && a.out_weights) a.out_weights[bt * M + lane + 32 * j] = w[j];
+#pragma unroll
+      for (int k = 0; k < DX; ++k) mix[k] += w[j] * m[j][k];
+    }
+    if (lane == 0 && a.out_loglik) a.out_loglik[bt] = mx + logf(Z);
+    if (a.out_mix_mean) {
+#pragma unroll
+      for (int k = 0; k < DX; ++k) mix[k] = warp_sum(mix[k]);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < DX; ++k) a.out_mix_mean[bt * DX + k] = mix[k];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      ekf_predict<Mo>(m[j], P[j], u, mc, GQG, cov_plus_p);
+      if (act[j]) {
+        const size_t btm = bt * M + lane + 32 * j;
+        if (a.out_pred_means) store_vec<DX>(a.out_pred_means + btm * DX, m[j]);
+        if (a.out_pred_covs) store_vec<DX * DX>(a.out_pred_covs + btm * DX * DX, P[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    if (act[j]) {
+      const size_t bm = (size_t)b * M + lane + 32 * j;
+      a.carry_w[bm] = w[j];
+#pragma unroll
+      for (int i = 0; i < DX; ++i) a.carry_m[bm * DX + i] = m[j][i];
+#pragma unroll
+      for (int i = 0; i < DX * DX; ++i) a.carry_P[bm * DX * DX + i] = P[j][i];
+    }
   }
 }

@@ -13,15 +13,16 @@
 struct UngmModel {
   static constexpr int DX = 1, DQ = 1, DY = 1, DR = 1;
   __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
-    float xx = x[0];
-    o[0] = c.theta[0] * xx + c.theta[1] * xx / (1.0f + xx * xx) + c.theta[2] * u + q[0];
+    const float xx = x[0];
+    const float inv = __frcp_rn(1.0f + xx * xx);          // correctly rounded reciprocal, shared with Fx below
+    o[0] = c.theta[0] * xx + c.theta[1] * xx * inv + c.theta[2] * u + q[0];
   }
   __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
     o[0] = c.theta[3] * x[0] + c.theta[4] * x[0] * x[0] + r[0];
   }
   __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
-    float x2 = x[0] * x[0], den = 1.0f + x2;
-    J[0] = c.theta[0] + c.theta[1] * (1.0f - x2) / (den * den);
+    const float x2 = x[0] * x[0], inv = __frcp_rn(1.0f + x2);
+    J[0] = c.theta[0] + c.theta[1] * (1.0f - x2) * inv * inv;
   }
   __device__ __forceinline__ static void Fq(const float* x, const float* q, float u, const ModelConst& c, float* J) { J[0] = 1.0f; }
   __device__ __forceinline__ static void Hx(const float* x, const float* r, float u, const ModelConst& c, float* J) {

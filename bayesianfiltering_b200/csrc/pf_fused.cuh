@@ -2,7 +2,7 @@
 // steps of gaussfiltax/inference.py:1330-1366 with the particle state streamed through HBM (sm_100a).
 //
 // Grid = every co-resident CTA of the device (cooperative launch).  A CTA owns a contiguous range of tiles
-// (NWARPS*128 particles, the unit of the canonical summation tree); inside it every WARP owns a contiguous run
+// (2048 particles, the unit of the canonical summation tree); inside it every WARP owns a contiguous run
 // of chunks (128 particles, 4 per lane) and works through them on its own -- the same 4 particles belong to the
 // same thread in every phase, and no phase has a CTA barrier inside its loop.  A step is
 //
@@ -38,7 +38,9 @@
 
 namespace cg = cooperative_groups;
 
-#define PF_FUSED_WARPS 16                   // 512 threads, 2 CTAs per SM, tiles of 2048 particles
+#define PF_FUSED_TILE_CHUNKS 16             // a tile = 16 chunks = 2048 particles: the unit whose sums one CTA scans
+#define PF_FUSED_WARPS 16                   // warps per CTA
+#define PF_FUSED_CTAS_PER_SM 2              // 2 x 512 threads per SM (64 registers per thread)
 #define PF_FUSED_WINCAP 512                 // floats of tau a warp stages in shared memory for one chunk of 128 slots
 
 struct PfFusedArgs {
@@ -241,23 +243,24 @@ __device__ __forceinline__ void load_state_cg(const float* base, size_t i, float
   }
 }
 
-template <class M, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 2048 / (NWARPS * 32) > 2 ? 2 : 2048 / (NWARPS * 32))
+template <class M, int CW, int CTAS_PER_SM>
+__global__ void __launch_bounds__(CW * 32, CTAS_PER_SM)
 k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFusedArgs a) {
   constexpr int DX = M::DX, DQ = M::DQ, DY = M::DY;
-  constexpr int NT = NWARPS * 32, TILE = NWARPS * 128, WINCAP = PF_FUSED_WINCAP;
+  constexpr int TW = PF_FUSED_TILE_CHUNKS;              // chunks per tile: a level of the canonical tree, not a CTA shape
+  constexpr int NT = CW * 32, TILE = TW * 128, WINCAP = PF_FUSED_WINCAP;
   cg::grid_group grid = cg::this_grid();
-  // dynamic shared memory (words): [NWARPS*tpc] chunk tree sums | [NWARPS*tpc] first weight of each chunk |
-  // [2*tpc] clamp interval of each tile | [NWARPS*tpc+2] tau window starts | [NWARPS*WINCAP] tau windows (phase A),
+  // dynamic shared memory (words): [TW*tpc] chunk tree sums | [TW*tpc] first weight of each chunk |
+  // [2*tpc] clamp interval of each tile | [TW*tpc+2] tau window starts | [CW*WINCAP] tau windows (phase A),
   // aliased by CTA 0's scan scratch (C1)
   extern __shared__ __align__(16) float s_dyn[];
   const int tpc = a.tiles_per_cta;
   float* s_wsum = s_dyn;
-  float* s_v0 = s_wsum + NWARPS * tpc;
-  float* s_meta_f = s_v0 + NWARPS * tpc;
-  int* s_lo = reinterpret_cast<int*>(s_meta_f + 2 * tpc);       // [NWARPS*tpc + 2] tau window start of each chunk
-  float* s_win = reinterpret_cast<float*>(s_lo + NWARPS * tpc + 2);
-  __shared__ PfPartial s_part[NWARPS];
+  float* s_v0 = s_wsum + TW * tpc;
+  float* s_meta_f = s_v0 + TW * tpc;
+  int* s_lo = reinterpret_cast<int*>(s_meta_f + 2 * tpc);       // [TW*tpc + 2] tau window start of each chunk
+  float* s_win = reinterpret_cast<float*>(s_lo + TW * tpc + 2);
+  __shared__ PfPartial s_part[CW];
   __shared__ StepStats s_stats;
   __shared__ int s_ctr[4];                            // chunk queues of phases A / B / C2
 
@@ -267,7 +270,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   const int tile1 = min(tile0 + tpc, a.ntiles);
   // chunks (128 consecutive particles) of this CTA: chunk q starts at particle cta_base + 128 q; warps take them
   // from a shared queue (the SM's warp arbiter favours some warps: a static split leaves the others as a tail)
-  const int nchunk_cta = NWARPS * (tile1 - tile0);
+  const int nchunk_cta = TW * (tile1 - tile0);
   const int cta_base = tile0 * TILE;
   const int nchunk_valid = max(0, min(nchunk_cta, (N - cta_base + 127) / 128));
 #ifdef BF_DYNAMIC_CHUNKS
@@ -282,11 +285,11 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     return __shfl_sync(BF_FULL, q, 0);
   };
 #else
-  // Static round-robin: warp w takes chunks w, w + NWARPS, ... -- the order in which a thread accumulates its
+  // Static round-robin: warp w takes chunks w, w + CW, ... -- the order in which a thread accumulates its
   // statistics is then fixed, so a run is bit-reproducible (and a run split in time equals the unsplit run).
   int turn[3] = {0, 0, 0};
-  auto next_chunk = [&](int which) -> int { return warp + NWARPS * turn[which]++; };
-  auto next_chunks4 = [&](int which) -> int { return 4 * (warp + NWARPS * turn[which]++); };
+  auto next_chunk = [&](int which) -> int { return warp + CW * turn[which]++; };
+  auto next_chunks4 = [&](int which) -> int { return 4 * (warp + CW * turn[which]++); };
 #endif
   if (tid < 4) s_ctr[tid] = 0;
   __syncthreads();
@@ -346,7 +349,13 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       const int lo = s_lo[q], wn = s_lo[q + 1] - lo;             // warp-uniform
       if (wn <= WINCAP) {
         float* win = s_win + warp * WINCAP;
-        for (int i = lane; i < wn; i += 32) win[i] = tau[lo + i];
+        for (int i0 = 0; i0 < wn; i0 += 128) {          // four independent loads in flight per lane
+          float tv[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) { const int i = i0 + lane + 32 * m; tv[m] = (i < wn) ? tau[lo + i] : 0.0f; }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) { const int i = i0 + lane + 32 * m; if (i < wn) win[i] = tv[m]; }
+        }
         __syncwarp();
         // a lane's four answers lie between its first answer and the next lane's first answer
         int p = lower_bound_window(win, 0, wn, r[0]);
@@ -404,19 +413,18 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         for (int k = 0; k < 4; ++k) if (k < nv) o[k] = anc[k];
       }
       float z[4][DQ];
+#ifdef BF_EXP_NORNG
+      for (int k = 0; k < 4; ++k) for (int c = 0; c < DQ; ++c) z[k][c] = 0.1f * (float)(k + c);
+#else
       if (!a.noise) philox_quad_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)a.trial, (uint32_t)(base >> 2), z);
+#endif
       float llv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (k < nv) {
           const int i = base + k;
           float x[DX], qn[DQ], xt[DX];
-#ifdef BF_EXP_NOGATHER
-          load_state_cg<DX>(x_prev, (size_t)i, x);
-          if (anc[k] == -12345) x[0] += 1.0f;
-#else
           load_state_cg<DX>(x_prev, (size_t)anc[k], x);
-#endif
           if (t > 0 && a.out_particles) store_state<DX>(a.out_particles + (size_t)(t - 1) * N * DX, (size_t)i, x);
           if (a.noise) {
             const float* np_ = a.noise + (size_t)t * a.B * N * DQ + (size_t)i * DQ;
@@ -434,7 +442,11 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
           M::f(x, qn, u_in, mc, xt);
           store_state<DX>(x_cur, (size_t)i, xt);
           if (a.out_propagated) store_state<DX>(a.out_propagated + (size_t)t * N * DX, (size_t)i, xt);
+#ifdef BF_EXP_NOLL
+          const float ll = -0.5f * xt[0] * xt[0];
+#else
           const float ll = emission_log_prob<M>(xt, y, u_in, mc);
+#endif
           llv[k] = ll;
           acc.add(ll, w_uni ? invN : a.W[i], xt);
         }
@@ -454,7 +466,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     __syncthreads();
     if (warp == 0) {
       acc.init();
-      if (lane < NWARPS) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
+      if (lane < CW) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
       acc.warp_reduce();
       if (lane == 0) {
         PfPartial* p = &a.partials[(size_t)(t & 1) * G + blockIdx.x];
@@ -488,7 +500,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     __syncthreads();
     if (warp == 0) {
       acc.init();
-      if (lane < NWARPS) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
+      if (lane < CW) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
       acc.warp_reduce();
       if (lane == 0) {
         StepStats st;
@@ -565,22 +577,22 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       w_uni = false; gather = false; lap(1); continue;
     }
     __syncthreads();
-    for (int i = tid; i < tile1 - tile0; i += NT) {   // tile sums: the top log2(NWARPS) levels of the tile's tree
-      float y16[NWARPS];
+    for (int i = tid; i < tile1 - tile0; i += NT) {   // tile sums: the top log2(TW) levels of the tile's tree
+      float y16[TW];
 #pragma unroll
-      for (int k = 0; k < NWARPS; ++k) y16[k] = s_wsum[i * NWARPS + k];
+      for (int k = 0; k < TW; ++k) y16[k] = s_wsum[i * TW + k];
 #pragma unroll
-      for (int w = NWARPS / 2; w >= 1; w >>= 1)
+      for (int w = TW / 2; w >= 1; w >>= 1)
 #pragma unroll
         for (int k = 0; k < w; ++k) y16[k] = __fadd_rn(y16[2 * k], y16[2 * k + 1]);
       a.tilesum[tile0 + i] = y16[0];
-      a.V[tile0 + i] = s_v0[i * NWARPS];
+      a.V[tile0 + i] = s_v0[i * TW];
     }
     grid.sync();
     lap(1);
 
     // ------------------------------------------------------------------ phase C1 (CTA 0)
-    if (blockIdx.x == 0) cta_exclusive_scan<NWARPS>(a.tilesum, a.Etile, a.ntiles, s_win);
+    if (blockIdx.x == 0) cta_exclusive_scan<CW>(a.tilesum, a.Etile, a.ntiles, s_win);
     grid.sync();
     lap(2);
 
@@ -609,17 +621,17 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         w4[j] = *reinterpret_cast<const float4*>(a.E + cta_base + 128 * (qb + j) + lane * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int q = qb + j, tl = q / NWARPS, wpos = q % NWARPS, tile = tile0 + tl;
+        const int q = qb + j, tl = q / TW, wpos = q % TW, tile = tile0 + tl;
         const int base = cta_base + 128 * q + lane * 4;
         float e[4], tau[4];
         const float v[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};
         float4 out;
         if (use_tau) {
-          chunk_scan<NWARPS, true>(v, wpos, s_wsum + tl * NWARPS, s_v0 + tl * NWARPS, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]),
+          chunk_scan<TW, true>(v, wpos, s_wsum + tl * TW, s_v0 + tl * TW, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]),
                                    s_meta_f[2 * tl], s_meta_f[2 * tl + 1], min(TILE, N), e, tau);
           out = make_float4(tau[0], tau[1], tau[2], tau[3]);
         } else {
-          chunk_scan<NWARPS, false>(v, wpos, s_wsum + tl * NWARPS, s_v0 + tl * NWARPS, __ldcg(&a.Etile[tile]), 0.0f, 0.0f, 0.0f, 0, e, tau);
+          chunk_scan<TW, false>(v, wpos, s_wsum + tl * TW, s_v0 + tl * TW, __ldcg(&a.Etile[tile]), 0.0f, 0.0f, 0.0f, 0, e, tau);
           out = make_float4(e[0], e[1], e[2], e[3]);
         }
 #pragma unroll
