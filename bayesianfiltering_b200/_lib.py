@@ -12,6 +12,7 @@ MODEL_UNGM, MODEL_BOT, MODEL_L63, MODEL_L96, MODEL_LG, MODEL_SIN1D = 1, 2, 3, 4,
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 PATH_AUTO, PATH_RESIDENT, PATH_STREAMED = 0, 1, 2
 GSF_PREDICT_FIRST, GSF_NO_JITTER, GSF_COV_PLUS_P = 1, 2, 4
+SHARD_BLOB_BYTES, NCCL_ID_BYTES = 256, 128
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)
@@ -26,7 +27,7 @@ class ModelDesc(C.Structure):
 class PfConfig(C.Structure):
     _fields_ = [("num_particles", C.c_int64), ("num_trials", C.c_int32), ("ess_threshold", C.c_float),
                 ("resampler", C.c_int32), ("path", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32)]
 
 
 class PfIO(C.Structure):
@@ -61,6 +62,10 @@ SYMBOLS = [
     ("bf_pf_kernel_launches", C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("bf_pf_phase_times", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),
     ("bf_pf_destroy", C.c_int, [C.c_void_p]),
+    ("bf_pf_shard_export", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("bf_pf_shard_import", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("bf_nccl_unique_id", C.c_int, [C.c_void_p]),
+    ("bf_pf_shard_comm_init", C.c_int, [C.c_void_p, C.c_void_p]),
     ("bf_gsf_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(GsfConfig), C.POINTER(C.c_void_p)]),
     ("bf_gsf_run", C.c_int, [C.c_void_p, C.POINTER(GsfIO), C.c_void_p]),
     ("bf_gsf_run_host", C.c_int, [C.c_void_p, C.POINTER(GsfIO)]),

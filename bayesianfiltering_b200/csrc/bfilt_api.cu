@@ -10,6 +10,8 @@
 #include <vector>
 #include <new>
 #include <algorithm>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "../../include/bfilt.h"
 #include "common.cuh"
 #include "models.cuh"
@@ -121,7 +123,7 @@ static cudaError_t pool_setup(int device) {
 }
 
 struct DevBuf {
-  void* p = nullptr; size_t cap = 0;
+  void* p = nullptr; size_t cap = 0; bool plain = false;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
     release();
@@ -130,8 +132,15 @@ struct DevBuf {
     if (e == cudaSuccess) cap = bytes; else p = nullptr;
     return e;
   }
+  cudaError_t ensure_plain(size_t bytes) {         // cudaMalloc: CUDA IPC cannot export pool memory
+    if (bytes <= cap) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) { cap = bytes; plain = true; } else p = nullptr;
+    return e;
+  }
   // callers synchronise the device first (bf_*_destroy), or the buffer has not been used yet
-  void release() { if (p) cudaFreeAsync(p, (cudaStream_t)0); p = nullptr; cap = 0; }
+  void release() { if (p) { if (plain) cudaFree(p); else cudaFreeAsync(p, (cudaStream_t)0); } p = nullptr; cap = 0; plain = false; }
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
@@ -144,7 +153,44 @@ extern "C" int bf_trim_memory(int32_t device) {
   return BF_OK;
 }
 
+// ------------------------------------------------------------------------------------------ NCCL, loaded on demand
+// (libbfilt.so must load on machines without NCCL; the sharded filter is the only user)
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);     // the copy torch already loaded, if any
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return nullptr;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  api.AllGather = (decltype(api.AllGather))dlsym(lib, "ncclAllGather");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(lib, "ncclAllReduce");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.AllReduce && api.CommDestroy && api.GetErrorString;
+  return api.ok ? &api : nullptr;
+}
+#define NCCL_OK(expr)                                                                              \
+  do {                                                                                             \
+    ncclResult_t _r = (expr);                                                                      \
+    if (_r != ncclSuccess) return fail(BF_ECOMM, "%s failed: %s (%s:%d)", #expr, nccl_api()->GetErrorString(_r), __FILE__, __LINE__); \
+  } while (0)
+
 // ========================================================================================== particle filter
+struct ShardBlob { cudaIpcMemHandle_t tau, xa, xb; int rank, grid, pad[14]; };
+static_assert(sizeof(ShardBlob) <= BF_SHARD_BLOB_BYTES, "blob too large");
+
 struct bf_pf_s {
   ModelConst mc;
   bf_pf_config cfg;
@@ -158,6 +204,12 @@ struct bf_pf_s {
   // streamed scratch
   DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats, phase_ns, V;
   int ntiles;
+  // sharded filter
+  int world = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  bool peers_ready = false;
+  void* peer_ptr[3][8] = {};          // imported tau / xa / xb of every rank (own entries = own buffers)
+  DevBuf peer_tab, barrier_buf;       // device tables [3][8] of the pointers above; 1 float for the step barrier
   // host-call staging
   DevBuf hbuf[24];
 };
@@ -172,6 +224,15 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
   int rc = build_model_const(model, &h->mc);
   if (rc) { delete h; return rc; }
   h->cfg = *cfg; h->N = (int)cfg->num_particles; h->B = cfg->num_trials; h->launches = 0; h->have_carry = false;
+  h->world = cfg->shard_world > 1 ? cfg->shard_world : 1;
+  h->rank = h->world > 1 ? cfg->shard_rank : 0;
+  if (h->world > 1) {
+    const int w = h->world, n = h->N;
+    if ((w & (w - 1)) || w > 8 || h->rank < 0 || h->rank >= w) { delete h; return fail(BF_EINVAL, "shard_world=%d / shard_rank=%d: need a power of two <= 8", w, h->rank); }
+    if ((n & (n - 1)) || n < PF_FUSED_TILE_CHUNKS * 128) { delete h; return fail(BF_EINVAL, "sharded filter: num_particles per rank (%d) must be a power of two >= %d", n, PF_FUSED_TILE_CHUNKS * 128); }
+    if (h->B != 1 || cfg->path == BF_PATH_RESIDENT) { delete h; return fail(BF_EINVAL, "sharded filter: one trial, streamed path"); }
+    if ((int64_t)n * w > ((int64_t)1 << 30)) { delete h; return fail(BF_EINVAL, "sharded filter: more than 2^30 particles in total"); }
+  }
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { delete h; return fail(BF_ECUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e)); }
   if ((e = pool_setup(cfg->device)) != cudaSuccess) { delete h; return fail(BF_ECUDA, "memory pool setup: %s", cudaGetErrorString(e)); }
@@ -191,23 +252,31 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
   if (cfg->path == BF_PATH_RESIDENT) {
     if (!fits) { delete h; return fail(BF_EINVAL, "N=%d does not fit the shared-memory resident path (%zu bytes)", h->N, h->resident_smem); }
     h->path = BF_PATH_RESIDENT;
-  } else if (cfg->path == BF_PATH_STREAMED) h->path = BF_PATH_STREAMED;
+  } else if (cfg->path == BF_PATH_STREAMED || h->world > 1) h->path = BF_PATH_STREAMED;
   else h->path = fits ? BF_PATH_RESIDENT : BF_PATH_STREAMED;
   const size_t nx = (size_t)h->B * h->N * h->mc.dx;
   if (h->carry_x.ensure(nx * 4) || h->carry_w.ensure((size_t)h->B * h->N * 4) || h->carry_uniform.ensure((size_t)h->B * 4) ||
-      h->carry_stats.ensure((size_t)h->B * sizeof(StepStats))) {
+      h->carry_stats.ensure((size_t)2 * h->B * sizeof(StepStats))) {
     bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the carry failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (h->path == BF_PATH_STREAMED) {
     constexpr int FT = PF_FUSED_TILE_CHUNKS * 128;
-    h->ntiles = (int)(((int64_t)h->N + 1 + FT - 1) / FT);
+    const bool sh = h->world > 1;
+    h->ntiles = sh ? h->N / FT : (int)(((int64_t)h->N + 1 + FT - 1) / FT);      // a shard has no "leaf N" of its own
     const size_t npad = (size_t)h->ntiles * FT;
-    if (h->xa.ensure((size_t)h->N * h->mc.dx * 4) || h->xb.ensure((size_t)h->N * h->mc.dx * 4) || h->LL.ensure(npad * 4) ||
-        h->E.ensure(npad * 4) || h->tilesum.ensure((size_t)h->ntiles * 4) || h->Etile.ensure(((size_t)h->ntiles + 1) * 4) ||
-        h->V.ensure(((size_t)h->ntiles + 4) * 4)) {
+    const size_t ntg = sh ? (size_t)h->world * h->ntiles + 1 : (size_t)h->ntiles; // tiles of the whole filter
+    const size_t xb_ = (size_t)h->N * h->mc.dx * 4;
+    cudaError_t ea = sh ? h->xa.ensure_plain(xb_) : h->xa.ensure(xb_);
+    if (!ea) ea = sh ? h->xb.ensure_plain(xb_) : h->xb.ensure(xb_);
+    if (!ea) ea = sh ? h->E.ensure_plain(npad * 4) : h->E.ensure(npad * 4);
+    if (ea || h->LL.ensure(npad * 4) || h->tilesum.ensure((ntg + 4) * 4) || h->Etile.ensure((ntg + 4) * 4) || h->V.ensure((ntg + 4) * 4) ||
+        (sh && (h->peer_tab.ensure(3 * 8 * sizeof(void*)) || h->barrier_buf.ensure(64)))) {
       bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the streamed scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     cudaMemset(h->LL.p, 0, npad * 4);
+    cudaMemset(h->tilesum.p, 0, (ntg + 4) * 4);
+    cudaMemset(h->V.p, 0, (ntg + 4) * 4);
+    if (sh) cudaMemset(h->barrier_buf.p, 0, 64);
     if (h->phase_ns.ensure(8 * sizeof(unsigned long long))) { bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc failed"); }
     cudaMemset(h->phase_ns.p, 0, 8 * sizeof(unsigned long long));
   }
@@ -219,11 +288,77 @@ extern "C" int bf_pf_destroy(bf_pf_handle h) {
   if (!h) return BF_OK;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();              // as cudaFree would: nothing enqueued by this handle may still be running
+  if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
+  if (h->peers_ready)
+    for (int k = 0; k < 3; ++k)
+      for (int r = 0; r < h->world; ++r)
+        if (r != h->rank && h->peer_ptr[k][r]) cudaIpcCloseMemHandle(h->peer_ptr[k][r]);
   DevBuf* all[] = {&h->carry_x, &h->carry_w, &h->carry_uniform, &h->carry_stats, &h->xa, &h->xb, &h->LL, &h->E, &h->anc,
-                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V};
+                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V, &h->peer_tab, &h->barrier_buf};
   for (DevBuf* b : all) b->release();
   for (DevBuf& b : h->hbuf) b.release();
   delete h;
+  return BF_OK;
+}
+
+extern "C" int bf_pf_shard_export(bf_pf_handle h, void* blob) {
+  if (!h || !blob) return fail(BF_EINVAL, "NULL argument");
+  if (h->world < 2) return fail(BF_EINVAL, "handle is not sharded");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  ShardBlob b; memset(&b, 0, sizeof b);
+  CUDA_OK(cudaIpcGetMemHandle(&b.tau, h->E.p));
+  CUDA_OK(cudaIpcGetMemHandle(&b.xa, h->xa.p));
+  CUDA_OK(cudaIpcGetMemHandle(&b.xb, h->xb.p));
+  b.rank = h->rank;
+  memset(blob, 0, BF_SHARD_BLOB_BYTES);
+  memcpy(blob, &b, sizeof b);
+  return BF_OK;
+}
+
+extern "C" int bf_pf_shard_import(bf_pf_handle h, const void* blobs) {
+  if (!h || !blobs) return fail(BF_EINVAL, "NULL argument");
+  if (h->world < 2) return fail(BF_EINVAL, "handle is not sharded");
+  if (h->peers_ready) return fail(BF_EINVAL, "peers already imported");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  for (int r = 0; r < h->world; ++r) {
+    ShardBlob b;
+    memcpy(&b, (const char*)blobs + (size_t)r * BF_SHARD_BLOB_BYTES, sizeof b);
+    if (b.rank != r) return fail(BF_EINVAL, "blob %d comes from rank %d: pass the blobs in rank order", r, b.rank);
+    if (r == h->rank) {
+      h->peer_ptr[0][r] = h->E.p; h->peer_ptr[1][r] = h->xa.p; h->peer_ptr[2][r] = h->xb.p;
+    } else {
+      CUDA_OK(cudaIpcOpenMemHandle(&h->peer_ptr[0][r], b.tau, cudaIpcMemLazyEnablePeerAccess));
+      CUDA_OK(cudaIpcOpenMemHandle(&h->peer_ptr[1][r], b.xa, cudaIpcMemLazyEnablePeerAccess));
+      CUDA_OK(cudaIpcOpenMemHandle(&h->peer_ptr[2][r], b.xb, cudaIpcMemLazyEnablePeerAccess));
+    }
+  }
+  CUDA_OK(cudaMemcpy(h->peer_tab.p, h->peer_ptr, sizeof h->peer_ptr, cudaMemcpyHostToDevice));
+  h->peers_ready = true;
+  return BF_OK;
+}
+
+extern "C" int bf_nccl_unique_id(void* id) {
+  if (!id) return fail(BF_EINVAL, "NULL argument");
+  NcclApi* nc = nccl_api();
+  if (!nc) return fail(BF_ECOMM, "libnccl.so.2 could not be loaded");
+  ncclUniqueId uid;
+  NCCL_OK(nc->GetUniqueId(&uid));
+  static_assert(sizeof(ncclUniqueId) <= BF_NCCL_ID_BYTES, "id size");
+  memset(id, 0, BF_NCCL_ID_BYTES);
+  memcpy(id, &uid, sizeof uid);
+  return BF_OK;
+}
+
+extern "C" int bf_pf_shard_comm_init(bf_pf_handle h, const void* id) {
+  if (!h || !id) return fail(BF_EINVAL, "NULL argument");
+  if (h->world < 2) return fail(BF_EINVAL, "handle is not sharded");
+  if (h->comm) return fail(BF_EINVAL, "communicator already initialised");
+  NcclApi* nc = nccl_api();
+  if (!nc) return fail(BF_ECOMM, "libnccl.so.2 could not be loaded");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  NCCL_OK(nc->CommInitRank(&h->comm, h->world, uid, h->rank));
   return BF_OK;
 }
 
@@ -278,7 +413,8 @@ struct PfRun {
     const int N = h->N, B = h->B, T = io->T;
     auto kern = k_pf_fused<M, NW, PF_FUSED_CTAS_PER_SM>;
     const int ntiles = h->ntiles;
-    const int nchunk = (ntiles + 1 + NW * 128 - 1) / (NW * 128);      // chunks of the one-CTA scan of the tile sums
+    const int ntiles_scan = h->world > 1 ? h->world * ntiles + 1 : ntiles;       // the scan covers the whole filter's tiles
+    const int nchunk = (ntiles_scan + 1 + NW * 128 - 1) / (NW * 128); // chunks of the one-CTA scan of the tile sums
     // shared memory depends on tiles_per_cta, which depends on the grid, which depends on shared memory: iterate
     int grid = 1, tpc = ntiles;
     size_t smem = 0;
@@ -300,10 +436,18 @@ struct PfRun {
       CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
       if (grid > per_sm * h->nsm) return fail(BF_ECUDA, "cooperative grid of %d CTAs does not fit (%d per SM)", grid, per_sm);
     }
-    CUDA_OK(h->partials.ensure((size_t)2 * grid * sizeof(PfPartial)));
+    const int world = h->world, rank = h->rank;
+    CUDA_OK(h->partials.ensure((size_t)2 * world * grid * sizeof(PfPartial)));
     const int grid_s = (int)std::min<int64_t>(((int64_t)N + 255) / 256, (int64_t)h->nsm * 8);
-    int log2n = -1;
+    const int Ng = N * world;
+    int log2n = -1, log2ng = -1;
     if ((N & (N - 1)) == 0) { log2n = 0; while ((1 << log2n) < N) ++log2n; }
+    if ((Ng & (Ng - 1)) == 0) { log2ng = 0; while ((1 << log2ng) < Ng) ++log2ng; }
+    const int ntiles_g = world > 1 ? world * ntiles + 1 : ntiles;
+    if (world > 1) {
+      if (!h->peers_ready || !h->comm) return fail(BF_EINVAL, "sharded filter: bf_pf_shard_import and bf_pf_shard_comm_init must be called first");
+      if (io->resume || io->t_offset != 0) return fail(BF_EINVAL, "sharded filter: resume / t_offset are not supported");
+    }
     for (int b = 0; b < B; ++b) {
       float* cx = h->carry_x.as<float>() + (size_t)b * N * DX;
       float* cw = h->carry_w.as<float>() + (size_t)b * N;
@@ -318,7 +462,7 @@ struct PfRun {
       if (io->resume) a.x_init = cx;
       else if (io->init_particles) a.x_init = io->init_particles + (size_t)b * N * DX;
       else {
-        k_init_particles<DX><<<grid_s, 256, 0, s>>>(h->mc, cx, N, h->cfg.seed, b);
+        k_init_particles<DX><<<grid_s, 256, 0, s>>>(h->mc, cx, N, h->cfg.seed, b, rank * N);
         LAUNCH_OK(); h->launches++;
         a.x_init = cx;
       }
@@ -327,10 +471,10 @@ struct PfRun {
       a.xbuf0 = h->xa.as<float>(); a.xbuf1 = h->xb.as<float>();
       a.W = cw; a.LL = h->LL.as<float>(); a.E = h->E.as<float>();
       a.tilesum = h->tilesum.as<float>(); a.Etile = h->Etile.as<float>();
-      a.V = h->V.as<float>(); a.total = h->V.as<float>() + ntiles + 1;
-      a.use_tau = (log2n >= 3) ? 1 : 0;
+      a.V = h->V.as<float>(); a.total = h->V.as<float>() + ntiles_g + 1;
+      a.use_tau = (log2ng >= 3 && log2n >= 0) ? 1 : 0;
       a.partials = h->partials.as<PfPartial>();
-      a.carry_stats = h->carry_stats.as<StepStats>() + b;
+      a.carry_stats = h->carry_stats.as<StepStats>() + 2 * b;
       a.noise = io->noise ? io->noise + (size_t)b * N * DQ : nullptr;
       a.res_u = io->resample_u ? (h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC ? io->resample_u + b : io->resample_u + (size_t)b * N)
                                : nullptr;
@@ -348,9 +492,56 @@ struct PfRun {
       a.final_particles = io->final_particles ? io->final_particles + (size_t)b * N * DX : nullptr;
       a.final_weights = io->final_weights ? io->final_weights + (size_t)b * N : nullptr;
       a.phase_ns = h->phase_ns.as<unsigned long long>();
-      void* params[] = {(void*)&h->mc, (void*)&a};
-      CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, s));
-      h->launches++;
+      a.world = world; a.rank = rank; a.goff = rank * N; a.Ng = Ng; a.log2ng = log2ng; a.log2ns = log2n;
+      a.tile_off = rank * (world > 1 ? ntiles : 0); a.ntiles_g = ntiles_g; a.phases = PF_PH_ALL;
+      if (world == 1) {
+        void* params[] = {(void*)&h->mc, (void*)&a};
+        CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, s));
+        h->launches++;
+        continue;
+      }
+      // ---- sharded filter: one launch per phase, the exchanges between them (see include/bfilt.h)
+      NcclApi* nc = nccl_api();
+      const float* const* tab = h->peer_tab.as<const float*>();
+      a.tau_peers = tab; a.xa_peers = tab + 8; a.xb_peers = tab + 16;
+      k_init_stats<<<1, 1, 0, s>>>(a.carry_stats, io->init_weights ? 0 : 1);
+      LAUNCH_OK(); h->launches++;
+      const size_t pf_floats = (size_t)grid * sizeof(PfPartial) / 4;
+      auto launch = [&](int phases, int t, int Tl) -> int {
+        PfFusedArgs p = a;
+        p.phases = phases; p.T = Tl; p.t_offset = t;
+        p.emissions = a.emissions + (size_t)t * DY;
+        p.inputs = a.inputs ? a.inputs + t : nullptr;
+        p.noise = a.noise ? a.noise + (size_t)t * B * N * DQ : nullptr;
+        p.res_u = a.res_u ? a.res_u + (size_t)t * B * (h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC ? 1 : N) : nullptr;
+        p.out_particles = a.out_particles ? a.out_particles + (size_t)t * N * DX : nullptr;
+        p.out_weights = a.out_weights ? a.out_weights + (size_t)t * N : nullptr;
+        p.out_propagated = a.out_propagated ? a.out_propagated + (size_t)t * N * DX : nullptr;
+        p.out_norm_weights = a.out_norm_weights ? a.out_norm_weights + (size_t)t * N : nullptr;
+        p.out_ancestors = a.out_ancestors ? a.out_ancestors + (size_t)t * N : nullptr;
+        p.out_mean = a.out_mean ? a.out_mean + (size_t)t * DX : nullptr;
+        p.out_loglik = a.out_loglik ? a.out_loglik + t : nullptr;
+        p.out_ess = a.out_ess ? a.out_ess + t : nullptr;
+        p.out_resampled = a.out_resampled ? a.out_resampled + t : nullptr;
+        void* params[] = {(void*)&h->mc, (void*)&p};
+        CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, s));
+        h->launches++;
+        return BF_OK;
+      };
+      int rc;
+      for (int t = 0; t < T; ++t) {
+        if ((rc = launch(PF_PH_A, t, 1))) return rc;
+        float* pbase = reinterpret_cast<float*>(a.partials) + (size_t)(t & 1) * world * pf_floats;
+        NCCL_OK(nc->AllGather(pbase + (size_t)rank * pf_floats, pbase, pf_floats, ncclFloat, h->comm, s));
+        if ((rc = launch(PF_PH_B, t, 1))) return rc;
+        NCCL_OK(nc->AllGather(a.tilesum + (size_t)rank * ntiles, a.tilesum, ntiles, ncclFloat, h->comm, s));
+        NCCL_OK(nc->AllGather(a.V + (size_t)rank * ntiles, a.V, ntiles, ncclFloat, h->comm, s));
+        if ((rc = launch(PF_PH_C, t, 1))) return rc;
+        // barrier: every rank's tau and particles of this step are complete before anyone's next step reads them
+        NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, s));
+      }
+      if ((rc = launch(PF_PH_FINAL, T, 0))) return rc;
+      NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, s));
     }
     return BF_OK;
   }

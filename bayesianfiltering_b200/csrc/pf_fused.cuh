@@ -69,7 +69,18 @@ struct PfFusedArgs {
   float* out_mean; float* out_loglik; float* out_ess; int* out_resampled;      // already offset to (trial, t=0)
   float* carry_x; float* final_particles; float* final_weights;               // carry_w is W
   unsigned long long* phase_ns;             // [5] accumulated wall time of phases A, B, C1, C2, final as seen by CTA 0
+  // ---- one filter sharded over `world` GPUs (power of two): this rank owns global particles [goff, goff + N).
+  // Every index that leaves the shard (resampling positions, ancestors, tiles of the summation tree, Philox
+  // counters) is GLOBAL; tau and the particle state of the peers are read through IPC-mapped pointers.
+  int world, rank, goff, Ng, log2ng, log2ns; // world = 1: Ng = N, goff = 0
+  int tile_off, ntiles_g;                    // global index of local tile 0; tiles of the whole filter (tilesum/Etile/V are global)
+  int phases;                                // PF_PH_* mask; PF_PH_ALL = the whole run in one launch (world = 1)
+  // device tables [world] (in global memory: indexing a kernel parameter dynamically would spill it to local memory)
+  const float* const* tau_peers;             // E of every rank (own entry = a.E)
+  const float* const* xa_peers; const float* const* xb_peers;   // xbuf0 / xbuf1 of every rank
 };
+
+enum { PF_PH_A = 1, PF_PH_B = 2, PF_PH_C = 4, PF_PH_FINAL = 8, PF_PH_ALL = 15 };
 
 // DQ standard normals for each of the 4 particles of quad `quad` (= particle index / 4): call k supplies
 // component k of all four.  Counter = (quad, trial, step, stream | k << 8).
@@ -293,66 +304,93 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #endif
   if (tid < 4) s_ctr[tid] = 0;
   __syncthreads();
-  const float invN = 1.0f / (float)N;
+  const int Ng = a.Ng;                                 // particles of the whole filter (= N unless sharded)
+  const float invN = 1.0f / (float)Ng;
   const int levels = bisect_levels(N);
   const bool use_tau = a.use_tau != 0;
+  const bool all_phases = a.phases == PF_PH_ALL;
+  const int ns_mask = (1 << (a.log2ns < 0 ? 0 : a.log2ns)) - 1;
+  // global accessors: entry j of the (virtual) global tau array, particle j of the previous step's state
+  auto tauG = [&](int j) -> float { return (a.world == 1) ? a.E[j] : a.tau_peers[j >> a.log2ns][j & ns_mask]; };
   const bool w_vec = (reinterpret_cast<size_t>(a.W) & 15) == 0;     // carry of trial b starts at b*N floats
   const bool use_win = use_tau && a.resampler == 1;      // sorted positions: windowed search
   // (i + u) / 2^k is an exact scaling: multiplying by 2^-k gives the same bits as the oracle's division
-  const float invn_pow2 = (a.log2n >= 0) ? __int_as_float((127 - a.log2n) << 23) : 0.0f;
+  const float invn_pow2 = (a.log2ng >= 0) ? __int_as_float((127 - a.log2ng) << 23) : 0.0f;
 
-  bool w_uni = a.resume ? (a.carry_stats->w_uniform != 0) : (a.w_uniform0 != 0);
-  bool gather = false;                                // the carry entering the call is materialised
+  // the carry entering the call: materialised particles (gather = false) for a whole run; for a single phase of a
+  // sharded step the host keeps carry_stats current between the launches
+  bool w_uni = (a.resume || !all_phases) ? (a.carry_stats->w_uniform != 0) : (a.w_uniform0 != 0);
+  bool gather = all_phases ? false : (a.carry_stats->flag != 0);
   const float* x_prev = a.x_init;
   float res_total = 0.0f, res_u0 = 0.0f;              // of the resampling being gathered
 
   auto position = [&](int slot, float u) -> float {
-    if (a.log2n >= 0)
+    if (a.log2ng >= 0)
       return (a.resampler == 1) ? __fmul_rn(res_total, __fmul_rn(__fadd_rn((float)slot, u), invn_pow2))
                                 : __fmul_rn(res_total, __fsub_rn(1.0f, u));
-    return resample_position(a.resampler, res_total, u, slot, N);
+    return resample_position(a.resampler, res_total, u, slot, Ng);
   };
 
   // Once per phase that gathers: total and the systematic uniform.  ts = local step whose resampling is gathered.
   auto begin_gather = [&](int ts) {
     res_total = __ldcg(a.total);
     if (a.resampler == 1)
-      res_u0 = a.res_u ? a.res_u[(size_t)ts * a.B]
+      res_u0 = a.res_u ? a.res_u[(ptrdiff_t)ts * a.B]
                        : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, 0ull);
     if (!use_win) return;
     // Sorted positions: every answer of chunk q lies in [lower_bound(first slot of q), lower_bound(first slot of q+1)].
     // One bisection per chunk, all of them in flight together (one latency per step instead of one per chunk).
     for (int q = tid; q <= nchunk_valid; q += NT) {
-      const int slot = (q < nchunk_valid) ? cta_base + 128 * q : min(cta_base + 128 * nchunk_cta, N) - 1;
-      s_lo[q] = (nchunk_valid > 0) ? lower_bound_tau_pow2(a.E, a.log2n, position(slot, res_u0)) : 0;
+      const int slot = a.goff + ((q < nchunk_valid) ? cta_base + 128 * q : min(cta_base + 128 * nchunk_cta, N) - 1);
+      int lb = 0;
+      if (nchunk_valid > 0) {
+        const float r = position(slot, res_u0);
+        if (a.world == 1) lb = lower_bound_tau_pow2(a.E, a.log2ng, r);
+        else {                                        // same bisection over the ranks' shards (peer loads)
+          unsigned low = 0;
+          for (unsigned sft = 1u << (a.log2ng - 1); sft != 0; sft >>= 1)
+            if (!(r <= tauG((int)(low + sft)))) low += sft;
+          lb = (int)(low + ((r <= tauG((int)low)) ? 0u : 1u));
+        }
+      }
+      s_lo[q] = lb;
     }
     __syncthreads();
   };
 
   // Ancestors of the 4 slots base..base+3 of the chunk starting at cbase.  Warp-synchronous (all lanes call it).
+  // one global lower bound (any rank's shard) -- used by the rare fallbacks and by unsorted (multinomial) positions
+  auto lb_global = [&](float r) -> int {
+    if (a.world == 1) return lower_bound_tau_pow2(a.E, a.log2ng, r);
+    unsigned low = 0;
+    for (unsigned sft = 1u << (a.log2ng - 1); sft != 0; sft >>= 1)
+      if (!(r <= tauG((int)(low + sft)))) low += sft;
+    return (int)(low + ((r <= tauG((int)low)) ? 0u : 1u));
+  };
+
+  // Ancestors (GLOBAL particle indices) of the 4 slots base..base+3 (local) of chunk q.  Warp-synchronous.
   auto ancestors4 = [&](int ts, int q, int base, int nv, int anc[4]) {
     float u[4] = {res_u0, res_u0, res_u0, res_u0};
     if (a.resampler != 1 && nv > 0) {
       if (a.res_u) {
-        const float* p = a.res_u + (size_t)ts * a.B * N;
+        const float* p = a.res_u + (ptrdiff_t)ts * a.B * N;
 #pragma unroll
         for (int k = 0; k < 4; ++k) u[k] = (k < nv) ? p[base + k] : 0.0f;
       } else {
-        philox_quad_uniforms(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, (uint32_t)(base >> 2), u);
+        philox_quad_uniforms(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, (uint32_t)((a.goff + base) >> 2), u);
       }
     }
     float r[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r[k] = position(base + k, u[k]);
+    for (int k = 0; k < 4; ++k) r[k] = position(a.goff + base + k, u[k]);
     if (use_win) {
-      const float* tau = a.E;
       const int lo = s_lo[q], wn = s_lo[q + 1] - lo;             // warp-uniform
       if (wn <= WINCAP) {
         float* win = s_win + warp * WINCAP;
         for (int i0 = 0; i0 < wn; i0 += 128) {          // four independent loads in flight per lane
           float tv[4];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) { const int i = i0 + lane + 32 * m; tv[m] = (i < wn) ? tau[lo + i] : 0.0f; }
+          for (int m = 0; m < 4; ++m) { const int i = i0 + lane + 32 * m; tv[m] = (i < wn) ? tauG(lo + i) : 0.0f; }
 #pragma unroll
           for (int m = 0; m < 4; ++m) { const int i = i0 + lane + 32 * m; if (i < wn) win[i] = tv[m]; }
         }
@@ -361,26 +399,36 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         int p = lower_bound_window(win, 0, wn, r[0]);
         int pn = __shfl_down_sync(BF_FULL, p, 1);
         if (lane == 31) pn = wn;
-        anc[0] = min(lo + p, N - 1);
+        anc[0] = min(lo + p, Ng - 1);
 #pragma unroll
         for (int k = 1; k < 4; ++k) {
           p = lower_bound_window(win, p, pn, r[k]);
-          anc[k] = min(lo + p, N - 1);
+          anc[k] = min(lo + p, Ng - 1);
         }
         __syncwarp();                                  // the window is overwritten by this warp's next chunk
       } else if (nv > 0) {                             // window larger than the cap (very uneven weights): rare
 #pragma unroll
-        for (int k = 0; k < 4; ++k) anc[k] = min(lower_bound_tau_pow2(tau, a.log2n, r[k]), N - 1);
+        for (int k = 0; k < 4; ++k) anc[k] = min(lb_global(r[k]), Ng - 1);
       }
       return;
     }
     if (nv <= 0) return;
     if (use_tau) {
-      bisect4_left_exclusive_pow2(a.E - 1, a.log2n, r, anc);       // ex[j+1] == tau[j]
+      if (a.world == 1) bisect4_left_exclusive_pow2(a.E - 1, a.log2ng, r, anc);       // ex[j+1] == tau[j]
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) anc[k] = min(lb_global(r[k]), Ng - 1);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k) anc[k] = fused_bisect_left_exclusive(a.E, N, levels, r[k]);
     }
+  };
+
+  // particle `g` (GLOBAL index) of the state the step reads: own shard or a peer's
+  auto load_prev = [&](int g, const float* xp_local, const float* const* xp_peers, float* x) {
+    if (a.world == 1) load_state_cg<DX>(xp_local, (size_t)g, x);
+    else load_state_cg<DX>(xp_peers[g >> a.log2ns], (size_t)(g & ns_mask), x);
   };
 
   const bool timer = (blockIdx.x == 0 && tid == 0 && a.phase_ns != nullptr);
@@ -389,26 +437,37 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (timer) { const unsigned long long now = globaltimer_ns(); a.phase_ns[phase] += now - tmark; tmark = now; }
   };
 
+  // single-phase launches (sharded filter): one step per launch, t_offset is its absolute index; the state that
+  // crosses launches lives in two StepStats slots, read at [pt & 1] and written (phase B) at [(pt + 1) & 1]
+  if (!all_phases) {
+    const StepStats* sin = a.carry_stats + (((a.phases & PF_PH_C) ? a.t_offset + 1 : a.t_offset) & 1);
+    w_uni = sin->w_uniform != 0; gather = sin->flag != 0;
+    if (a.t_offset > 0) x_prev = (a.t_offset & 1) ? a.xbuf0 : a.xbuf1;
+  }
   for (int t = 0; t < T; ++t) {
-    float* x_cur = (t & 1) ? a.xbuf1 : a.xbuf0;
+    const int pt = all_phases ? t : a.t_offset;        // ping-pong parity and "is there a previous step"
+    float* x_cur = (pt & 1) ? a.xbuf1 : a.xbuf0;
+    const float* const* xp_peers = (pt & 1) ? a.xa_peers : a.xb_peers;
     const float u_in = a.inputs ? a.inputs[t] : 0.0f;
     float y[DY];
 #pragma unroll
     for (int k = 0; k < DY; ++k) y[k] = a.emissions[(size_t)t * DY + k];
+    OnlineAcc<DX> acc;
 
     // ------------------------------------------------------------------ phase A
+    if (a.phases & PF_PH_A) {
     if (gather) begin_gather(t - 1);
-    OnlineAcc<DX> acc; acc.init();
+    acc.init();
     for (int q = next_chunk(0); q < nchunk_valid; q = next_chunk(0)) {
       const int base = cta_base + 128 * q + lane * 4;
       const int nv = max(0, min(4, N - base));
-      int anc[4] = {base, base + 1, base + 2, base + 3};
+      int anc[4] = {a.goff + base, a.goff + base + 1, a.goff + base + 2, a.goff + base + 3};     // global indices
 #ifndef BF_EXP_NOSEARCH
       if (gather) ancestors4(t - 1, q, base, nv, anc);
 #endif
       if (nv <= 0) continue;
-      if (t > 0 && a.out_ancestors) {
-        int* o = a.out_ancestors + (size_t)(t - 1) * N + base;
+      if (pt > 0 && a.out_ancestors) {
+        int* o = a.out_ancestors + ((ptrdiff_t)t - 1) * N + base;
 #pragma unroll
         for (int k = 0; k < 4; ++k) if (k < nv) o[k] = anc[k];
       }
@@ -416,7 +475,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #ifdef BF_EXP_NORNG
       for (int k = 0; k < 4; ++k) for (int c = 0; c < DQ; ++c) z[k][c] = 0.1f * (float)(k + c);
 #else
-      if (!a.noise) philox_quad_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)a.trial, (uint32_t)(base >> 2), z);
+      if (!a.noise) philox_quad_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)a.trial, (uint32_t)((a.goff + base) >> 2), z);
 #endif
       float llv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
@@ -424,8 +483,9 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         if (k < nv) {
           const int i = base + k;
           float x[DX], qn[DQ], xt[DX];
-          load_state_cg<DX>(x_prev, (size_t)anc[k], x);
-          if (t > 0 && a.out_particles) store_state<DX>(a.out_particles + (size_t)(t - 1) * N * DX, (size_t)i, x);
+          if (gather) load_prev(anc[k], x_prev, xp_peers, x);
+          else load_state_cg<DX>(x_prev, (size_t)i, x);
+          if (pt > 0 && a.out_particles) store_state<DX>(a.out_particles + ((ptrdiff_t)t - 1) * N * DX, (size_t)i, x);
           if (a.noise) {
             const float* np_ = a.noise + (size_t)t * a.B * N * DQ + (size_t)i * DQ;
 #pragma unroll
@@ -469,23 +529,29 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       if (lane < CW) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
       acc.warp_reduce();
       if (lane == 0) {
-        PfPartial* p = &a.partials[(size_t)(t & 1) * G + blockIdx.x];
+        PfPartial* p = &a.partials[((size_t)(pt & 1) * a.world + a.rank) * G + blockIdx.x];
         p->m = acc.m; p->s = acc.s; p->s2 = acc.s2;
 #pragma unroll
         for (int k = 0; k < DX; ++k) p->sx[k] = acc.sx[k];
       }
     }
-    grid.sync();
+    }  // phase A
+    if (all_phases) grid.sync();
     lap(0);
+    if (!(a.phases & (PF_PH_B | PF_PH_C))) break;
 
     // ------------------------------------------------------------------ phase B
     if (tid == 0) s_ctr[0] = 0;                        // queue of the next phase A / the final gather
 #ifndef BF_DYNAMIC_CHUNKS
     turn[0] = 0;
 #endif
+    if (!(a.phases & PF_PH_B)) {                       // C-only launch: phase B left the step's statistics here
+      if (tid == 0) s_stats = a.carry_stats[(pt + 1) & 1];
+      __syncthreads();
+    } else {
     acc.init();
-    for (int b = tid; b < G; b += NT) {               // same order in every CTA: bit-identical stats
-      const PfPartial* p = &a.partials[(size_t)(t & 1) * G + b];
+    for (int b = tid; b < a.world * G; b += NT) {     // same order in every CTA of every rank: bit-identical stats
+      const PfPartial* p = &a.partials[(size_t)(pt & 1) * a.world * G + b];
       float sx[DX];
 #pragma unroll
       for (int k = 0; k < DX; ++k) sx[k] = __ldcg(&p->sx[k]);
@@ -507,13 +573,14 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         st.mx = acc.m; st.Z = acc.s;
         st.loglik = acc.m + logf(acc.s);                       // log p(y_t | y_1:t-1)
         st.ess = acc.s * acc.s / acc.s2;                       // 1 / sum (e/Z)^2   (inference.py:1356)
-        st.flag = (st.ess < a.ess_threshold * (float)N) ? 1 : 0;
+        st.flag = (st.ess < a.ess_threshold * (float)Ng) ? 1 : 0;
         st.w_uniform = st.flag;
         st.pad0 = st.pad1 = 0;
 #pragma unroll
         for (int k = 0; k < BF_MAXD; ++k) st.mean[k] = (k < DX) ? acc.sx[k] / acc.s : 0.0f;
         s_stats = st;
-        if (blockIdx.x == 0) {
+        if (blockIdx.x == 0 && !all_phases) a.carry_stats[(pt + 1) & 1] = st;
+        if (blockIdx.x == 0 && a.rank == 0) {
           if (a.out_loglik) a.out_loglik[t] = st.loglik;
           if (a.out_ess) a.out_ess[t] = st.ess;
           if (a.out_resampled) a.out_resampled[t] = st.flag;
@@ -525,8 +592,10 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
     }
     __syncthreads();
+    }  // statistics
     const float mx = s_stats.mx, rZ = 1.0f / s_stats.Z;
     const bool flag = s_stats.flag != 0;
+    if (a.phases & PF_PH_B) {
 
     // normalised weights (exp(ll - max) * w_prev) / sum (inference.py:1350-1353), four chunks per turn so that four
     // 512-byte loads per warp are in flight (one at a time left this phase latency-bound)
@@ -571,11 +640,13 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         }
       }
     }
+    }  // phase B weights
     x_prev = x_cur;
     if (!flag) {                         // grid-uniform branch: no grid sync, but chunks change hands between warps
       __syncthreads();                   // W of this step is complete before any warp of the CTA starts the next step
       w_uni = false; gather = false; lap(1); continue;
     }
+    if (a.phases & PF_PH_B) {
     __syncthreads();
     for (int i = tid; i < tile1 - tile0; i += NT) {   // tile sums: the top log2(TW) levels of the tile's tree
       float y16[TW];
@@ -585,14 +656,16 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       for (int w = TW / 2; w >= 1; w >>= 1)
 #pragma unroll
         for (int k = 0; k < w; ++k) y16[k] = __fadd_rn(y16[2 * k], y16[2 * k + 1]);
-      a.tilesum[tile0 + i] = y16[0];
-      a.V[tile0 + i] = s_v0[i * TW];
+      a.tilesum[a.tile_off + tile0 + i] = y16[0];
+      a.V[a.tile_off + tile0 + i] = s_v0[i * TW];
     }
-    grid.sync();
+    }  // phase B tile sums
+    if (all_phases) grid.sync();
     lap(1);
+    if (!(a.phases & PF_PH_C)) break;
 
-    // ------------------------------------------------------------------ phase C1 (CTA 0)
-    if (blockIdx.x == 0) cta_exclusive_scan<CW>(a.tilesum, a.Etile, a.ntiles, s_win);
+    // ------------------------------------------------------------------ phase C1 (CTA 0; every rank of a sharded filter)
+    if (blockIdx.x == 0) cta_exclusive_scan<CW>(a.tilesum, a.Etile, a.ntiles_g, s_win);
     grid.sync();
     lap(2);
 
@@ -601,10 +674,10 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       // clamp interval of each owned tile from the bisection levels above it (half-widths N/2 .. TILE); the probe
       // value of a node whose middle is the first boundary of tile m is cdf[m*TILE] = Etile[m] + w[m*TILE]
       for (int i = tid; i < tile1 - tile0; i += NT) {
-        const int jt = (tile0 + i) * TILE;
+        const int jt = (a.tile_off + tile0 + i) * TILE;          // global boundary index
         float lo = -INFINITY, hi = INFINITY;
-        if (jt < N) {
-          for (int s = N >> 1; s >= TILE; s >>= 1) {
+        if (jt < Ng) {
+          for (int s = Ng >> 1; s >= TILE; s >>= 1) {
             const int mid = (jt & ~(2 * s - 1)) + s, m = mid / TILE;
             const float c = clampf(__fadd_rn(__ldcg(&a.Etile[m]), __ldcg(&a.V[m])), lo, hi);
             if (jt < mid) hi = c; else lo = c;
@@ -621,14 +694,14 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         w4[j] = *reinterpret_cast<const float4*>(a.E + cta_base + 128 * (qb + j) + lane * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int q = qb + j, tl = q / TW, wpos = q % TW, tile = tile0 + tl;
+        const int q = qb + j, tl = q / TW, wpos = q % TW, tile = a.tile_off + tile0 + tl;
         const int base = cta_base + 128 * q + lane * 4;
         float e[4], tau[4];
         const float v[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};
         float4 out;
         if (use_tau) {
           chunk_scan<TW, true>(v, wpos, s_wsum + tl * TW, s_v0 + tl * TW, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]),
-                                   s_meta_f[2 * tl], s_meta_f[2 * tl + 1], min(TILE, N), e, tau);
+                                   s_meta_f[2 * tl], s_meta_f[2 * tl + 1], min(TILE, Ng), e, tau);
           out = make_float4(tau[0], tau[1], tau[2], tau[3]);
         } else {
           chunk_scan<TW, false>(v, wpos, s_wsum + tl * TW, s_v0 + tl * TW, __ldcg(&a.Etile[tile]), 0.0f, 0.0f, 0.0f, 0, e, tau);
@@ -639,28 +712,33 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         if (!use_tau || base < N) *reinterpret_cast<float4*>(a.E + base) = out;
       }
     }
-    grid.sync();
+    if (a.world > 1 && blockIdx.x == 0 && tid == 0) *a.total = __ldcg(&a.Etile[a.ntiles_g - 1]);   // E[Ng]
+    if (all_phases) grid.sync();
     lap(3);
     w_uni = true; gather = true;
   }
+  if (!(a.phases & PF_PH_FINAL)) return;
 
   // ------------------------------------------------------------------ materialise the carry
+  const int ptf = all_phases ? T : a.t_offset;          // number of steps behind the carry
+  const float* const* xpf_peers = (ptf & 1) ? a.xa_peers : a.xb_peers;
   if (gather) begin_gather(T - 1);
   for (int q = next_chunk(0); q < nchunk_valid; q = next_chunk(0)) {
     const int base = cta_base + 128 * q + lane * 4;
     const int nv = max(0, min(4, N - base));
-    int anc[4] = {base, base + 1, base + 2, base + 3};
+    int anc[4] = {a.goff + base, a.goff + base + 1, a.goff + base + 2, a.goff + base + 3};
     if (gather) ancestors4(T - 1, q, base, nv, anc);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < nv) {
         const int i = base + k;
         float x[DX];
-        load_state_cg<DX>(x_prev, (size_t)anc[k], x);
+        if (gather) load_prev(anc[k], x_prev, xpf_peers, x);
+        else load_state_cg<DX>(x_prev, (size_t)i, x);
         store_state<DX>(a.carry_x, (size_t)i, x);
         if (a.final_particles) store_state<DX>(a.final_particles, (size_t)i, x);
-        if (a.out_particles) store_state<DX>(a.out_particles + (size_t)(T - 1) * N * DX, (size_t)i, x);
-        if (a.out_ancestors) a.out_ancestors[(size_t)(T - 1) * N + i] = anc[k];
+        if (a.out_particles) store_state<DX>(a.out_particles + ((ptrdiff_t)T - 1) * N * DX, (size_t)i, x);
+        if (a.out_ancestors) a.out_ancestors[((ptrdiff_t)T - 1) * N + i] = anc[k];
         const float w = w_uni ? invN : a.W[i];
         if (w_uni) a.W[i] = invN;
         if (a.final_weights) a.final_weights[i] = w;
@@ -669,8 +747,9 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   }
   lap(4);
   if (blockIdx.x == 0 && tid == 0) {
-    StepStats st = s_stats;
+    StepStats st = all_phases ? s_stats : a.carry_stats[a.t_offset & 1];
     st.flag = 0; st.w_uniform = w_uni ? 1 : 0;
-    *a.carry_stats = st;
+    a.carry_stats[0] = st;
+    if (!all_phases) a.carry_stats[1] = st;
   }
 }

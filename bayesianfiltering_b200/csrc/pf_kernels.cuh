@@ -399,10 +399,10 @@ __global__ void k_clear_gather(StepStats* st) { st->flag = 0; }
 // initial particles ~ N(m0, P0) from Philox (inference.py:1372-1373 with our own stream)
 template <int DX>
 __global__ void __launch_bounds__(256)
-k_init_particles(const __grid_constant__ ModelConst mc, float* __restrict__ x, int N, unsigned long long seed, int trial) {
+k_init_particles(const __grid_constant__ ModelConst mc, float* __restrict__ x, int N, unsigned long long seed, int trial, int goff) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     float z[DX], o[DX];
-    philox_normals<DX>(seed, BF_STREAM_INIT, 0u, (uint32_t)trial, (uint64_t)i, z);
+    philox_normals<DX>(seed, BF_STREAM_INIT, 0u, (uint32_t)trial, (uint64_t)(goff + i), z);   // goff: shard of a sharded filter
 #pragma unroll
     for (int r = 0; r < DX; ++r) {
       float s = mc.m0[r];

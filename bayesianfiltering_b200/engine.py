@@ -84,7 +84,7 @@ class ParticleFilterEngine:
     """Owns a bf_pf_handle: N particles x B independent trials of one registry model."""
 
     def __init__(self, host_model, num_particles, num_trials=1, ess_threshold=0.5, resampler="multinomial",
-                 path="auto", seed=0, device=None):
+                 path="auto", seed=0, device=None, shard_rank=0, shard_world=1):
         self.lib = _lib.load()
         self.hm = host_model
         self.N, self.B = int(num_particles), int(num_trials)
@@ -92,7 +92,7 @@ class ParticleFilterEngine:
         self.resampler = resampler
         self.device = _default_device() if device is None else int(device)
         cfg = _lib.PfConfig(self.N, self.B, float(ess_threshold), _RESAMPLERS[resampler], _PATHS[path],
-                            int(seed) & 0xFFFFFFFFFFFFFFFF, self.device, 0)
+                            int(seed) & 0xFFFFFFFFFFFFFFFF, self.device, 0, int(shard_rank), int(shard_world))
         self.h = C.c_void_p()
         _lib.check(self.lib.bf_pf_create(C.byref(host_model.desc), C.byref(cfg), C.byref(self.h)))
 
@@ -204,6 +204,43 @@ class ParticleFilterEngine:
         if a.numel() != int(np.prod(shape)):
             raise ValueError(f"{name} has {a.numel()} elements, expected shape {tuple(shape)}")
         return a.view(shape)
+
+
+class ShardedParticleFilterEngine(ParticleFilterEngine):
+    """ONE bootstrap particle filter whose particles are sharded over the GPUs of a box: this rank owns
+    `num_particles // world` consecutive particles.  Needs an initialised `torch.distributed` process group (one
+    process per GPU, e.g. torchrun); the group carries only the set-up (CUDA-IPC handles, NCCL id).  Per time step
+    libbfilt itself exchanges the weight statistics and the scan offsets with NCCL and gathers ancestors that live on
+    another rank straight from its memory over NVLink (include/bfilt.h, bf_pf_shard_*).
+
+    `run` / `run_host` take and return the LOCAL shard of every per-particle array (noise [T,1,N/world,dq],
+    uniforms [T,1,N/world], outputs [1,T,N/world,...], ancestors as GLOBAL indices); per-step scalars (means,
+    log_likelihood, ess, resampled) are those of the whole filter, written by rank 0 (other ranks get zeros)."""
+
+    def __init__(self, host_model, num_particles, ess_threshold=0.5, resampler="multinomial", seed=0, device=None, group=None):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("ShardedParticleFilterEngine needs an initialised torch.distributed process group")
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if num_particles % world:
+            raise ValueError(f"num_particles={num_particles} is not divisible by the {world} ranks")
+        self.world, self.rank, self.N_global = world, rank, int(num_particles)
+        super().__init__(host_model, num_particles // world, 1, ess_threshold, resampler, "streamed", seed, device,
+                         shard_rank=rank, shard_world=world)
+        if world == 1:
+            return
+        blob = C.create_string_buffer(_lib.SHARD_BLOB_BYTES)
+        _lib.check(self.lib.bf_pf_shard_export(self.h, blob))
+        blobs = [None] * world
+        dist.all_gather_object(blobs, blob.raw, group=group)
+        _lib.check(self.lib.bf_pf_shard_import(self.h, b"".join(blobs)))
+        uid = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)
+            _lib.check(self.lib.bf_nccl_unique_id(buf))
+            uid = [buf.raw]
+        dist.broadcast_object_list(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        _lib.check(self.lib.bf_pf_shard_comm_init(self.h, uid[0]))
 
 
 class GaussianSumFilterEngine:

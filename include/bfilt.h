@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BF_ABI_VERSION 1
+#define BF_ABI_VERSION 2
 
 typedef enum bf_status {
   BF_OK = 0, BF_EINVAL = -1, BF_ECUDA = -2, BF_ENOMODEL = -3, BF_ENOMEM = -4, BF_ECOMM = -5
@@ -73,6 +73,9 @@ typedef struct bf_pf_config {
   uint64_t seed;             /* Philox key for every random input that is not supplied          */
   int32_t device;            /* CUDA device ordinal                                             */
   int32_t reserved;
+  /* One filter sharded over the GPUs of a box (one process per GPU): this rank owns num_particles consecutive
+   * particles of a filter of shard_world * num_particles.  0/0 or x/1 = not sharded.  See bf_pf_shard_* below. */
+  int32_t shard_rank, shard_world;
 } bf_pf_config;
 
 typedef struct bf_pf_io {
@@ -110,6 +113,24 @@ int bf_pf_kernel_launches(bf_pf_handle h, int64_t* out);   /* launches enqueued 
  * [2] scan of the tile sums, [3] in-tile scan -> cdf, [4] final gather.  Synchronises the device. */
 int bf_pf_phase_times(bf_pf_handle h, double* out_ms5, int32_t reset);
 int bf_pf_destroy(bf_pf_handle h);
+
+/* ---- one particle filter sharded over `shard_world` GPUs (power of two <= 8, one process per GPU).
+ * The reference has no multi-device code; this is `bootstrap_particle_filter` (inference.py:1302-1380) for an N that
+ * one GPU should not hold alone.  num_particles (per rank) must be a power of two >= 2048, one trial, streamed path.
+ * Per time step the ranks exchange, with NCCL over NVLink, (1) their CTA partials of (max, sum, sum^2, sum x) -- every
+ * rank folds all of them in the same order, so the ESS test takes the same branch everywhere -- (2) the tile sums and
+ * first weights of their tiles, from which every rank derives the same canonical scan offsets, and (3) a barrier
+ * before the next step reads the peers' cdf (tau) and particle state through CUDA-IPC mapped pointers: ancestors
+ * that live on another rank are gathered directly from its memory.
+ * Protocol: create on every rank -> bf_pf_shard_export -> exchange the blobs between the processes (any transport)
+ * -> bf_pf_shard_import; rank 0 bf_nccl_unique_id -> broadcast -> bf_pf_shard_comm_init on every rank; then bf_pf_run /
+ * bf_pf_run_host as usual with the LOCAL shard of every per-particle array (resume / t_offset are not supported). */
+#define BF_SHARD_BLOB_BYTES 256
+#define BF_NCCL_ID_BYTES 128
+int bf_pf_shard_export(bf_pf_handle h, void* blob /* BF_SHARD_BLOB_BYTES */);
+int bf_pf_shard_import(bf_pf_handle h, const void* blobs /* shard_world * BF_SHARD_BLOB_BYTES, rank order */);
+int bf_nccl_unique_id(void* id /* BF_NCCL_ID_BYTES */);
+int bf_pf_shard_comm_init(bf_pf_handle h, const void* id /* BF_NCCL_ID_BYTES */);
 
 /* ---------------------------------------------------------------- Gaussian-sum (EKF) filter */
 typedef struct bf_gsf_s* bf_gsf_handle;

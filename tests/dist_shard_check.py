@@ -1,0 +1,80 @@
+"""Run under torchrun on >= 2 GPUs (tests/test_gpu_shard.py launches it): ONE particle filter sharded over the ranks
+against the oracle, step by step, with the randomness supplied -- the same checks as tests/test_gpu_pf._stepwise,
+on arrays gathered from the shards.  Exits non-zero on any mismatch."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from tests.parity_cases import case, close
+    from tests.test_gpu_pf import _stepwise
+    from bayesianfiltering_b200.engine import ShardedParticleFilterEngine, ParticleFilterEngine
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    outs = ("weights", "particles", "propagated", "norm_weights", "ancestors", "means", "log_likelihood", "ess",
+            "resampled", "final_particles", "final_weights")
+    scal = ("means", "log_likelihood", "ess", "resampled")
+    for name, T, N, thr, res in (("lg42", 10, 4096 * world, 0.6, "systematic"), ("bot2", 8, 8192 * world, 1.0, "systematic"),
+                                 ("ungm", 10, 2048 * world, 0.5, "multinomial")):
+        c = case(name)
+        _, ys = c.simulate(T, 7)
+        u = c.inputs(T)
+        x0, noise, ru = c.pf_randomness(T, N, 8, res)               # identical on every rank (seeded)
+        Ns = N // world
+        sl = slice(rank * Ns, (rank + 1) * Ns)
+        eng = ShardedParticleFilterEngine(c.host_model(), N, thr, res, seed=3, device=local)
+        out = eng.run_host(ys, inputs=u, init_particles=x0[sl], noise=noise[:, sl],
+                           resample_u=(ru[:, sl] if res == "multinomial" else ru), outputs=outs)
+        eng.close()
+        # assemble the whole filter on every rank
+        full = {}
+        for k, v in out.items():
+            if k in scal:
+                t = torch.from_numpy(np.ascontiguousarray(v)).cuda()
+                dist.broadcast(t, src=0)
+                full[k] = t.cpu().numpy()
+            else:
+                parts = [None] * world
+                dist.all_gather_object(parts, v)
+                full[k] = np.concatenate(parts, axis=1 if k.startswith("final_") else 2)      # the particle axis
+        if rank == 0:
+            n_res = _stepwise(c, full, ys, u, x0, noise, ru, thr, res)
+            assert n_res > 0, "case never resampled"
+            # and against the unsharded filter on one GPU: same decisions, same estimates
+            one = ParticleFilterEngine(c.host_model(), N, 1, thr, res, "streamed", 3, local)
+            o1 = one.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=("means", "log_likelihood", "resampled"))
+            one.close()
+            assert np.array_equal(o1["resampled"], full["resampled"])
+            close(full["log_likelihood"], o1["log_likelihood"], rtol=1e-5, atol_scale=1e-5, what=f"{name} loglik vs one GPU")
+            close(full["means"], o1["means"], rtol=1e-4, atol_scale=1e-4, what=f"{name} means vs one GPU")
+            print(f"sharded {name}: N={N} over {world} ranks, T={T}, {n_res} resampling steps: ok", flush=True)
+        dist.barrier()
+    # Philox mode: the random numbers are indexed by GLOBAL particle, so the filter does not depend on the sharding
+    c = case("bot2")
+    T, N = 6, 16384 * world
+    _, ys = c.simulate(T, 9)
+    u = c.inputs(T)
+    eng = ShardedParticleFilterEngine(c.host_model(), N, 1.0, "systematic", seed=11, device=local)
+    out = eng.run_host(ys, inputs=u, outputs=("means", "log_likelihood"))
+    eng.close()
+    if rank == 0:
+        one = ParticleFilterEngine(c.host_model(), N, 1, 1.0, "systematic", "streamed", 11, local)
+        o1 = one.run_host(ys, inputs=u, outputs=("means", "log_likelihood"))
+        one.close()
+        close(out["log_likelihood"], o1["log_likelihood"], rtol=1e-5, atol_scale=1e-5, what="philox loglik vs one GPU")
+        close(out["means"], o1["means"], rtol=1e-4, atol_scale=1e-4, what="philox means vs one GPU")
+        print("sharded philox run equals the one-GPU run: ok", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
