@@ -66,6 +66,7 @@ SYMBOLS = [
     ("bf_pf_shard_import", C.c_int, [C.c_void_p, C.c_void_p]),
     ("bf_nccl_unique_id", C.c_int, [C.c_void_p]),
     ("bf_pf_shard_comm_init", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("bf_pf_shard_comm_ready", C.c_int, [C.c_void_p]),
     ("bf_gsf_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(GsfConfig), C.POINTER(C.c_void_p)]),
     ("bf_gsf_run", C.c_int, [C.c_void_p, C.POINTER(GsfIO), C.c_void_p]),
     ("bf_gsf_run_host", C.c_int, [C.c_void_p, C.POINTER(GsfIO)]),

@@ -187,6 +187,15 @@ static NcclApi* nccl_api() {
     if (_r != ncclSuccess) return fail(BF_ECOMM, "%s failed: %s (%s:%d)", #expr, nccl_api()->GetErrorString(_r), __FILE__, __LINE__); \
   } while (0)
 
+// NCCL communicators are expensive to create (hundreds of ms) and the reference-facing entry points create one handle
+// per call: keep one communicator per (device, world, rank) for the life of the process.
+struct CommSlot { int device, world, rank; ncclComm_t comm; };
+static std::vector<CommSlot> g_comms;
+static ncclComm_t find_comm(int device, int world, int rank) {
+  for (auto& c : g_comms) if (c.device == device && c.world == world && c.rank == rank) return c.comm;
+  return nullptr;
+}
+
 // ========================================================================================== particle filter
 struct ShardBlob { cudaIpcMemHandle_t tau, xa, xb; int rank, grid, pad[14]; };
 static_assert(sizeof(ShardBlob) <= BF_SHARD_BLOB_BYTES, "blob too large");
@@ -210,6 +219,9 @@ struct bf_pf_s {
   bool peers_ready = false;
   void* peer_ptr[3][8] = {};          // imported tau / xa / xb of every rank (own entries = own buffers)
   DevBuf peer_tab, barrier_buf;       // device tables [3][8] of the pointers above; 1 float for the step barrier
+  // the T x (4 launches + 4 collectives) of a sharded run, captured once per distinct call and replayed
+  cudaStream_t gstream = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t gexec = nullptr; size_t gkey = 0; int64_t glaunches = 0;
   // host-call staging
   DevBuf hbuf[24];
 };
@@ -288,7 +300,10 @@ extern "C" int bf_pf_destroy(bf_pf_handle h) {
   if (!h) return BF_OK;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();              // as cudaFree would: nothing enqueued by this handle may still be running
-  if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
   if (h->peers_ready)
     for (int k = 0; k < 3; ++k)
       for (int r = 0; r < h->world; ++r)
@@ -359,7 +374,14 @@ extern "C" int bf_pf_shard_comm_init(bf_pf_handle h, const void* id) {
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof uid);
   NCCL_OK(nc->CommInitRank(&h->comm, h->world, uid, h->rank));
+  g_comms.push_back({h->cfg.device, h->world, h->rank, h->comm});
   return BF_OK;
+}
+
+extern "C" int bf_pf_shard_comm_ready(bf_pf_handle h) {
+  if (!h || h->world < 2) return 0;
+  if (!h->comm) h->comm = find_comm(h->cfg.device, h->world, h->rank);     // a communicator an earlier handle created
+  return h->comm ? 1 : 0;
 }
 
 extern "C" int bf_pf_phase_times(bf_pf_handle h, double* out_ms, int32_t reset) {
@@ -504,10 +526,9 @@ struct PfRun {
       NcclApi* nc = nccl_api();
       const float* const* tab = h->peer_tab.as<const float*>();
       a.tau_peers = tab; a.xa_peers = tab + 8; a.xb_peers = tab + 16;
-      k_init_stats<<<1, 1, 0, s>>>(a.carry_stats, io->init_weights ? 0 : 1);
-      LAUNCH_OK(); h->launches++;
       const size_t pf_floats = (size_t)grid * sizeof(PfPartial) / 4;
-      auto launch = [&](int phases, int t, int Tl) -> int {
+      int64_t nlaunch = 0;
+      auto launch = [&](cudaStream_t st, int phases, int t, int Tl) -> int {
         PfFusedArgs p = a;
         p.phases = phases; p.T = Tl; p.t_offset = t;
         p.emissions = a.emissions + (size_t)t * DY;
@@ -524,24 +545,70 @@ struct PfRun {
         p.out_ess = a.out_ess ? a.out_ess + t : nullptr;
         p.out_resampled = a.out_resampled ? a.out_resampled + t : nullptr;
         void* params[] = {(void*)&h->mc, (void*)&p};
-        CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, s));
-        h->launches++;
+        CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, st));
+        ++nlaunch;
         return BF_OK;
       };
-      int rc;
-      for (int t = 0; t < T; ++t) {
-        if ((rc = launch(PF_PH_A, t, 1))) return rc;
-        float* pbase = reinterpret_cast<float*>(a.partials) + (size_t)(t & 1) * world * pf_floats;
-        NCCL_OK(nc->AllGather(pbase + (size_t)rank * pf_floats, pbase, pf_floats, ncclFloat, h->comm, s));
-        if ((rc = launch(PF_PH_B, t, 1))) return rc;
-        NCCL_OK(nc->AllGather(a.tilesum + (size_t)rank * ntiles, a.tilesum, ntiles, ncclFloat, h->comm, s));
-        NCCL_OK(nc->AllGather(a.V + (size_t)rank * ntiles, a.V, ntiles, ncclFloat, h->comm, s));
-        if ((rc = launch(PF_PH_C, t, 1))) return rc;
-        // barrier: every rank's tau and particles of this step are complete before anyone's next step reads them
-        NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, s));
+      auto enqueue_all = [&](cudaStream_t st) -> int {
+        int rc;
+        k_init_stats<<<1, 1, 0, st>>>(a.carry_stats, io->init_weights ? 0 : 1);
+        LAUNCH_OK(); ++nlaunch;
+        for (int t = 0; t < T; ++t) {
+          if ((rc = launch(st, PF_PH_A, t, 1))) return rc;
+          float* pbase = reinterpret_cast<float*>(a.partials) + (size_t)(t & 1) * world * pf_floats;
+          NCCL_OK(nc->AllGather(pbase + (size_t)rank * pf_floats, pbase, pf_floats, ncclFloat, h->comm, st));
+          if ((rc = launch(st, PF_PH_B, t, 1))) return rc;
+          NCCL_OK(nc->AllGather(a.tilesum + (size_t)rank * ntiles, a.tilesum, ntiles, ncclFloat, h->comm, st));
+          NCCL_OK(nc->AllGather(a.V + (size_t)rank * ntiles, a.V, ntiles, ncclFloat, h->comm, st));
+          if ((rc = launch(st, PF_PH_C, t, 1))) return rc;
+          // barrier: every rank's tau and particles of this step are complete before anyone's next step reads them
+          NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, st));
+        }
+        if ((rc = launch(st, PF_PH_FINAL, T, 0))) return rc;
+        NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, st));
+        return BF_OK;
+      };
+      // Capture the whole run as one CUDA graph (keyed by the call's arguments) and replay it: the ~8 T enqueues
+      // otherwise cost more host time than the GPU needs for the steps.  BF_SHARD_GRAPH=0 disables.
+      size_t key = 1469598103934665603ull;
+      {
+        const unsigned char* pb = reinterpret_cast<const unsigned char*>(io);
+        for (size_t i = 0; i < sizeof(*io); ++i) key = (key ^ pb[i]) * 1099511628211ull;
       }
-      if ((rc = launch(PF_PH_FINAL, T, 0))) return rc;
-      NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, s));
+      const char* genv = getenv("BF_SHARD_GRAPH");
+      bool use_graph = !(genv && genv[0] == '0');
+      if (use_graph && !h->gstream) {
+        if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess) { use_graph = false; cudaGetLastError(); }
+      }
+      if (use_graph) {
+        CUDA_OK(cudaEventRecord(h->ev_in, s));
+        CUDA_OK(cudaStreamWaitEvent(h->gstream, h->ev_in, 0));
+        if (!h->gexec || h->gkey != key) {
+          if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+          cudaGraph_t graph = nullptr;
+          nlaunch = 0;
+          bool ok = cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+          int rc = ok ? enqueue_all(h->gstream) : BF_ECUDA;
+          if (ok && cudaStreamEndCapture(h->gstream, &graph) != cudaSuccess) rc = BF_ECUDA;
+          if (rc == BF_OK && cudaGraphInstantiate(&h->gexec, graph, 0) != cudaSuccess) rc = BF_ECUDA;
+          if (graph) cudaGraphDestroy(graph);
+          if (rc != BF_OK) { cudaGetLastError(); h->gexec = nullptr; use_graph = false; }
+          else { h->gkey = key; h->glaunches = nlaunch; }
+        }
+      }
+      if (use_graph) {
+        CUDA_OK(cudaGraphLaunch(h->gexec, h->gstream));
+        CUDA_OK(cudaEventRecord(h->ev_out, h->gstream));
+        CUDA_OK(cudaStreamWaitEvent(s, h->ev_out, 0));
+        h->launches += h->glaunches;
+      } else {
+        nlaunch = 0;
+        int rc = enqueue_all(s);
+        if (rc) return rc;
+        h->launches += nlaunch;
+      }
     }
     return BF_OK;
   }

@@ -234,6 +234,8 @@ class ShardedParticleFilterEngine(ParticleFilterEngine):
         blobs = [None] * world
         dist.all_gather_object(blobs, blob.raw, group=group)
         _lib.check(self.lib.bf_pf_shard_import(self.h, b"".join(blobs)))
+        if self.lib.bf_pf_shard_comm_ready(self.h):       # the process already has a communicator for this (device, world, rank)
+            return
         uid = [None]
         if rank == 0:
             buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)

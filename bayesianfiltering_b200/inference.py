@@ -54,7 +54,7 @@ def bootstrap_particle_filter(params: ParamsBPF, emissions, num_particles, key=P
                               ess_threshold: float = 0.5, *, resampler: str = "multinomial", noise=None,
                               resample_uniforms=None, init_particles=None, init_weights=None,
                               outputs=("weights", "particles"), num_trials=None, path: str = "auto", device=None,
-                              engine: Optional[ParticleFilterEngine] = None):
+                              engine: Optional[ParticleFilterEngine] = None, shard_particles: bool = False):
     r"""Bootstrap particle filter for the nonlinear state space model (inference.py:1302-1380).
 
     Args (reference): params, emissions [T,dy], num_particles, key, inputs [T] or None, ess_threshold.
@@ -68,6 +68,9 @@ def bootstrap_particle_filter(params: ParamsBPF, emissions, num_particles, key=P
         num_trials         B independent filters; every array above then takes a leading/embedded B axis
                            (emissions [B,T,dy] or shared [T,dy], noise [T,B,N,dq], uniforms [T,B,N] / [T,B]).
         path               'auto' | 'resident' (one CTA per trial, shared memory) | 'streamed' (HBM pipeline).
+        shard_particles    True under torchrun: ONE filter whose num_particles are split over the ranks' GPUs
+                           (engine.ShardedParticleFilterEngine); per-particle arguments and results are then the
+                           local shard, per-step scalars come from rank 0.
     Returns: dict; 'weights' [N,T], 'particles' [N,T,dx] as in the reference (views of time-major buffers),
         extras keyed by name ('log_likelihood' is returned as 'log_likelihood_increments' [T] plus the scalar
         'marginal_log_likelihood').
@@ -75,8 +78,12 @@ def bootstrap_particle_filter(params: ParamsBPF, emissions, num_particles, key=P
     if engine is None:
         _, hm = zoo.host_model_from_params(params)
         B = 1 if num_trials is None else int(num_trials)
-        engine = ParticleFilterEngine(hm, int(num_particles), B, float(ess_threshold), resampler, path,
-                                      key_to_seed(key), device)
+        if shard_particles:
+            from .engine import ShardedParticleFilterEngine
+            engine = ShardedParticleFilterEngine(hm, int(num_particles), float(ess_threshold), resampler, key_to_seed(key), device)
+        else:
+            engine = ParticleFilterEngine(hm, int(num_particles), B, float(ess_threshold), resampler, path,
+                                          key_to_seed(key), device)
         own = True
     else:
         own = False

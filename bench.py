@@ -32,6 +32,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PF_LOG2N = int(os.environ.get("BF_BENCH_LOG2N", "24"))
+# "trials": every rank runs its own N = 2^24 filter (weak scaling, no collective) -- the default;
+# "particles": ONE filter of N = 2^24 particles sharded over the ranks (strong scaling; NCCL + peer gathers every step)
+PF_MODE = os.environ.get("BF_BENCH_MODE", "trials")
 PF_T = int(os.environ.get("BF_BENCH_T", "1000"))
 GSF_M, GSF_B, GSF_T = 100, 1024, 500
 BYTES_PER_PARTICLE_STEP = 84     # 4*(4*dx + 5) for dx=4, in-kernel RNG, resampling step
@@ -156,7 +159,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from bayesianfiltering_b200 import inference as gf
-    from bayesianfiltering_b200.engine import ParticleFilterEngine, GaussianSumFilterEngine
+    from bayesianfiltering_b200.engine import ParticleFilterEngine, GaussianSumFilterEngine, ShardedParticleFilterEngine
     from bayesianfiltering_b200.random import PRNGKey
     from tests.parity_cases import case
 
@@ -185,10 +188,16 @@ def run_ours(args):
     peak, peak_src = _peaks()
     c = _bot_case()
     N, T = 1 << PF_LOG2N, PF_T
-    _, ys = c.simulate(T, 1000 + rank)
+    _, ys = c.simulate(T, 1000 + (0 if PF_MODE == 'particles' else rank))       # one filter: the same data on every rank
     u = c.inputs(T)
     ys_d, u_d = torch.from_numpy(ys).to(dev), torch.from_numpy(u).to(dev)
-    eng = ParticleFilterEngine(c.host_model(), N, 1, 1.0, "systematic", "streamed", 1234 + rank, local)
+    sharded = PF_MODE == "particles" and world > 1
+    if sharded:
+        eng = ShardedParticleFilterEngine(c.host_model(), N, 1.0, "systematic", seed=1234, device=local)
+        Nloc = N // world
+    else:
+        eng = ParticleFilterEngine(c.host_model(), N, 1, 1.0, "systematic", "streamed", 1234 + rank, local)
+        Nloc = N
     outs = ("means", "log_likelihood")
     bufs = {"means": torch.empty((1, T, 4), device=dev), "log_likelihood": torch.empty((1, T), device=dev)}
 
@@ -215,27 +224,29 @@ def run_ours(args):
     launches = eng.launches() - l0
     phases = {k: v * 1e3 / (args.steps * T) for k, v in eng.phase_times().items()}     # us per time step
     ll = bufs["log_likelihood"].double().sum().item()
+    if sharded and rank != 0:
+        ll = 0.0                                   # per-step scalars of a sharded filter are written by rank 0
     if not np.isfinite(ll):
         raise SystemExit(f"benchmark produced a non-finite log-likelihood ({ll})")
     ms_per_step = ms / args.steps
-    value = world * N * T / (ms_per_step * 1e-3)
-    # roofline: algorithmic bytes of one filter run / its device time (one rank)
-    achieved = N * T * BYTES_PER_PARTICLE_STEP / (ms_per_step * 1e-3) / 1e9
+    value = (N if sharded else world * N) * T / (ms_per_step * 1e-3)
+    # roofline: algorithmic bytes of one rank's share of a run / its device time
+    achieved = Nloc * T * BYTES_PER_PARTICLE_STEP / (ms_per_step * 1e-3) / 1e9
     eng.close()
 
     # ---- end to end through the reference-facing entry point: host emissions in, host estimates out
     params = c.params_bpf()
     ne2e = max(1, min(args.steps, 3))
     gf.bootstrap_particle_filter(params, ys, N, PRNGKey(7), u, 1.0, resampler="systematic", outputs=outs, path="streamed",
-                                 device=local)
+                                 device=local, shard_particles=sharded)
     barrier()
     t0 = time.perf_counter()
     for _ in range(ne2e):
         post = gf.bootstrap_particle_filter(params, ys, N, PRNGKey(7), u, 1.0, resampler="systematic", outputs=outs,
-                                            path="streamed", device=local)
+                                            path="streamed", device=local, shard_particles=sharded)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / ne2e
-    e2e = {"value": world * N * T / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(ys.nbytes + u.nbytes),
+    e2e = {"value": (N if sharded else world * N) * T / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(ys.nbytes + u.nbytes),
            "d2h_bytes_per_step": int(post["means"].nbytes + post["log_likelihood_increments"].nbytes),
            "call": "inference.bootstrap_particle_filter(params, emissions[host], N, key, inputs, 1.0, "
                    "resampler='systematic', outputs=('means','log_likelihood'))", "ms_per_step": e2e_ms}
@@ -282,12 +293,14 @@ def run_ours(args):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"BPF bearings-only (BOT) dx=4 dq=2 dy=2, N=2^{PF_LOG2N} particles per GPU, T={T}, "
+                "config": {"workload": f"BPF bearings-only (BOT) dx=4 dq=2 dy=2, N=2^{PF_LOG2N} particles {'in total' if sharded else 'per GPU'}, T={T}, "
                                        "ess_threshold=1.0 (resample every step), systematic resampling, Philox noise in-kernel, "
                                        "outputs=weighted mean + log-lik per step",
-                           "parallelism": f"trial-sharded x{world} (one independent filter per GPU, no collective)",
+                           "parallelism": (f"ONE filter, particles sharded x{world} (NCCL: weight statistics + scan offsets per step; "
+                                           f"ancestors on other ranks gathered over NVLink peer memory)") if sharded else
+                                          f"trial-sharded x{world} (one independent filter per GPU, no collective)",
                            "l2_policy": "inputs larger than L2 (268 MB particle state per buffer)",
                            "step": "one whole filter run = N*T particle-steps"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

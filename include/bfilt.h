@@ -131,6 +131,9 @@ int bf_pf_shard_export(bf_pf_handle h, void* blob /* BF_SHARD_BLOB_BYTES */);
 int bf_pf_shard_import(bf_pf_handle h, const void* blobs /* shard_world * BF_SHARD_BLOB_BYTES, rank order */);
 int bf_nccl_unique_id(void* id /* BF_NCCL_ID_BYTES */);
 int bf_pf_shard_comm_init(bf_pf_handle h, const void* id /* BF_NCCL_ID_BYTES */);
+/* 1 if the handle has a communicator -- one created for an earlier handle of the same (device, world, rank) is reused
+ * for the life of the process, so only the first sharded handle pays for ncclCommInitRank */
+int bf_pf_shard_comm_ready(bf_pf_handle h);
 
 /* ---------------------------------------------------------------- Gaussian-sum (EKF) filter */
 typedef struct bf_gsf_s* bf_gsf_handle;
