@@ -94,6 +94,18 @@ __device__ __forceinline__ void philox_quad_normals(unsigned long long seed, uin
     box_muller(r.z, r.w, z[2][k], z[3][k]);
   }
 }
+// DQ % 4 == 0: the DQ normals of ONE particle (k-th of its quad) from DQ/4 calls -- nothing to share across the quad,
+// and only one particle's noise is live at a time (large states would otherwise spill).
+template <int DQ>
+__device__ __forceinline__ void philox_particle_normals(unsigned long long seed, uint32_t stream, uint32_t t, uint32_t b,
+                                                        uint32_t quad, uint32_t k, float* z) {
+#pragma unroll
+  for (int c = 0; c < DQ / 4; ++c) {
+    const uint4x r = philox4x32(quad, b, t, stream | ((uint32_t)c << 8) | (k << 16), (uint32_t)seed, (uint32_t)(seed >> 32));
+    box_muller(r.x, r.y, z[4 * c], z[4 * c + 1]);
+    box_muller(r.z, r.w, z[4 * c + 2], z[4 * c + 3]);
+  }
+}
 __device__ __forceinline__ void philox_quad_uniforms(unsigned long long seed, uint32_t stream, uint32_t t, uint32_t b,
                                                      uint32_t quad, float u[4]) {
   const uint4x r = philox4x32(quad, b, t, stream, (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -471,12 +483,11 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #pragma unroll
         for (int k = 0; k < 4; ++k) if (k < nv) o[k] = anc[k];
       }
-      float z[4][DQ];
-#ifdef BF_EXP_NORNG
-      for (int k = 0; k < 4; ++k) for (int c = 0; c < DQ; ++c) z[k][c] = 0.1f * (float)(k + c);
-#else
-      if (!a.noise) philox_quad_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)a.trial, (uint32_t)((a.goff + base) >> 2), z);
-#endif
+      constexpr bool RNG_PER_PARTICLE = (DQ % 4 == 0);
+      float z[RNG_PER_PARTICLE ? 1 : 4][DQ];
+      if (!a.noise && !RNG_PER_PARTICLE)
+        philox_quad_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)a.trial, (uint32_t)((a.goff + base) >> 2),
+                                reinterpret_cast<float(*)[DQ]>(z));
       float llv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -491,11 +502,15 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #pragma unroll
             for (int c = 0; c < DQ; ++c) qn[c] = np_[c];
           } else {
+            if (RNG_PER_PARTICLE)
+              philox_particle_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)a.trial,
+                                          (uint32_t)((a.goff + base) >> 2), (uint32_t)k, z[0]);
+            const float* zk = z[RNG_PER_PARTICLE ? 0 : k];
 #pragma unroll
             for (int r = 0; r < DQ; ++r) {             // q = q0 + L_Q z  (models.py:83, TFP MVN sample)
               float s = mc.q0[r];
 #pragma unroll
-              for (int c = 0; c <= r; ++c) s += mc.LQ[r * DQ + c] * z[k][c];
+              for (int c = 0; c <= r; ++c) s += mc.LQ[r * DQ + c] * zk[c];
               qn[r] = s;
             }
           }
