@@ -20,6 +20,7 @@
 #include "pf_resident.cuh"
 #include "pf_fused.cuh"
 #include "gsf_kernels.cuh"
+#include "gsf_large.cuh"
 
 // ------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -700,6 +701,9 @@ extern "C" int bf_pf_run_host(bf_pf_handle h, const bf_pf_io* hio) {
 struct bf_gsf_s {
   ModelConst mc;
   bf_gsf_config cfg;
+  bool large = false;       // Lorenz-96: state too large for registers, gsf_large.cuh
+  int dx = 0, dy = 0;
+  DevBuf lconst, post_m;
   int64_t launches;
   bool have_carry;
   DevBuf carry_w, carry_m, carry_P;
@@ -713,11 +717,42 @@ extern "C" int bf_gsf_create(const bf_model_desc* model, const bf_gsf_config* cf
   if (cfg->num_trials < 1) return fail(BF_EINVAL, "num_trials must be >= 1");
   bf_gsf_s* h = new (std::nothrow) bf_gsf_s();
   if (!h) return fail(BF_ENOMEM, "out of host memory");
-  int rc = build_model_const(model, &h->mc);
-  if (rc) { delete h; return rc; }
+  LargeConst* lch = nullptr;
+  int rc;
+  if (model && model->model_id == BF_MODEL_L96) {
+    // large-state path: dims and the diagonal noise covariances travel in a device-resident LargeConst
+    const int dx = model->dx, dy = model->dy;
+    if (dx < 4 || dx > GL_MAXDX || (dx & 1) || dy != dx / 2 || model->dq != dx || model->dr != dy || model->n_theta != 4 ||
+        !model->theta || !model->q0 || !model->Q || !model->r0 || !model->R || !model->m0 || !model->P0) {
+      delete h; return fail(BF_EINVAL, "L96 needs even 4 <= dx <= %d, dq = dx, dy = dr = dx/2, theta = [F dt c1 c2] and every array", GL_MAXDX);
+    }
+    for (int i = 0; i < dx; ++i) for (int j = 0; j < dx; ++j) if (i != j && model->Q[i * dx + j] != 0.0f) { delete h; return fail(BF_ENOMODEL, "L96: dynamics_noise_covariance must be diagonal"); }
+    for (int i = 0; i < dy; ++i) for (int j = 0; j < dy; ++j) if (i != j && model->R[i * dy + j] != 0.0f) { delete h; return fail(BF_ENOMODEL, "L96: emission_noise_covariance must be diagonal"); }
+    lch = new (std::nothrow) LargeConst();
+    if (!lch) { delete h; return fail(BF_ENOMEM, "out of host memory"); }
+    memset(lch, 0, sizeof *lch);
+    lch->dx = dx; lch->dy = dy; lch->F = model->theta[0]; lch->dt = model->theta[1]; lch->c1 = model->theta[2]; lch->c2 = model->theta[3];
+    for (int i = 0; i < dx; ++i) { lch->q0[i] = model->q0[i]; lch->qd[i] = model->Q[i * dx + i]; lch->m0[i] = model->m0[i]; }
+    for (int i = 0; i < dy; ++i) { lch->r0[i] = model->r0[i]; lch->rd[i] = model->R[i * dy + i]; }
+    for (int i = 0; i < dx * dx; ++i) lch->P0[i] = model->P0[i];
+    h->large = true; h->dx = dx; h->dy = dy;
+    memset(&h->mc, 0, sizeof h->mc); h->mc.model_id = BF_MODEL_L96; h->mc.dx = dx; h->mc.dy = dy; h->mc.dq = dx; h->mc.dr = dy;
+  } else {
+    rc = build_model_const(model, &h->mc);
+    if (rc) { delete h; return rc; }
+    h->dx = h->mc.dx; h->dy = h->mc.dy;
+  }
   h->cfg = *cfg; h->launches = 0; h->have_carry = false;
   cudaError_t e = cudaSetDevice(cfg->device);
-  if (e != cudaSuccess) { delete h; return fail(BF_ECUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { delete lch; delete h; return fail(BF_ECUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e)); }
+  if (lch) {
+    const size_t bmx = (size_t)cfg->num_trials * cfg->num_components * h->dx;
+    if (h->lconst.ensure(sizeof(LargeConst)) || h->post_m.ensure(bmx * 4) ||
+        cudaMemcpy(h->lconst.p, lch, sizeof(LargeConst), cudaMemcpyHostToDevice) != cudaSuccess) {
+      delete lch; bf_gsf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the large-state constants failed");
+    }
+    delete lch;
+  }
   if ((e = pool_setup(cfg->device)) != cudaSuccess) { delete h; return fail(BF_ECUDA, "memory pool setup: %s", cudaGetErrorString(e)); }
   h->nsm = 148;
   cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -733,7 +768,7 @@ extern "C" int bf_gsf_destroy(bf_gsf_handle h) {
   if (!h) return BF_OK;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
-  h->carry_w.release(); h->carry_m.release(); h->carry_P.release();
+  h->carry_w.release(); h->carry_m.release(); h->carry_P.release(); h->lconst.release(); h->post_m.release();
   for (DevBuf& b : h->hbuf) b.release();
   delete h;
   return BF_OK;
@@ -797,6 +832,21 @@ extern "C" int bf_gsf_run(bf_gsf_handle h, const bf_gsf_io* io, void* stream) {
   int rc = gsf_check_io(h, io);
   if (rc) return rc;
   CUDA_OK(cudaSetDevice(h->cfg.device));
+  if (h->large) {
+    GsfLargeArgs a;
+    a.M = h->cfg.num_components; a.T = io->T; a.resume = io->resume; a.emissions_per_trial = io->emissions_per_trial; a.flags = h->cfg.flags;
+    a.lc = h->lconst.as<LargeConst>();
+    a.emissions = io->emissions; a.inputs = io->inputs; a.init_means = io->init_means; a.init_covs = io->init_covs; a.init_weights = io->init_weights;
+    a.carry_w = h->carry_w.as<float>(); a.carry_m = h->carry_m.as<float>(); a.carry_P = h->carry_P.as<float>(); a.post_m = h->post_m.as<float>();
+    a.out_weights = io->out_weights; a.out_means = io->out_means; a.out_covs = io->out_covs; a.out_pred_means = io->out_pred_means;
+    a.out_pred_covs = io->out_pred_covs; a.out_loglik = io->out_loglik; a.out_mix_mean = io->out_mix_mean;
+    const size_t smem = gsf_large_smem_bytes(h->dx, h->dy, a.M);
+    CUDA_OK(cudaFuncSetAttribute(k_gsf_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gsf_large<<<h->cfg.num_trials, GL_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    LAUNCH_OK();
+    h->launches += 1; h->have_carry = true;
+    return BF_OK;
+  }
   GsfRun fn{h, io, (cudaStream_t)stream};
   rc = bf_dispatch_model(h->mc, fn);
   if (rc == -3) return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", h->mc.model_id, h->mc.dx, h->mc.dy);

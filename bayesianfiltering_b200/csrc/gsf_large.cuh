@@ -1,0 +1,278 @@
+// gsf_large.cuh -- Gaussian-sum (EKF) filter for LARGE states: Lorenz-96, dx up to 64 (BASELINE configs[3]: dx = 40,
+// dy = 20, M = 256 components x 4096 trials).
+//
+// Same recursion as gsf_kernels.cuh (gaussfiltax/inference.py:333-365: `_condition_on` :72-105 on the carried
+// prediction, max-shifted reweighting :347-350, `_predict` :51-70), but a component's covariance is 6.4 KB: it cannot
+// live in registers, and the M components of a trial (1.6 MB) do not fit one SM's shared memory, so the carry
+// (predicted mean and covariance of every component) STREAMS through HBM once per step -- read, update, predict,
+// write back, 8 (dx + dx^2) bytes per component-step -- while one component at a time is worked on in a warp's
+// shared-memory workspace.  One CTA per trial; its warps take the trial's components in turn; the only coupling
+// (max and sum of the M log-likelihoods) happens in shared memory after the pass.  Predict does not depend on the
+// weights, so update and predict of a component are fused in one visit.
+//
+// Model (oracle/models.py L96; gaussfiltax/nonlinearities.py:37-52 with the advection term restored):
+//   f_i = x_i + dt ((x_{i+1} - x_{i-2}) x_{i-1} - x_i + F) + q_i         Jacobian: 4 non-zeros per row (cyclic band)
+//   h_j = c1 x_{2j} + c2 x_{2j}^2 + r_j,  j < dx/2                       Jacobian: 1 non-zero per row
+// Q and R must be diagonal here (they are in the configs).  Arithmetic mirrors the reference: K = solve(S + 1e-6
+// [every element], H P)^T by LU with partial pivoting, P+ = P - (K S) K^T with the un-jittered S, log-likelihood by
+// Cholesky of the un-jittered S.
+#pragma once
+#include "common.cuh"
+#include "../../include/bfilt.h"
+
+#define GL_MAXDX 64
+#define GL_WARPS 4
+
+struct LargeConst {                 // lives in global memory (too big for a kernel parameter)
+  int dx, dy;
+  float F, dt, c1, c2;
+  float q0[GL_MAXDX], qd[GL_MAXDX], m0[GL_MAXDX];       // dynamics noise bias / variance (diagonal Q), initial mean
+  float r0[GL_MAXDX / 2], rd[GL_MAXDX / 2];             // emission noise bias / variance (diagonal R)
+  float P0[GL_MAXDX * GL_MAXDX];
+};
+
+struct GsfLargeArgs {
+  int M, T, resume, emissions_per_trial, flags;
+  const LargeConst* lc;
+  const float* emissions; const float* inputs;
+  const float* init_means; const float* init_covs; const float* init_weights;
+  float* carry_w; float* carry_m; float* carry_P;        // [B,M], [B,M,dx], [B,M,dx,dx]  (predicted moments)
+  float* post_m;                                         // [B,M,dx] scratch: posterior means of the current step
+  float* out_weights; float* out_means; float* out_covs; float* out_pred_means; float* out_pred_covs;
+  float* out_loglik; float* out_mix_mean;
+};
+
+static inline size_t gsf_large_smem_bytes(int dx, int dy, int M) {
+  const size_t per_warp = (size_t)dx * dx + 2 * (size_t)dy * dx + 2 * (size_t)dy * dy + 4 * (size_t)dx + 4 * (size_t)dy + 8;
+  return (GL_WARPS * per_warp + (size_t)M + 64) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(GL_WARPS * 32)
+k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const LargeConst& lc = *a.lc;
+  const int dx = lc.dx, dy = lc.dy, M = a.M, T = a.T, b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t per_warp = (size_t)dx * dx + 2 * (size_t)dy * dx + 2 * (size_t)dy * dy + 4 * (size_t)dx + 4 * (size_t)dy + 8;
+  float* ws = smem + warp * per_warp;
+  float* P = ws;                         // [dx,dx]
+  float* X = P + dx * dx;                // [dy,dx]  H P, then X = solve(S', H P)  (K = X^T)
+  float* KS = X + dy * dx;               // [dx,dy]  K S ; X and KS together are reused as F P [dx,dx] in the predict
+  float* S = KS + dx * dy;               // [dy,dy]  un-jittered innovation covariance
+  float* Sj = S + dy * dy;               // [dy,dy]  S + 1e-6, LU-factored in place; later the Cholesky factor of S
+  float* mv = Sj + dy * dy;              // [dx] mean
+  float* mn = mv + dx;                   // [dx] new mean
+  float* fa = mn + dx;                   // [dx] dt * x_{i-1}
+  float* fb = fa + dx;                   // [dx] dt * (x_{i+1} - x_{i-2})
+  float* hv = fb + dx;                   // [dy] dh_j/dx_{2j}
+  float* dv = hv + dy;                   // [dy] innovation
+  float* zv = dv + dy;                   // [dy] scratch
+  float* lr = zv + dy;                   // [dy] LU multipliers of the current column
+  float* s_ll = smem + GL_WARPS * per_warp;      // [M] log-likelihoods, then normalised weights
+  float* s_red = s_ll + M;                        // [64]
+  const float jitter = (a.flags & BF_GSF_NO_JITTER) ? 0.0f : 1e-6f;
+  const bool cov_plus_p = (a.flags & BF_GSF_COV_PLUS_P) != 0;
+  const float dt = lc.dt, onemdt = 1.0f - lc.dt;
+
+  auto wrap = [&](int i) { return i < 0 ? i + dx : (i >= dx ? i - dx : i); };
+
+  // ---- EKF predict of the component in (mv, P): mv <- f(mv), P <- F P F^T + Q     (inference.py:51-70)
+  auto predict = [&](float u) {
+    for (int i = lane; i < dx; i += 32) {
+      const float xm1 = mv[wrap(i - 1)], xm2 = mv[wrap(i - 2)], xp1 = mv[wrap(i + 1)];
+      fa[i] = dt * xm1;
+      fb[i] = dt * (xp1 - xm2);
+      mn[i] = mv[i] + dt * ((xp1 - xm2) * xm1 - mv[i] + lc.F) + lc.q0[i];
+    }
+    __syncwarp();
+    float* FP = X;                       // [dx,dx] over X and KS
+    // row i of F: (i-2): -fa_i, (i-1): fb_i, (i): 1-dt, (i+1): fa_i   (oracle/models.py L96.Fx, summed in column order)
+    for (int idx = lane; idx < dx * dx; idx += 32) {
+      const int i = idx / dx, c = idx - i * dx;
+      const int j2 = wrap(i - 2), j1 = wrap(i - 1), jp = wrap(i + 1);
+      FP[idx] = -fa[i] * P[j2 * dx + c] + fb[i] * P[j1 * dx + c] + onemdt * P[i * dx + c] + fa[i] * P[jp * dx + c];
+    }
+    __syncwarp();
+    for (int idx = lane; idx < dx * dx; idx += 32) {
+      const int i = idx / dx, c = idx - i * dx;
+      const int j2 = wrap(c - 2), j1 = wrap(c - 1), jp = wrap(c + 1);
+      const float v = -fa[c] * FP[i * dx + j2] + fb[c] * FP[i * dx + j1] + onemdt * FP[i * dx + c] + fa[c] * FP[i * dx + jp];
+      const float add = cov_plus_p ? P[idx] : ((i == c) ? lc.qd[i] : 0.0f);     // this loop reads FP only, P[idx] is this lane's own
+      P[idx] = v + add;
+    }
+    for (int i = lane; i < dx; i += 32) mv[i] = mn[i];
+    __syncwarp();
+  };
+
+  for (int t = 0; t < T; ++t) {
+    const float* y = a.emissions + ((size_t)(a.emissions_per_trial ? b : 0) * T + t) * dy;
+    const float u = a.inputs ? a.inputs[t] : 0.0f;
+    const size_t bt = (size_t)b * T + t;
+
+    for (int m = warp; m < M; m += GL_WARPS) {
+      const size_t bm = (size_t)b * M + m;
+      // ---- load the carried prediction
+      const bool fresh = (t == 0 && !a.resume);
+      const float* msrc = fresh ? a.init_means + bm * dx : a.carry_m + bm * dx;
+      const float* Psrc = fresh ? (a.init_covs ? a.init_covs + bm * dx * dx : lc.P0) : a.carry_P + bm * dx * dx;
+      for (int i = lane; i < dx; i += 32) mv[i] = msrc[i];
+      for (int i = lane; i < dx * dx; i += 32) P[i] = Psrc[i];
+      __syncwarp();
+      if (fresh && (a.flags & BF_GSF_PREDICT_FIRST)) predict(u);
+
+      // ---- `_condition_on`  (inference.py:72-105)
+      for (int j = lane; j < dy; j += 32) {
+        const float xs = mv[2 * j];
+        hv[j] = lc.c1 + 2.0f * lc.c2 * xs;
+        dv[j] = y[j] - (lc.c1 * xs + lc.c2 * xs * xs + lc.r0[j]);
+      }
+      __syncwarp();
+      for (int idx = lane; idx < dy * dx; idx += 32) {           // H P
+        const int j = idx / dx, c = idx - j * dx;
+        X[idx] = hv[j] * P[(2 * j) * dx + c];
+      }
+      __syncwarp();
+      for (int idx = lane; idx < dy * dy; idx += 32) {           // S = H_r R H_r^T + H P H^T ; S' = S + 1e-6
+        const int j = idx / dy, k = idx - j * dy;
+        const float s = ((j == k) ? lc.rd[j] : 0.0f) + X[j * dx + 2 * k] * hv[k];
+        S[idx] = s; Sj[idx] = s + jitter;
+      }
+      __syncwarp();
+      // LU with partial pivoting of S', applied to the dx right-hand sides in X   (jnp.linalg.solve, utils.py:259)
+      for (int k = 0; k < dy; ++k) {
+        float best = -1.0f; int bi = k;
+        for (int r = k + lane; r < dy; r += 32) { const float v = fabsf(Sj[r * dy + k]); if (v > best) { best = v; bi = r; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(BF_FULL, best, o); const int oi = __shfl_xor_sync(BF_FULL, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (bi != k) {
+          for (int c = lane; c < dy; c += 32) { const float t0 = Sj[k * dy + c]; Sj[k * dy + c] = Sj[bi * dy + c]; Sj[bi * dy + c] = t0; }
+          for (int c = lane; c < dx; c += 32) { const float t0 = X[k * dx + c]; X[k * dx + c] = X[bi * dx + c]; X[bi * dx + c] = t0; }
+        }
+        __syncwarp();
+        const float piv = Sj[k * dy + k];
+        for (int r = k + 1 + lane; r < dy; r += 32) lr[r] = Sj[r * dy + k] / piv;
+        __syncwarp();
+        const int nr = dy - k - 1, ncs = dy - k - 1;
+        for (int idx = lane; idx < nr * (ncs + dx); idx += 32) {
+          const int r = k + 1 + idx / (ncs + dx), cc = idx % (ncs + dx);
+          if (cc < ncs) Sj[r * dy + k + 1 + cc] -= lr[r] * Sj[k * dy + k + 1 + cc];
+          else X[r * dx + (cc - ncs)] -= lr[r] * X[k * dx + (cc - ncs)];
+        }
+        __syncwarp();
+      }
+      for (int k = dy - 1; k >= 0; --k) {                        // back substitution, one column of X per lane
+        for (int c = lane; c < dx; c += 32) {
+          float s = X[k * dx + c];
+          for (int j = k + 1; j < dy; ++j) s -= Sj[k * dy + j] * X[j * dx + c];
+          X[k * dx + c] = s / Sj[k * dy + k];
+        }
+        __syncwarp();
+      }
+      for (int idx = lane; idx < dx * dy; idx += 32) {           // K S,  K = X^T
+        const int i = idx / dy, j = idx - i * dy;
+        float s = 0.0f;
+        for (int k = 0; k < dy; ++k) s += X[k * dx + i] * S[k * dy + j];
+        KS[idx] = s;
+      }
+      __syncwarp();
+      for (int idx = lane; idx < dx * dx; idx += 32) {           // P - (K S) K^T      (inference.py:101)
+        const int i = idx / dx, c = idx - i * dx;
+        float s = 0.0f;
+        for (int k = 0; k < dy; ++k) s += KS[i * dy + k] * X[k * dx + c];
+        P[idx] -= s;
+      }
+      for (int i = lane; i < dx; i += 32) {                      // m + K (y - h(m))   (inference.py:102)
+        float s = 0.0f;
+        for (int k = 0; k < dy; ++k) s += X[k * dx + i] * dv[k];
+        mv[i] += s;
+      }
+      __syncwarp();
+      // log N(y; h(m), S): Cholesky of the un-jittered S (TFP), column by column, in Sj
+      float logdet = 0.0f;
+      for (int j = 0; j < dy; ++j) {
+        float s = S[j * dy + j];
+        for (int k = 0; k < j; ++k) s -= Sj[j * dy + k] * Sj[j * dy + k];
+        const float ljj = sqrtf(s);
+        logdet += logf(ljj);
+        __syncwarp();
+        for (int i = j + lane; i < dy; i += 32) {
+          float v = S[i * dy + j];
+          for (int k = 0; k < j; ++k) v -= Sj[i * dy + k] * Sj[j * dy + k];
+          Sj[i * dy + j] = (i == j) ? ljj : v / ljj;
+        }
+        __syncwarp();
+      }
+      float ss = 0.0f;
+      for (int i = 0; i < dy; ++i) {                             // forward substitution (uniform across the warp)
+        float s = dv[i];
+        for (int k = 0; k < i; ++k) s -= Sj[i * dy + k] * zv[k];
+        const float z = s / Sj[i * dy + i];
+        __syncwarp();
+        if (lane == 0) zv[i] = z;
+        __syncwarp();
+        ss += z * z;
+      }
+      if (lane == 0) s_ll[m] = -0.5f * ss - logdet - 0.5f * (float)dy * 1.8378770664093453f;
+      // posterior outputs, and the posterior mean for the mixture mean after the reweighting
+      const size_t btm = bt * M + m;
+      for (int i = lane; i < dx; i += 32) {
+        a.post_m[bm * dx + i] = mv[i];
+        if (a.out_means) a.out_means[btm * dx + i] = mv[i];
+      }
+      if (a.out_covs) for (int i = lane; i < dx * dx; i += 32) a.out_covs[btm * dx * dx + i] = P[i];
+      __syncwarp();
+      // ---- `_predict`, then the carry goes back to HBM
+      predict(u);
+      for (int i = lane; i < dx; i += 32) {
+        a.carry_m[bm * dx + i] = mv[i];
+        if (a.out_pred_means) a.out_pred_means[btm * dx + i] = mv[i];
+      }
+      for (int i = lane; i < dx * dx; i += 32) {
+        a.carry_P[bm * dx * dx + i] = P[i];
+        if (a.out_pred_covs) a.out_pred_covs[btm * dx * dx + i] = P[i];
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---- lls -= max ; w = exp(lls) * w ; w /= sum(w)       (inference.py:347-350)
+    float mx = -INFINITY;
+    for (int m = tid; m < M; m += GL_WARPS * 32) mx = fmaxf(mx, s_ll[m]);
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = s_red[0];
+    for (int w = 1; w < GL_WARPS; ++w) mx = fmaxf(mx, s_red[w]);
+    float z = 0.0f;
+    for (int m = tid; m < M; m += GL_WARPS * 32) {
+      const size_t bm = (size_t)b * M + m;
+      const float wprev = (t == 0 && !a.resume) ? (a.init_weights ? a.init_weights[bm] : 1.0f / (float)M) : a.carry_w[bm];
+      const float e = expf(s_ll[m] - mx) * wprev;
+      s_ll[m] = e; z += e;
+    }
+    z = warp_sum(z);
+    __syncthreads();
+    if (lane == 0) s_red[32 + warp] = z;
+    __syncthreads();
+    float Z = 0.0f;
+    for (int w = 0; w < GL_WARPS; ++w) Z += s_red[32 + w];
+    for (int m = tid; m < M; m += GL_WARPS * 32) {
+      const float w = s_ll[m] / Z;
+      s_ll[m] = w;
+      a.carry_w[(size_t)b * M + m] = w;
+      if (a.out_weights) a.out_weights[bt * M + m] = w;
+    }
+    if (tid == 0 && a.out_loglik) a.out_loglik[bt] = mx + logf(Z);
+    __syncthreads();
+    if (a.out_mix_mean) {
+      for (int i = tid; i < dx; i += GL_WARPS * 32) {
+        float s = 0.0f;
+        for (int m = 0; m < M; ++m) s += s_ll[m] * a.post_m[((size_t)b * M + m) * dx + i];
+        a.out_mix_mean[bt * dx + i] = s;
+      }
+    }
+    __syncthreads();
+  }
+}

@@ -102,6 +102,15 @@ def lorenz63(sigma=10.0, rho=28.0, beta=2.667, dt=0.01, c=0.001):
     return RegisteredModel(_lib.MODEL_L63, "l63", 3, 3, 1, 1, [sigma, rho, beta, dt, c])
 
 
+def lorenz96(dx=40, F=8.0, dt=0.01, c1=1.0, c2=0.05):
+    """Lorenz-96, Euler step, every second state observed through c1 x + c2 x^2 (BASELINE configs[3]; the constants of
+    gaussfiltax/nonlinearities.py:37-41 with the advection term restored).  Gaussian-sum filter only, on the
+    large-state kernel (csrc/gsf_large.cuh); the noise covariances must be diagonal."""
+    if dx % 2 or not 4 <= dx <= 64:
+        raise ValueError("lorenz96 needs an even 4 <= dx <= 64")
+    return RegisteredModel(_lib.MODEL_L96, "l96", dx, dx, dx // 2, dx // 2, [F, dt, c1, c2])
+
+
 def linear_gaussian(A, H):
     A = np.asarray(A, dtype=np.float32); H = np.asarray(H, dtype=np.float32)
     dx, dy = A.shape[0], H.shape[0]

@@ -30,6 +30,7 @@ def _engine(c, M, B=1):
     ("ungm_q10", 20, 33),
     ("bot1", 20, 8), ("bot2", 20, 5), ("l63", 20, 6), ("lg3", 20, 4), ("lg42", 20, 7), ("lg8", 12, 3),
     ("sin1d", 20, 5), ("sin3d", 4, 40),      # sin3d: the fp32 EKF loses positive definiteness at t=4
+    ("l96s", 12, 9), ("l96", 6, 5),          # large-state kernel (gsf_large.cuh): Lorenz-96 d=8 and BASELINE configs[3]'s d=40
 ])
 def test_gsf_stepwise_parity(name, T, M):
     """Each step from the ORACLE's carry (weights, predicted means, predicted covariances): one `_step`
@@ -136,6 +137,35 @@ def test_gsf_device_tensor_mode_and_shared_emissions():
         assert np.array_equal(dev[k].cpu().numpy(), host[k]), k
     assert eng.launches() == 2
     eng.close()
+
+
+def test_gsf_lorenz96_whole_run_batch_and_resume():
+    """BASELINE configs[3] shape at test size: Lorenz-96 d=40, M components x B trials, against the oracle over a
+    whole run (the map is only mildly expanding at dt = 0.01), trial batching and chunked resume bit for bit."""
+    c = case("l96")
+    T, M, B = 8, 6, 3
+    ys = np.stack([c.simulate(T, 300 + b)[1] for b in range(B)])
+    means0 = np.stack([c.gsf_means0(M, 310 + b) for b in range(B)])
+    eng = _engine(c, M, B)
+    full = eng.run_host(ys, init_means=means0, outputs=ALL_OUT)
+    a = eng.run_host(ys[:, :3], init_means=means0, outputs=ALL_OUT)
+    b2 = eng.run_host(ys[:, 3:], outputs=ALL_OUT, resume=True)
+    eng.close()
+    for name in ALL_OUT:
+        assert np.array_equal(np.concatenate([a[name], b2[name]], axis=1), full[name]), name
+    for b in range(B):
+        ref = ogsf.gaussian_sum_filter(c.omodel, ys[b], None, means0[b], c.P0, c.Q, c.q0, c.R, c.r0)
+        ref8 = ogsf.gaussian_sum_filter(c.omodel, ys[b].astype(np.float64), None, means0[b].astype(np.float64), c.P0.astype(np.float64),
+                                        c.Q.astype(np.float64), c.q0.astype(np.float64), c.R.astype(np.float64), c.r0.astype(np.float64))
+        for k in FIELDS:
+            close_cond(np.swapaxes(full[k][b], 0, 1), ref[k], ref8[k], rtol=2e-5, k=16.0, what=f"l96 {k} trial {b}")
+        ll_scale = max(1.0, float(np.max(np.abs(ref["loglik_inc"]))))
+        assert np.max(np.abs(full["log_likelihood"][b] - ref["loglik_inc"])) <= 2e-5 * ll_scale + 16 * np.max(np.abs(ref["loglik_inc"] - ref8["loglik_inc"]))
+    np.testing.assert_allclose(full["weights"].sum(axis=-1), 1.0, rtol=1e-5)
+    with pytest.raises(ValueError):                      # full noise covariances are not supported on the large-state path
+        from bayesianfiltering_b200 import zoo
+        from bayesianfiltering_b200.engine import GaussianSumFilterEngine
+        GaussianSumFilterEngine(zoo.lorenz96(8).host_model(Q=np.eye(8, dtype=np.float32) + 0.1), 2, 1, 0)
 
 
 def test_gsf_errors_are_loud():
