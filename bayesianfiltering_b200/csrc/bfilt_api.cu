@@ -841,8 +841,13 @@ extern "C" int bf_gsf_run(bf_gsf_handle h, const bf_gsf_io* io, void* stream) {
     a.out_weights = io->out_weights; a.out_means = io->out_means; a.out_covs = io->out_covs; a.out_pred_means = io->out_pred_means;
     a.out_pred_covs = io->out_pred_covs; a.out_loglik = io->out_loglik; a.out_mix_mean = io->out_mix_mean;
     const size_t smem = gsf_large_smem_bytes(h->dx, h->dy, a.M);
-    CUDA_OK(cudaFuncSetAttribute(k_gsf_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gsf_large<<<h->cfg.num_trials, GL_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    if (h->dx == 40) {
+      CUDA_OK(cudaFuncSetAttribute(k_gsf_large<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_gsf_large<40><<<h->cfg.num_trials, GL_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(k_gsf_large<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_gsf_large<0><<<h->cfg.num_trials, GL_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    }
     LAUNCH_OK();
     h->launches += 1; h->have_carry = true;
     return BF_OK;

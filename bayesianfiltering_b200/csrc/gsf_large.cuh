@@ -21,14 +21,14 @@
 #include "../../include/bfilt.h"
 
 #define GL_MAXDX 64
-#define GL_WARPS 4
+#define GL_WARPS 6                  // 104 KB of shared memory per CTA at dx = 40: two CTAs (12 warps) per SM
 
 struct LargeConst {                 // lives in global memory (too big for a kernel parameter)
   int dx, dy;
   float F, dt, c1, c2;
   float q0[GL_MAXDX], qd[GL_MAXDX], m0[GL_MAXDX];       // dynamics noise bias / variance (diagonal Q), initial mean
   float r0[GL_MAXDX / 2], rd[GL_MAXDX / 2];             // emission noise bias / variance (diagonal R)
-  float P0[GL_MAXDX * GL_MAXDX];
+  alignas(16) float P0[GL_MAXDX * GL_MAXDX];       // read with 128-bit loads
 };
 
 struct GsfLargeArgs {
@@ -47,11 +47,14 @@ static inline size_t gsf_large_smem_bytes(int dx, int dy, int M) {
   return (GL_WARPS * per_warp + (size_t)M + 64) * sizeof(float);
 }
 
+// DXT: compile-time state dimension (0 = read it from LargeConst): index arithmetic folds, and for DXT = 40 the two
+// rank-dy products are register-tiled.
+template <int DXT>
 __global__ void __launch_bounds__(GL_WARPS * 32)
 k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
   extern __shared__ __align__(16) float smem[];
   const LargeConst& lc = *a.lc;
-  const int dx = lc.dx, dy = lc.dy, M = a.M, T = a.T, b = blockIdx.x;
+  const int dx = DXT ? DXT : lc.dx, dy = DXT ? DXT / 2 : lc.dy, M = a.M, T = a.T, b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t per_warp = (size_t)dx * dx + 2 * (size_t)dy * dx + 2 * (size_t)dy * dy + 4 * (size_t)dx + 4 * (size_t)dy + 8;
   float* ws = smem + warp * per_warp;
@@ -116,7 +119,9 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
       const float* msrc = fresh ? a.init_means + bm * dx : a.carry_m + bm * dx;
       const float* Psrc = fresh ? (a.init_covs ? a.init_covs + bm * dx * dx : lc.P0) : a.carry_P + bm * dx * dx;
       for (int i = lane; i < dx; i += 32) mv[i] = msrc[i];
-      for (int i = lane; i < dx * dx; i += 32) P[i] = Psrc[i];
+#pragma unroll 4
+      for (int i = lane; i < dx * dx / 4; i += 32)           // dx is even: dx^2 is a multiple of 4, rows are 16-byte aligned
+        reinterpret_cast<float4*>(P)[i] = reinterpret_cast<const float4*>(Psrc)[i];
       __syncwarp();
       if (fresh && (a.flags & BF_GSF_PREDICT_FIRST)) predict(u);
 
@@ -171,19 +176,70 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
         }
         __syncwarp();
       }
-      for (int idx = lane; idx < dx * dy; idx += 32) {           // K S,  K = X^T
-        const int i = idx / dy, j = idx - i * dy;
-        float s = 0.0f;
-        for (int k = 0; k < dy; ++k) s += X[k * dx + i] * S[k * dy + j];
-        KS[idx] = s;
+      if constexpr (DXT == 40) {
+        // register tiles: lane = (row group of 5) x (column group): 25 / 50 accumulators, 10 / 15 loads per 25 / 50 FMAs
+        const int rg = lane >> 2, cg = lane & 3;
+        {
+          float acc[5][5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) acc[i][j] = 0.0f;
+          for (int k = 0; k < 20; ++k) {                           // K S,  K = X^T
+            float xk[5], sk[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) xk[i] = X[k * 40 + 5 * rg + i];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) sk[j] = S[k * 20 + 5 * cg + j];
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+              for (int j = 0; j < 5; ++j) acc[i][j] += xk[i] * sk[j];
+          }
+#pragma unroll
+          for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) KS[(5 * rg + i) * 20 + 5 * cg + j] = acc[i][j];
+        }
+        __syncwarp();
+        {
+          float acc[5][10];
+#pragma unroll
+          for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 10; ++j) acc[i][j] = 0.0f;
+          for (int k = 0; k < 20; ++k) {                           // (K S) K^T
+            float ks[5], xr[10];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) ks[i] = KS[(5 * rg + i) * 20 + k];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) xr[j] = X[k * 40 + 10 * cg + j];
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+              for (int j = 0; j < 10; ++j) acc[i][j] += ks[i] * xr[j];
+          }
+#pragma unroll
+          for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 10; ++j) P[(5 * rg + i) * 40 + 10 * cg + j] -= acc[i][j];      // P - (K S) K^T  (inference.py:101)
+        }
+      } else {
+        for (int idx = lane; idx < dx * dy; idx += 32) {           // K S,  K = X^T
+          const int i = idx / dy, j = idx - i * dy;
+          float s = 0.0f;
+          for (int k = 0; k < dy; ++k) s += X[k * dx + i] * S[k * dy + j];
+          KS[idx] = s;
+        }
+        __syncwarp();
+        for (int idx = lane; idx < dx * dx; idx += 32) {           // P - (K S) K^T      (inference.py:101)
+          const int i = idx / dx, c = idx - i * dx;
+          float s = 0.0f;
+          for (int k = 0; k < dy; ++k) s += KS[i * dy + k] * X[k * dx + c];
+          P[idx] -= s;
+        }
       }
       __syncwarp();
-      for (int idx = lane; idx < dx * dx; idx += 32) {           // P - (K S) K^T      (inference.py:101)
-        const int i = idx / dx, c = idx - i * dx;
-        float s = 0.0f;
-        for (int k = 0; k < dy; ++k) s += KS[i * dy + k] * X[k * dx + c];
-        P[idx] -= s;
-      }
       for (int i = lane; i < dx; i += 32) {                      // m + K (y - h(m))   (inference.py:102)
         float s = 0.0f;
         for (int k = 0; k < dy; ++k) s += X[k * dx + i] * dv[k];
@@ -230,9 +286,11 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
         a.carry_m[bm * dx + i] = mv[i];
         if (a.out_pred_means) a.out_pred_means[btm * dx + i] = mv[i];
       }
-      for (int i = lane; i < dx * dx; i += 32) {
-        a.carry_P[bm * dx * dx + i] = P[i];
-        if (a.out_pred_covs) a.out_pred_covs[btm * dx * dx + i] = P[i];
+#pragma unroll 4
+      for (int i = lane; i < dx * dx / 4; i += 32)
+        reinterpret_cast<float4*>(a.carry_P + bm * dx * dx)[i] = reinterpret_cast<const float4*>(P)[i];
+      if (a.out_pred_covs) for (int i = lane; i < dx * dx; i += 32) {
+        a.out_pred_covs[btm * dx * dx + i] = P[i];
       }
       __syncwarp();
     }
