@@ -38,6 +38,10 @@ PF_MODE = os.environ.get("BF_BENCH_MODE", "trials")
 PF_T = int(os.environ.get("BF_BENCH_T", "1000"))
 GSF_M, GSF_B, GSF_T = 100, 1024, 500
 BYTES_PER_PARTICLE_STEP = 84     # 4*(4*dx + 5) for dx=4, in-kernel RNG, resampling step
+# DRAM bytes the fused kernel actually moves per particle-step: ncu --set full, dram__bytes_read+write of one launch /
+# (N*T) (profiles/r1_e_pf_fused_T40_ncu.txt).  Below the algorithmic figure because the resampled copy of the
+# particles is never materialised (the gather is fused into the next step's propagate).
+MOVED_BYTES_PER_PARTICLE_STEP = 52.8
 METRIC, UNIT = "particle-steps/s", "particle-steps/s"
 
 
@@ -146,7 +150,7 @@ def run_reference(args):
     v = float(np.mean(times))
     N = 1 << 17
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * (1 << 17) * cores / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"BPF bearings-only dx=4 dy=2, resample every step, systematic; CPU sample: {sample}"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -304,7 +308,10 @@ def run_ours(args):
                            "l2_policy": "inputs larger than L2 (268 MB particle state per buffer)",
                            "step": "one whole filter run = N*T particle-steps"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
+                             "traffic": MOVED_BYTES_PER_PARTICLE_STEP * Nloc * T, "traffic_source": "ncu capture of a T=40 launch, scaled to this T",
+                             "moved_bytes_per_particle_step": MOVED_BYTES_PER_PARTICLE_STEP,
+                             "peak_source": peak_src, "bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
+                             "bound_note": "this model is instruction-issue-bound (~500 SASS instructions per particle-step, issue slots 56% busy, DRAM 25% of peak)",
                              "kernel": "k_pf_fused (persistent cooperative kernel, all T steps in one launch)",
                              "phase_us_per_time_step": phases},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "gsf": gsf}

@@ -168,6 +168,24 @@ def test_gsf_lorenz96_whole_run_batch_and_resume():
         GaussianSumFilterEngine(zoo.lorenz96(8).host_model(Q=np.eye(8, dtype=np.float32) + 0.1), 2, 1, 0)
 
 
+def test_monte_carlo_trial_driver_single_process():
+    """montecarlo.*_trials without a process group: the reference drivers' Nsim loop (BOT_Experiment_script.py:89) as one call."""
+    from bayesianfiltering_b200 import montecarlo as mc
+    c = case("lg3")
+    T, B = 20, 6
+    sims = [c.simulate(T, 400 + b) for b in range(B)]
+    xs = np.stack([s[0] for s in sims]); ys = np.stack([s[1] for s in sims])
+    g = mc.gaussian_sum_filter_trials(c.params_nlssm(), ys, 4, true_states=xs, key=3)
+    p = mc.particle_filter_trials(c.params_bpf(), ys, 4096, true_states=xs, key=3)
+    for out in (g, p):
+        assert out["means"].shape == (B, T, 3) and out["rmse"].shape == (B,) and out["marginal_log_likelihood"].shape == (B,)
+        assert np.all(np.isfinite(out["rmse"]))
+    # a linear-Gaussian model: both filters estimate the same posterior mean
+    assert np.mean(np.abs(g["means"] - p["means"])) < 0.15
+    m, (lo, hi) = mc.bootstrap_ci(p["rmse"])
+    assert lo <= m <= hi
+
+
 def test_gsf_errors_are_loud():
     from bayesianfiltering_b200.engine import GaussianSumFilterEngine
     c = case("ungm")
