@@ -250,6 +250,24 @@ __device__ __forceinline__ void chunk_scan(const float v[4], int wpos, const flo
   tau[3] = clampf(nxt, c3, hi);
 }
 
+// The particle state is read once and written once per step and is far larger than L2: stream it (evict-first), so
+// that the per-particle scalars that ARE re-read within a step (log-likelihoods, weights, tau: 4 B each) stay in L2.
+template <int DX>
+__device__ __forceinline__ void store_state_cs(float* base, size_t i, const float* x) {
+  if constexpr (DX % 4 == 0) {
+    float4* p = reinterpret_cast<float4*>(base) + i * (DX / 4);
+#pragma unroll
+    for (int k = 0; k < DX / 4; ++k) __stcs(p + k, make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]));
+  } else if constexpr (DX % 2 == 0) {
+    float2* p = reinterpret_cast<float2*>(base) + i * (DX / 2);
+#pragma unroll
+    for (int k = 0; k < DX / 2; ++k) __stcs(p + k, make_float2(x[2 * k], x[2 * k + 1]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < DX; ++k) __stcs(base + i * DX + k, x[k]);
+  }
+}
+
 template <int DX>
 __device__ __forceinline__ void load_state_cg(const float* base, size_t i, float* x) {
   if constexpr (DX % 4 == 0) {
@@ -515,7 +533,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
             }
           }
           M::f(x, qn, u_in, mc, xt);
-          store_state<DX>(x_cur, (size_t)i, xt);
+          store_state_cs<DX>(x_cur, (size_t)i, xt);
           if (a.out_propagated) store_state<DX>(a.out_propagated + (size_t)t * N * DX, (size_t)i, xt);
 #ifdef BF_EXP_NOLL
           const float ll = -0.5f * xt[0] * xt[0];
