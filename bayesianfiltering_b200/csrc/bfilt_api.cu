@@ -214,6 +214,11 @@ struct bf_pf_s {
   // streamed scratch
   DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats, phase_ns, V;
   int ntiles;
+  // Independent trials of the streamed path run CONCURRENTLY (one cooperative kernel each, on its own stream, with its
+  // own scratch): at the reference's sizes (Nsim = 100 trials of N = 10^4) one trial fills a few SMs only.
+  struct Slot { DevBuf xa, xb, LL, E, tilesum, Etile, V, partials; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; };
+  Slot extra[31];                     // slots 1..31 (slot 0 = the members above), allocated on first use
+  cudaEvent_t ev_fork = nullptr;
   // sharded filter
   int world = 1, rank = 0;
   ncclComm_t comm = nullptr;
@@ -301,6 +306,13 @@ extern "C" int bf_pf_destroy(bf_pf_handle h) {
   if (!h) return BF_OK;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();              // as cudaFree would: nothing enqueued by this handle may still be running
+  for (auto& sl : h->extra) {
+    DevBuf* bufs[] = {&sl.xa, &sl.xb, &sl.LL, &sl.E, &sl.tilesum, &sl.Etile, &sl.V, &sl.partials};
+    for (DevBuf* bf : bufs) bf->release();
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
@@ -474,7 +486,35 @@ struct PfRun {
       if (!h->peers_ready || !h->comm) return fail(BF_EINVAL, "sharded filter: bf_pf_shard_import and bf_pf_shard_comm_init must be called first");
       if (io->resume || io->t_offset != 0) return fail(BF_EINVAL, "sharded filter: resume / t_offset are not supported");
     }
+    // concurrent trials: K slots, bounded by the co-resident CTA budget and by 4 GB of scratch
+    const size_t slot_bytes = (size_t)2 * N * DX * 4 + (size_t)2 * ntiles * PF_FUSED_TILE_CHUNKS * 128 * 4 + (size_t)3 * (ntiles_g + 8) * 4;
+    int K = 1;
+    if (world == 1 && B > 1) {
+      int per_sm = 0;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
+      K = std::min<int64_t>(std::min(B, 32), std::max<int64_t>(1, (int64_t)per_sm * h->nsm / grid));
+      K = (int)std::min<int64_t>(K, std::max<int64_t>(1, ((int64_t)4 << 30) / (int64_t)slot_bytes));
+    }
+    cudaStream_t caller = s;
+    if (K > 1) {
+      if (!h->ev_fork) CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CUDA_OK(cudaEventRecord(h->ev_fork, caller));
+      for (int k = 1; k < K; ++k) {
+        bf_pf_s::Slot& sl = h->extra[k - 1];
+        if (!sl.stream) { CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
+        const size_t npad = (size_t)ntiles * PF_FUSED_TILE_CHUNKS * 128;
+        if (sl.xa.ensure((size_t)N * DX * 4) || sl.xb.ensure((size_t)N * DX * 4) || sl.LL.ensure(npad * 4) || sl.E.ensure(npad * 4) ||
+            sl.tilesum.ensure(((size_t)ntiles_g + 4) * 4) || sl.Etile.ensure(((size_t)ntiles_g + 4) * 4) || sl.V.ensure(((size_t)ntiles_g + 4) * 4) ||
+            sl.partials.ensure((size_t)2 * grid * sizeof(PfPartial)))
+          return fail(BF_ENOMEM, "cudaMalloc of the scratch of concurrent trial %d failed", k);
+        CUDA_OK(cudaMemsetAsync(sl.LL.p, 0, npad * 4, sl.stream));
+        CUDA_OK(cudaStreamWaitEvent(sl.stream, h->ev_fork, 0));
+      }
+    }
     for (int b = 0; b < B; ++b) {
+      const int slot = b % K;
+      bf_pf_s::Slot* sl = slot ? &h->extra[slot - 1] : nullptr;
+      s = slot ? sl->stream : caller;
       float* cx = h->carry_x.as<float>() + (size_t)b * N * DX;
       float* cw = h->carry_w.as<float>() + (size_t)b * N;
       PfFusedArgs a;
@@ -494,12 +534,12 @@ struct PfRun {
       }
       if (!io->resume && io->init_weights)
         CUDA_OK(cudaMemcpyAsync(cw, io->init_weights + (size_t)b * N, (size_t)N * 4, cudaMemcpyDeviceToDevice, s));
-      a.xbuf0 = h->xa.as<float>(); a.xbuf1 = h->xb.as<float>();
-      a.W = cw; a.LL = h->LL.as<float>(); a.E = h->E.as<float>();
-      a.tilesum = h->tilesum.as<float>(); a.Etile = h->Etile.as<float>();
-      a.V = h->V.as<float>(); a.total = h->V.as<float>() + ntiles_g + 1;
+      a.xbuf0 = (sl ? sl->xa : h->xa).as<float>(); a.xbuf1 = (sl ? sl->xb : h->xb).as<float>();
+      a.W = cw; a.LL = (sl ? sl->LL : h->LL).as<float>(); a.E = (sl ? sl->E : h->E).as<float>();
+      a.tilesum = (sl ? sl->tilesum : h->tilesum).as<float>(); a.Etile = (sl ? sl->Etile : h->Etile).as<float>();
+      a.V = (sl ? sl->V : h->V).as<float>(); a.total = a.V + ntiles_g + 1;
       a.use_tau = (log2ng >= 3 && log2n >= 0) ? 1 : 0;
-      a.partials = h->partials.as<PfPartial>();
+      a.partials = (sl ? sl->partials : h->partials).as<PfPartial>();
       a.carry_stats = h->carry_stats.as<StepStats>() + 2 * b;
       a.noise = io->noise ? io->noise + (size_t)b * N * DQ : nullptr;
       a.res_u = io->resample_u ? (h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC ? io->resample_u + b : io->resample_u + (size_t)b * N)
@@ -517,7 +557,7 @@ struct PfRun {
       a.carry_x = cx;
       a.final_particles = io->final_particles ? io->final_particles + (size_t)b * N * DX : nullptr;
       a.final_weights = io->final_weights ? io->final_weights + (size_t)b * N : nullptr;
-      a.phase_ns = h->phase_ns.as<unsigned long long>();
+      a.phase_ns = (K > 1) ? nullptr : h->phase_ns.as<unsigned long long>();
       a.world = world; a.rank = rank; a.goff = rank * N; a.Ng = Ng; a.log2ng = log2ng; a.log2ns = log2n;
       a.tile_off = rank * (world > 1 ? ntiles : 0); a.ntiles_g = ntiles_g; a.phases = PF_PH_ALL;
       if (world == 1) {
@@ -613,6 +653,13 @@ struct PfRun {
         if (rc) return rc;
         h->launches += nlaunch;
       }
+    }
+    if (K > 1) {                        // join: the caller's stream continues when every slot has drained
+      for (int k = 1; k < K; ++k) {
+        CUDA_OK(cudaEventRecord(h->extra[k - 1].done, h->extra[k - 1].stream));
+        CUDA_OK(cudaStreamWaitEvent(caller, h->extra[k - 1].done, 0));
+      }
+      s = caller;
     }
     return BF_OK;
   }
