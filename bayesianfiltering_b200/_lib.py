@@ -12,7 +12,7 @@ MODEL_UNGM, MODEL_BOT, MODEL_L63, MODEL_L96, MODEL_LG, MODEL_SIN1D = 1, 2, 3, 4,
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 PATH_AUTO, PATH_RESIDENT, PATH_STREAMED = 0, 1, 2
 GSF_PREDICT_FIRST, GSF_NO_JITTER, GSF_COV_PLUS_P = 1, 2, 4
-SHARD_BLOB_BYTES, NCCL_ID_BYTES = 256, 128
+SHARD_BLOB_BYTES, NCCL_ID_BYTES = 512, 128
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)

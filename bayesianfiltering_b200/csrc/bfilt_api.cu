@@ -198,7 +198,7 @@ static ncclComm_t find_comm(int device, int world, int rank) {
 }
 
 // ========================================================================================== particle filter
-struct ShardBlob { cudaIpcMemHandle_t tau, xa, xb; int rank, grid, pad[14]; };
+struct ShardBlob { cudaIpcMemHandle_t tau, xa, xb, xchg; int rank, grid, pad[14]; };
 static_assert(sizeof(ShardBlob) <= BF_SHARD_BLOB_BYTES, "blob too large");
 
 struct bf_pf_s {
@@ -223,8 +223,10 @@ struct bf_pf_s {
   int world = 1, rank = 0;
   ncclComm_t comm = nullptr;
   bool peers_ready = false;
-  void* peer_ptr[3][8] = {};          // imported tau / xa / xb of every rank (own entries = own buffers)
-  DevBuf peer_tab, barrier_buf;       // device tables [3][8] of the pointers above; 1 float for the step barrier
+  void* peer_ptr[4][8] = {};          // imported tau / xa / xb / exchange buffer of every rank (own entries = own buffers)
+  DevBuf peer_tab, barrier_buf;       // device tables [4][8] of the pointers above; 1 float for the step barrier
+  DevBuf xchg;                        // exchange buffer: flags [3][8] u64 | epoch | err | partials | tilesum | V  (pf_fused.cuh)
+  size_t off_part = 0, off_ts = 0, off_V = 0;
   // the T x (4 launches + 4 collectives) of a sharded run, captured once per distinct call and replayed
   cudaStream_t gstream = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t gexec = nullptr; size_t gkey = 0; int64_t glaunches = 0;
@@ -288,13 +290,22 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
     if (!ea) ea = sh ? h->xb.ensure_plain(xb_) : h->xb.ensure(xb_);
     if (!ea) ea = sh ? h->E.ensure_plain(npad * 4) : h->E.ensure(npad * 4);
     if (ea || h->LL.ensure(npad * 4) || h->tilesum.ensure((ntg + 4) * 4) || h->Etile.ensure((ntg + 4) * 4) || h->V.ensure((ntg + 4) * 4) ||
-        (sh && (h->peer_tab.ensure(3 * 8 * sizeof(void*)) || h->barrier_buf.ensure(64)))) {
+        (sh && (h->peer_tab.ensure(4 * 8 * sizeof(void*)) || h->barrier_buf.ensure(64)))) {
       bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the streamed scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     cudaMemset(h->LL.p, 0, npad * 4);
     cudaMemset(h->tilesum.p, 0, (ntg + 4) * 4);
     cudaMemset(h->V.p, 0, (ntg + 4) * 4);
-    if (sh) cudaMemset(h->barrier_buf.p, 0, 64);
+    if (sh) {
+      cudaMemset(h->barrier_buf.p, 0, 64);
+      const size_t gmax = (size_t)h->nsm * 4;                       // upper bound of the cooperative grid
+      h->off_part = 512;
+      h->off_ts = h->off_part + (((size_t)2 * 8 * gmax * sizeof(PfPartial) + 255) & ~(size_t)255);
+      h->off_V = h->off_ts + (((ntg + 4) * 4 + 255) & ~(size_t)255);
+      const size_t xbytes = h->off_V + (((ntg + 4) * 4 + 255) & ~(size_t)255);
+      if (h->xchg.ensure_plain(xbytes)) { bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the exchange buffer failed"); }
+      cudaMemset(h->xchg.p, 0, xbytes);
+    }
     if (h->phase_ns.ensure(8 * sizeof(unsigned long long))) { bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc failed"); }
     cudaMemset(h->phase_ns.p, 0, 8 * sizeof(unsigned long long));
   }
@@ -318,11 +329,11 @@ extern "C" int bf_pf_destroy(bf_pf_handle h) {
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   if (h->gstream) cudaStreamDestroy(h->gstream);
   if (h->peers_ready)
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 4; ++k)
       for (int r = 0; r < h->world; ++r)
         if (r != h->rank && h->peer_ptr[k][r]) cudaIpcCloseMemHandle(h->peer_ptr[k][r]);
   DevBuf* all[] = {&h->carry_x, &h->carry_w, &h->carry_uniform, &h->carry_stats, &h->xa, &h->xb, &h->LL, &h->E, &h->anc,
-                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V, &h->peer_tab, &h->barrier_buf};
+                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V, &h->peer_tab, &h->barrier_buf, &h->xchg};
   for (DevBuf* b : all) b->release();
   for (DevBuf& b : h->hbuf) b.release();
   delete h;
@@ -337,6 +348,7 @@ extern "C" int bf_pf_shard_export(bf_pf_handle h, void* blob) {
   CUDA_OK(cudaIpcGetMemHandle(&b.tau, h->E.p));
   CUDA_OK(cudaIpcGetMemHandle(&b.xa, h->xa.p));
   CUDA_OK(cudaIpcGetMemHandle(&b.xb, h->xb.p));
+  CUDA_OK(cudaIpcGetMemHandle(&b.xchg, h->xchg.p));
   b.rank = h->rank;
   memset(blob, 0, BF_SHARD_BLOB_BYTES);
   memcpy(blob, &b, sizeof b);
@@ -353,11 +365,12 @@ extern "C" int bf_pf_shard_import(bf_pf_handle h, const void* blobs) {
     memcpy(&b, (const char*)blobs + (size_t)r * BF_SHARD_BLOB_BYTES, sizeof b);
     if (b.rank != r) return fail(BF_EINVAL, "blob %d comes from rank %d: pass the blobs in rank order", r, b.rank);
     if (r == h->rank) {
-      h->peer_ptr[0][r] = h->E.p; h->peer_ptr[1][r] = h->xa.p; h->peer_ptr[2][r] = h->xb.p;
+      h->peer_ptr[0][r] = h->E.p; h->peer_ptr[1][r] = h->xa.p; h->peer_ptr[2][r] = h->xb.p; h->peer_ptr[3][r] = h->xchg.p;
     } else {
       CUDA_OK(cudaIpcOpenMemHandle(&h->peer_ptr[0][r], b.tau, cudaIpcMemLazyEnablePeerAccess));
       CUDA_OK(cudaIpcOpenMemHandle(&h->peer_ptr[1][r], b.xa, cudaIpcMemLazyEnablePeerAccess));
       CUDA_OK(cudaIpcOpenMemHandle(&h->peer_ptr[2][r], b.xb, cudaIpcMemLazyEnablePeerAccess));
+      CUDA_OK(cudaIpcOpenMemHandle(&h->peer_ptr[3][r], b.xchg, cudaIpcMemLazyEnablePeerAccess));
     }
   }
   CUDA_OK(cudaMemcpy(h->peer_tab.p, h->peer_ptr, sizeof h->peer_ptr, cudaMemcpyHostToDevice));
@@ -456,7 +469,8 @@ struct PfRun {
     // shared memory depends on tiles_per_cta, which depends on the grid, which depends on shared memory: iterate
     int grid = 1, tpc = ntiles;
     size_t smem = 0;
-    auto smem_for = [&](int t) { return (size_t)((3 * TW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, nchunk + 1 + NW + 8) + 8) * sizeof(float); };
+    auto smem_for = [&](int t) { return (size_t)((3 * TW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, nchunk + 1 + NW + 8) +
+                                                (h->world > 1 ? NW * PF_FUSED_XCAP * DX : 0) + 8) * sizeof(float); };
     for (int round = 0; round < 3; ++round) {
       smem = smem_for(round == 0 ? 64 : tpc);
       if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -540,6 +554,18 @@ struct PfRun {
       a.V = (sl ? sl->V : h->V).as<float>(); a.total = a.V + ntiles_g + 1;
       a.use_tau = (log2ng >= 3 && log2n >= 0) ? 1 : 0;
       a.partials = (sl ? sl->partials : h->partials).as<PfPartial>();
+      if (world > 1) {                   // the exchanged arrays live in the IPC-mapped exchange buffer
+        char* xb = h->xchg.as<char>();
+        if ((size_t)2 * world * grid * sizeof(PfPartial) > h->off_ts - h->off_part) return fail(BF_EINVAL, "cooperative grid of %d CTAs exceeds the exchange buffer", grid);
+        a.partials = reinterpret_cast<PfPartial*>(xb + h->off_part);
+        a.tilesum = reinterpret_cast<float*>(xb + h->off_ts);
+        a.V = reinterpret_cast<float*>(xb + h->off_V); a.total = h->V.as<float>();
+        a.off_part = (int)h->off_part; a.off_ts = (int)h->off_ts; a.off_V = (int)h->off_V;
+        a.xchg_peers = reinterpret_cast<char* const*>(h->peer_tab.as<char*>() + 24);
+        a.flags = reinterpret_cast<unsigned long long*>(xb);
+        a.epoch = reinterpret_cast<unsigned long long*>(xb + 256);
+        a.err = reinterpret_cast<int*>(xb + 264);
+      }
       a.carry_stats = h->carry_stats.as<StepStats>() + 2 * b;
       a.noise = io->noise ? io->noise + (size_t)b * N * DQ : nullptr;
       a.res_u = io->resample_u ? (h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC ? io->resample_u + b : io->resample_u + (size_t)b * N)
@@ -566,10 +592,21 @@ struct PfRun {
         h->launches++;
         continue;
       }
-      // ---- sharded filter: one launch per phase, the exchanges between them (see include/bfilt.h)
+      // ---- sharded filter (see include/bfilt.h)
       NcclApi* nc = nccl_api();
       const float* const* tab = h->peer_tab.as<const float*>();
       a.tau_peers = tab; a.xa_peers = tab + 8; a.xb_peers = tab + 16;
+      const char* smode = getenv("BF_SHARD_MODE");
+      if (!(smode && strcmp(smode, "nccl") == 0)) {
+        // one persistent kernel for the whole run; the ranks meet through peer-memory stores and flags inside it
+        a.p2p = 1;
+        void* params[] = {(void*)&h->mc, (void*)&a};
+        CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, s));
+        h->launches++;
+        // the next run reuses the buffers the peers' final gather may still be reading
+        NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, s));
+        continue;
+      }
       const size_t pf_floats = (size_t)grid * sizeof(PfPartial) / 4;
       int64_t nlaunch = 0;
       auto launch = [&](cudaStream_t st, int phases, int t, int Tl) -> int {
@@ -736,6 +773,12 @@ extern "C" int bf_pf_run_host(bf_pf_handle h, const bf_pf_io* hio) {
   rc = bf_pf_run(h, &d, s);
   if (rc) return rc;
 #define BACK(field, count) if (hio->field) CUDA_OK(cudaMemcpyAsync(hio->field, d.field, (size_t)(count) * 4, cudaMemcpyDeviceToHost, s));
+  if (h->world > 1) {                   // a peer that never raised its flag: the kernel gave up instead of hanging
+    int err = 0;
+    CUDA_OK(cudaMemcpyAsync(&err, h->xchg.as<char>() + 264, sizeof err, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (err) { cudaMemsetAsync(h->xchg.as<char>() + 264, 0, sizeof err, s); return fail(BF_ECOMM, "sharded filter: a peer rank did not reach the exchange within 4 s"); }
+  }
   BACK(out_particles, B * T * N * dx) BACK(out_weights, B * T * N) BACK(out_propagated, B * T * N * dx)
   BACK(out_norm_weights, B * T * N) BACK(out_ancestors, B * T * N) BACK(out_mean, B * T * dx) BACK(out_loglik, B * T)
   BACK(out_ess, B * T) BACK(out_resampled, B * T) BACK(final_particles, B * N * dx) BACK(final_weights, B * N)

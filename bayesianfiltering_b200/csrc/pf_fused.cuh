@@ -42,6 +42,7 @@ namespace cg = cooperative_groups;
 #define PF_FUSED_WARPS 16                   // warps per CTA
 #define PF_FUSED_CTAS_PER_SM 2              // 2 x 512 threads per SM (64 registers per thread)
 #define PF_FUSED_WINCAP 512                 // floats of tau a warp stages in shared memory for one chunk of 128 slots
+#define PF_FUSED_XCAP 256                   // particles a warp of a SHARDED filter stages when a chunk's ancestors live on a peer
 
 struct PfFusedArgs {
   int N, T, t_offset, trial, B;
@@ -78,6 +79,14 @@ struct PfFusedArgs {
   // device tables [world] (in global memory: indexing a kernel parameter dynamically would spill it to local memory)
   const float* const* tau_peers;             // E of every rank (own entry = a.E)
   const float* const* xa_peers; const float* const* xb_peers;   // xbuf0 / xbuf1 of every rank
+  // Exchange without NCCL (p2p = 1, phases = ALL): each rank owns an IPC-mapped exchange buffer holding
+  // [flags 3 x 8 u64 | epoch | err | partials | tilesum | V]; a rank STORES its contribution straight into every peer's
+  // buffer over NVLink and raises a sequence-numbered flag there; the readers spin on their own (local) flags.
+  int p2p, off_part, off_ts, off_V;          // byte offsets of partials / tilesum / V inside an exchange buffer
+  char* const* xchg_peers;                   // device table [world] of the exchange buffers (own entry = own buffer)
+  unsigned long long* flags;                 // own flags [3][8]
+  unsigned long long* epoch;                 // runs completed on this handle (device side: CUDA-graph replays need no new arguments)
+  int* err;                                  // set when a peer did not show up within the spin budget
 };
 
 enum { PF_PH_A = 1, PF_PH_B = 2, PF_PH_C = 4, PF_PH_FINAL = 8, PF_PH_ALL = 15 };
@@ -301,6 +310,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   float* s_meta_f = s_v0 + TW * tpc;
   int* s_lo = reinterpret_cast<int*>(s_meta_f + 2 * tpc);       // [TW*tpc + 2] tau window start of each chunk
   float* s_win = reinterpret_cast<float*>(s_lo + TW * tpc + 2);
+  float* s_xst = s_win + CW * WINCAP;                           // [CW][XCAP*DX], sharded filters only (host sizes it)
   __shared__ PfPartial s_part[CW];
   __shared__ StepStats s_stats;
   __shared__ int s_ctr[4];                            // chunk queues of phases A / B / C2
@@ -346,6 +356,27 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   const bool use_win = use_tau && a.resampler == 1;      // sorted positions: windowed search
   // (i + u) / 2^k is an exact scaling: multiplying by 2^-k gives the same bits as the oracle's division
   const float invn_pow2 = (a.log2ng >= 0) ? __int_as_float((127 - a.log2ng) << 23) : 0.0f;
+  // ---- cross-GPU barrier of the persistent sharded kernel.  Every thread that stored into a peer's buffer has run
+  // __threadfence_system() and the grid has synchronised before CTA 0 raises the flags; readers spin on local memory.
+  const bool p2p = a.p2p != 0 && a.world > 1;
+  const unsigned long long seq0 = p2p ? (*a.epoch) * (3ull << 22) : 0ull;
+  auto xbarrier = [&](int ph, int step) {
+    const unsigned long long seq = seq0 + 3ull * (unsigned long long)step + (unsigned long long)ph + 1ull;
+    if (blockIdx.x == 0 && tid < a.world && tid != a.rank) {
+      __threadfence_system();
+      volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(a.xchg_peers[tid]) + ph * 8 + a.rank;
+      *f = seq;
+    }
+    if (tid < a.world && tid != a.rank) {
+      volatile unsigned long long* f = a.flags + ph * 8 + tid;
+      const unsigned long long t0 = globaltimer_ns();
+      while (*f < seq) {
+        if (globaltimer_ns() - t0 > 4000000000ull) { *a.err = 1; break; }     // 4 s: a peer died; do not hang the GPU
+      }
+      __threadfence_system();          // acquire; a fence of scope >= cluster also drops this SM's stale L1 lines
+    }
+    __syncthreads();
+  };
 
   // the carry entering the call: materialised particles (gather = false) for a whole run; for a single phase of a
   // sharded step the host keeps carry_stats current between the launches
@@ -353,6 +384,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   bool gather = all_phases ? false : (a.carry_stats->flag != 0);
   const float* x_prev = a.x_init;
   float res_total = 0.0f, res_u0 = 0.0f;              // of the resampling being gathered
+  const float* const* xp_stage = nullptr;             // peers' copies of the state being gathered (sharded filter)
 
   auto position = [&](int slot, float u) -> float {
     if (a.log2ng >= 0)
@@ -399,7 +431,8 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   };
 
   // Ancestors (GLOBAL particle indices) of the 4 slots base..base+3 (local) of chunk q.  Warp-synchronous.
-  auto ancestors4 = [&](int ts, int q, int base, int nv, int anc[4]) {
+  auto ancestors4 = [&](int ts, int q, int base, int nv, int anc[4], int& xs_lo) {
+    xs_lo = -1;                                        // >= 0: the chunk's ancestors x[xs_lo ...] are staged in shared memory
     float u[4] = {res_u0, res_u0, res_u0, res_u0};
     if (a.resampler != 1 && nv > 0) {
       if (a.res_u) {
@@ -434,6 +467,28 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         for (int k = 1; k < 4; ++k) {
           p = lower_bound_window(win, p, pn, r[k]);
           anc[k] = min(lo + p, Ng - 1);
+        }
+        // Sharded filter, ancestors (partly) on another rank: x[lo .. lo+wn] is a contiguous range -- fetch it with
+        // coalesced 512-byte peer reads into shared memory instead of one 16-byte NVLink round trip per particle.
+        if (a.world > 1 && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
+          float* xs = s_xst + (size_t)warp * PF_FUSED_XCAP * DX;
+          for (int i0 = 0; i0 <= wn; i0 += 128) {       // four peer loads in flight per lane (an NVLink round trip is ~3 us)
+            float xv[4][DX];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int g = min(lo + min(i0 + lane + 32 * m, wn), Ng - 1);
+              load_state_cg<DX>(xp_stage[g >> a.log2ns], (size_t)(g & ns_mask), xv[m]);
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int i = i0 + lane + 32 * m;
+              if (i <= wn) {
+#pragma unroll
+                for (int c = 0; c < DX; ++c) xs[(size_t)i * DX + c] = xv[m][c];
+              }
+            }
+          }
+          xs_lo = lo;
         }
         __syncwarp();                                  // the window is overwritten by this warp's next chunk
       } else if (nv > 0) {                             // window larger than the cap (very uneven weights): rare
@@ -492,8 +547,10 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       const int base = cta_base + 128 * q + lane * 4;
       const int nv = max(0, min(4, N - base));
       int anc[4] = {a.goff + base, a.goff + base + 1, a.goff + base + 2, a.goff + base + 3};     // global indices
+      int xs_lo = -1;
+      xp_stage = xp_peers;
 #ifndef BF_EXP_NOSEARCH
-      if (gather) ancestors4(t - 1, q, base, nv, anc);
+      if (gather) ancestors4(t - 1, q, base, nv, anc, xs_lo);
 #endif
       if (nv <= 0) continue;
       if (pt > 0 && a.out_ancestors) {
@@ -512,7 +569,11 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         if (k < nv) {
           const int i = base + k;
           float x[DX], qn[DQ], xt[DX];
-          if (gather) load_prev(anc[k], x_prev, xp_peers, x);
+          if (xs_lo >= 0) {
+            const float* xs = s_xst + ((size_t)warp * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
+#pragma unroll
+            for (int c = 0; c < DX; ++c) x[c] = xs[c];
+          } else if (gather) load_prev(anc[k], x_prev, xp_peers, x);
           else load_state_cg<DX>(x_prev, (size_t)i, x);
           if (pt > 0 && a.out_particles) store_state<DX>(a.out_particles + ((ptrdiff_t)t - 1) * N * DX, (size_t)i, x);
           if (a.noise) {
@@ -562,14 +623,26 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       if (lane < CW) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
       acc.warp_reduce();
       if (lane == 0) {
-        PfPartial* p = &a.partials[((size_t)(pt & 1) * a.world + a.rank) * G + blockIdx.x];
+        const size_t pidx = ((size_t)(pt & 1) * a.world + a.rank) * G + blockIdx.x;
+        PfPartial* p = &a.partials[pidx];
         p->m = acc.m; p->s = acc.s; p->s2 = acc.s2;
 #pragma unroll
         for (int k = 0; k < DX; ++k) p->sx[k] = acc.sx[k];
+        if (p2p) {                                   // the same record into every peer's exchange buffer
+          for (int r = 0; r < a.world; ++r) {
+            if (r == a.rank) continue;
+            PfPartial* rp = reinterpret_cast<PfPartial*>(a.xchg_peers[r] + a.off_part) + pidx;
+            rp->m = acc.m; rp->s = acc.s; rp->s2 = acc.s2;
+#pragma unroll
+            for (int k = 0; k < DX; ++k) rp->sx[k] = acc.sx[k];
+          }
+          __threadfence_system();
+        }
       }
     }
     }  // phase A
     if (all_phases) grid.sync();
+    if (p2p) xbarrier(0, t);
     lap(0);
     if (!(a.phases & (PF_PH_B | PF_PH_C))) break;
 
@@ -689,11 +762,21 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       for (int w = TW / 2; w >= 1; w >>= 1)
 #pragma unroll
         for (int k = 0; k < w; ++k) y16[k] = __fadd_rn(y16[2 * k], y16[2 * k + 1]);
-      a.tilesum[a.tile_off + tile0 + i] = y16[0];
-      a.V[a.tile_off + tile0 + i] = s_v0[i * TW];
+      const int gi = a.tile_off + tile0 + i;
+      a.tilesum[gi] = y16[0];
+      a.V[gi] = s_v0[i * TW];
+      if (p2p) {
+        for (int r = 0; r < a.world; ++r) {
+          if (r == a.rank) continue;
+          reinterpret_cast<float*>(a.xchg_peers[r] + a.off_ts)[gi] = y16[0];
+          reinterpret_cast<float*>(a.xchg_peers[r] + a.off_V)[gi] = s_v0[i * TW];
+        }
+        __threadfence_system();
+      }
     }
     }  // phase B tile sums
     if (all_phases) grid.sync();
+    if (p2p) xbarrier(1, t);
     lap(1);
     if (!(a.phases & PF_PH_C)) break;
 
@@ -746,7 +829,9 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
     }
     if (a.world > 1 && blockIdx.x == 0 && tid == 0) *a.total = __ldcg(&a.Etile[a.ntiles_g - 1]);   // E[Ng]
-    if (all_phases) grid.sync();
+    if (all_phases) grid.sync();                       // (gpu-scope fence: tau and the particles of this step are in this GPU's L2,
+                                                       //  which is where the peers' NVLink reads are served from)
+    if (p2p) xbarrier(2, t);
     lap(3);
     w_uni = true; gather = true;
   }
@@ -760,13 +845,19 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     const int base = cta_base + 128 * q + lane * 4;
     const int nv = max(0, min(4, N - base));
     int anc[4] = {a.goff + base, a.goff + base + 1, a.goff + base + 2, a.goff + base + 3};
-    if (gather) ancestors4(T - 1, q, base, nv, anc);
+    int xs_lo = -1;
+    xp_stage = xpf_peers;
+    if (gather) ancestors4(T - 1, q, base, nv, anc, xs_lo);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < nv) {
         const int i = base + k;
         float x[DX];
-        if (gather) load_prev(anc[k], x_prev, xpf_peers, x);
+        if (xs_lo >= 0) {
+          const float* xs = s_xst + ((size_t)warp * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
+#pragma unroll
+          for (int c = 0; c < DX; ++c) x[c] = xs[c];
+        } else if (gather) load_prev(anc[k], x_prev, xpf_peers, x);
         else load_state_cg<DX>(x_prev, (size_t)i, x);
         store_state<DX>(a.carry_x, (size_t)i, x);
         if (a.final_particles) store_state<DX>(a.final_particles, (size_t)i, x);
@@ -780,6 +871,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   }
   lap(4);
   if (blockIdx.x == 0 && tid == 0) {
+    if (p2p) *a.epoch = *a.epoch + 1ull;
     StepStats st = all_phases ? s_stats : a.carry_stats[a.t_offset & 1];
     st.flag = 0; st.w_uniform = w_uni ? 1 : 0;
     a.carry_stats[0] = st;

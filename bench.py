@@ -227,6 +227,8 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     launches = eng.launches() - l0
     phases = {k: v * 1e3 / (args.steps * T) for k, v in eng.phase_times().items()}     # us per time step
+    if os.environ.get("BF_BENCH_ALLRANKS"):
+        print(f"rank {rank}: phases us/step {({k: round(v, 1) for k, v in phases.items()})}", file=sys.stderr, flush=True)
     ll = bufs["log_likelihood"].double().sum().item()
     if sharded and rank != 0:
         ll = 0.0                                   # per-step scalars of a sharded filter are written by rank 0

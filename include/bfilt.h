@@ -117,15 +117,18 @@ int bf_pf_destroy(bf_pf_handle h);
 /* ---- one particle filter sharded over `shard_world` GPUs (power of two <= 8, one process per GPU).
  * The reference has no multi-device code; this is `bootstrap_particle_filter` (inference.py:1302-1380) for an N that
  * one GPU should not hold alone.  num_particles (per rank) must be a power of two >= 2048, one trial, streamed path.
- * Per time step the ranks exchange, with NCCL over NVLink, (1) their CTA partials of (max, sum, sum^2, sum x) -- every
- * rank folds all of them in the same order, so the ESS test takes the same branch everywhere -- (2) the tile sums and
- * first weights of their tiles, from which every rank derives the same canonical scan offsets, and (3) a barrier
- * before the next step reads the peers' cdf (tau) and particle state through CUDA-IPC mapped pointers: ancestors
- * that live on another rank are gathered directly from its memory.
+ * Per time step the ranks exchange (1) their CTA partials of (max, sum, sum^2, sum x) -- every rank folds all of them
+ * in the same order, so the ESS test takes the same branch everywhere -- (2) the tile sums and first weights of their
+ * tiles, from which every rank derives the same canonical scan offsets, and (3) a barrier before the next step reads
+ * the peers' cdf (tau) and particle state through CUDA-IPC mapped pointers: ancestors that live on another rank are
+ * gathered directly from its memory over NVLink.  Default transport (BF_SHARD_MODE=p2p): ONE persistent kernel per
+ * run; a rank stores its contribution straight into every peer's exchange buffer and raises a sequence-numbered flag
+ * there, readers spin on their own flags (bounded: a missing peer makes the run fail with BF_ECOMM instead of
+ * hanging).  BF_SHARD_MODE=nccl: one launch per phase with ncclAllGather / ncclAllReduce between them.
  * Protocol: create on every rank -> bf_pf_shard_export -> exchange the blobs between the processes (any transport)
  * -> bf_pf_shard_import; rank 0 bf_nccl_unique_id -> broadcast -> bf_pf_shard_comm_init on every rank; then bf_pf_run /
  * bf_pf_run_host as usual with the LOCAL shard of every per-particle array (resume / t_offset are not supported). */
-#define BF_SHARD_BLOB_BYTES 256
+#define BF_SHARD_BLOB_BYTES 512
 #define BF_NCCL_ID_BYTES 128
 int bf_pf_shard_export(bf_pf_handle h, void* blob /* BF_SHARD_BLOB_BYTES */);
 int bf_pf_shard_import(bf_pf_handle h, const void* blobs /* shard_world * BF_SHARD_BLOB_BYTES, rank order */);
