@@ -466,11 +466,13 @@ struct PfRun {
     const int ntiles = h->ntiles;
     const int ntiles_scan = h->world > 1 ? h->world * ntiles + 1 : ntiles;       // the scan covers the whole filter's tiles
     const int nchunk = (ntiles_scan + 1 + NW * 128 - 1) / (NW * 128); // chunks of the one-CTA scan of the tile sums
+    const char* xenv = getenv("BF_SHARD_STAGE");
+    const bool xstage = h->world > 1 && !(xenv && xenv[0] == '0');
     // shared memory depends on tiles_per_cta, which depends on the grid, which depends on shared memory: iterate
     int grid = 1, tpc = ntiles;
     size_t smem = 0;
     auto smem_for = [&](int t) { return (size_t)((3 * TW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, nchunk + 1 + NW + 8) +
-                                                (h->world > 1 ? NW * PF_FUSED_XCAP * DX : 0) + 8) * sizeof(float); };
+                                                (xstage ? NW * PF_FUSED_XCAP * DX : 0) + 8) * sizeof(float); };
     for (int round = 0; round < 3; ++round) {
       smem = smem_for(round == 0 ? 64 : tpc);
       if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -565,6 +567,7 @@ struct PfRun {
         a.flags = reinterpret_cast<unsigned long long*>(xb);
         a.epoch = reinterpret_cast<unsigned long long*>(xb + 256);
         a.err = reinterpret_cast<int*>(xb + 264);
+        a.xstage = xstage ? 1 : 0;
       }
       a.carry_stats = h->carry_stats.as<StepStats>() + 2 * b;
       a.noise = io->noise ? io->noise + (size_t)b * N * DQ : nullptr;

@@ -83,6 +83,7 @@ struct PfFusedArgs {
   // [flags 3 x 8 u64 | epoch | err | partials | tilesum | V]; a rank STORES its contribution straight into every peer's
   // buffer over NVLink and raises a sequence-numbered flag there; the readers spin on their own (local) flags.
   int p2p, off_part, off_ts, off_V;          // byte offsets of partials / tilesum / V inside an exchange buffer
+  int xstage;                                // stage remote ancestor ranges in shared memory (needs the extra dynamic shared memory)
   char* const* xchg_peers;                   // device table [world] of the exchange buffers (own entry = own buffer)
   unsigned long long* flags;                 // own flags [3][8]
   unsigned long long* epoch;                 // runs completed on this handle (device side: CUDA-graph replays need no new arguments)
@@ -470,7 +471,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         }
         // Sharded filter, ancestors (partly) on another rank: x[lo .. lo+wn] is a contiguous range -- fetch it with
         // coalesced 512-byte peer reads into shared memory instead of one 16-byte NVLink round trip per particle.
-        if (a.world > 1 && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
+        if (a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
           float* xs = s_xst + (size_t)warp * PF_FUSED_XCAP * DX;
           for (int i0 = 0; i0 <= wn; i0 += 128) {       // four peer loads in flight per lane (an NVLink round trip is ~3 us)
             float xv[4][DX];
