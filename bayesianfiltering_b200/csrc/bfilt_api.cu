@@ -462,7 +462,7 @@ struct PfRun {
     // large states (dx > 4) need ~128 registers per thread to keep a particle, its noise and the statistics out of
     // local memory: one CTA per SM for them
     constexpr int CPS = (M::DX > 4) ? 1 : PF_FUSED_CTAS_PER_SM;
-    auto kern = k_pf_fused<M, NW, CPS>;
+    auto kern = (h->world > 1) ? k_pf_fused<M, NW, CPS, true> : k_pf_fused<M, NW, CPS, false>;
     const int ntiles = h->ntiles;
     const int ntiles_scan = h->world > 1 ? h->world * ntiles + 1 : ntiles;       // the scan covers the whole filter's tiles
     const int nchunk = (ntiles_scan + 1 + NW * 128 - 1) / (NW * 128); // chunks of the one-CTA scan of the tile sums

@@ -294,7 +294,9 @@ __device__ __forceinline__ void load_state_cg(const float* base, size_t i, float
   }
 }
 
-template <class M, int CW, int CTAS_PER_SM>
+// SH: the sharded-filter code paths (peer tables, staging of remote ancestor ranges, cross-GPU barriers) are compiled
+// only into the SH = true instantiation; the one-GPU kernel does not carry their registers.
+template <class M, int CW, int CTAS_PER_SM, bool SH>
 __global__ void __launch_bounds__(CW * 32, CTAS_PER_SM)
 k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFusedArgs a) {
   constexpr int DX = M::DX, DQ = M::DQ, DY = M::DY;
@@ -352,14 +354,14 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   const bool all_phases = a.phases == PF_PH_ALL;
   const int ns_mask = (1 << (a.log2ns < 0 ? 0 : a.log2ns)) - 1;
   // global accessors: entry j of the (virtual) global tau array, particle j of the previous step's state
-  auto tauG = [&](int j) -> float { return (a.world == 1) ? a.E[j] : a.tau_peers[j >> a.log2ns][j & ns_mask]; };
+  auto tauG = [&](int j) -> float { if constexpr (!SH) return a.E[j]; else return a.tau_peers[j >> a.log2ns][j & ns_mask]; };
   const bool w_vec = (reinterpret_cast<size_t>(a.W) & 15) == 0;     // carry of trial b starts at b*N floats
   const bool use_win = use_tau && a.resampler == 1;      // sorted positions: windowed search
   // (i + u) / 2^k is an exact scaling: multiplying by 2^-k gives the same bits as the oracle's division
   const float invn_pow2 = (a.log2ng >= 0) ? __int_as_float((127 - a.log2ng) << 23) : 0.0f;
   // ---- cross-GPU barrier of the persistent sharded kernel.  Every thread that stored into a peer's buffer has run
   // __threadfence_system() and the grid has synchronised before CTA 0 raises the flags; readers spin on local memory.
-  const bool p2p = a.p2p != 0 && a.world > 1;
+  const bool p2p = SH && a.p2p != 0 && a.world > 1;
   const unsigned long long seq0 = p2p ? (*a.epoch) * (3ull << 22) : 0ull;
   auto xbarrier = [&](int ph, int step) {
     const unsigned long long seq = seq0 + 3ull * (unsigned long long)step + (unsigned long long)ph + 1ull;
@@ -408,7 +410,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       int lb = 0;
       if (nchunk_valid > 0) {
         const float r = position(slot, res_u0);
-        if (a.world == 1) lb = lower_bound_tau_pow2(a.E, a.log2ng, r);
+        if (!SH) lb = lower_bound_tau_pow2(a.E, a.log2ng, r);
         else {                                        // same bisection over the ranks' shards (peer loads)
           unsigned low = 0;
           for (unsigned sft = 1u << (a.log2ng - 1); sft != 0; sft >>= 1)
@@ -424,7 +426,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   // Ancestors of the 4 slots base..base+3 of the chunk starting at cbase.  Warp-synchronous (all lanes call it).
   // one global lower bound (any rank's shard) -- used by the rare fallbacks and by unsorted (multinomial) positions
   auto lb_global = [&](float r) -> int {
-    if (a.world == 1) return lower_bound_tau_pow2(a.E, a.log2ng, r);
+    if (!SH) return lower_bound_tau_pow2(a.E, a.log2ng, r);
     unsigned low = 0;
     for (unsigned sft = 1u << (a.log2ng - 1); sft != 0; sft >>= 1)
       if (!(r <= tauG((int)(low + sft)))) low += sft;
@@ -471,7 +473,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         }
         // Sharded filter, ancestors (partly) on another rank: x[lo .. lo+wn] is a contiguous range -- fetch it with
         // coalesced 512-byte peer reads into shared memory instead of one 16-byte NVLink round trip per particle.
-        if (a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
+        if (SH && a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
           float* xs = s_xst + (size_t)warp * PF_FUSED_XCAP * DX;
           for (int i0 = 0; i0 <= wn; i0 += 128) {       // four peer loads in flight per lane (an NVLink round trip is ~3 us)
             float xv[4][DX];
@@ -500,7 +502,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     }
     if (nv <= 0) return;
     if (use_tau) {
-      if (a.world == 1) bisect4_left_exclusive_pow2(a.E - 1, a.log2ng, r, anc);       // ex[j+1] == tau[j]
+      if (!SH) bisect4_left_exclusive_pow2(a.E - 1, a.log2ng, r, anc);       // ex[j+1] == tau[j]
       else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) anc[k] = min(lb_global(r[k]), Ng - 1);
@@ -513,7 +515,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 
   // particle `g` (GLOBAL index) of the state the step reads: own shard or a peer's
   auto load_prev = [&](int g, const float* xp_local, const float* const* xp_peers, float* x) {
-    if (a.world == 1) load_state_cg<DX>(xp_local, (size_t)g, x);
+    if (!SH) load_state_cg<DX>(xp_local, (size_t)g, x);
     else load_state_cg<DX>(xp_peers[g >> a.log2ns], (size_t)(g & ns_mask), x);
   };
 
@@ -570,7 +572,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         if (k < nv) {
           const int i = base + k;
           float x[DX], qn[DQ], xt[DX];
-          if (xs_lo >= 0) {
+          if (SH && xs_lo >= 0) {
             const float* xs = s_xst + ((size_t)warp * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
 #pragma unroll
             for (int c = 0; c < DX; ++c) x[c] = xs[c];
@@ -829,7 +831,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         if (!use_tau || base < N) *reinterpret_cast<float4*>(a.E + base) = out;
       }
     }
-    if (a.world > 1 && blockIdx.x == 0 && tid == 0) *a.total = __ldcg(&a.Etile[a.ntiles_g - 1]);   // E[Ng]
+    if (SH && blockIdx.x == 0 && tid == 0) *a.total = __ldcg(&a.Etile[a.ntiles_g - 1]);   // E[Ng]
     if (all_phases) grid.sync();                       // (gpu-scope fence: tau and the particles of this step are in this GPU's L2,
                                                        //  which is where the peers' NVLink reads are served from)
     if (p2p) xbarrier(2, t);
@@ -854,7 +856,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       if (k < nv) {
         const int i = base + k;
         float x[DX];
-        if (xs_lo >= 0) {
+        if (SH && xs_lo >= 0) {
           const float* xs = s_xst + ((size_t)warp * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
 #pragma unroll
           for (int c = 0; c < DX; ++c) x[c] = xs[c];
