@@ -1,6 +1,9 @@
 // bfilt_api.cu -- C ABI of libbfilt.so (see include/bfilt.h).  Host-side orchestration only: builds the
-// model constants, owns scratch + carry buffers, enqueues the kernels of pf_kernels.cuh / pf_resident.cuh /
-// gsf_kernels.cuh on the caller's stream.  No device synchronisation except in the *_host entry points.
+// model constants, owns scratch + carry buffers, enqueues the kernels of pf_fused.cuh / pf_resident.cuh /
+// gsf_kernels.cuh / gsf_large.cuh on the caller's stream.  No device synchronisation except in the *_host entry
+// points.  The model-templated kernels are compiled in other translation units (tu_kernels.cu) and reached through
+// the address table of ktable.h; this file only sees their argument structs.
+#define BF_TU_MAIN
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
@@ -14,6 +17,7 @@
 #include <nccl.h>
 #include "../../include/bfilt.h"
 #include "common.cuh"
+#include "ktable.h"
 #include "models.cuh"
 #include "scan.cuh"
 #include "pf_kernels.cuh"
@@ -43,6 +47,45 @@ static int fail(int code, const char* fmt, ...) {
 
 extern "C" const char* bf_last_error(void) { return g_err.c_str(); }
 extern "C" int bf_abi_version(void) { return BF_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------ kernel address table
+// csrc/build.sh compiles BF_NG_<KIND> slices of each kind and tells this file how many there are.
+#ifndef BF_NG_FUSED
+#error "build with csrc/build.sh (BF_NG_FUSED / BF_NG_RESIDENT / BF_NG_GSF / BF_NG_MISC are not defined)"
+#endif
+#define BFK_DECL(kind, g) int bfk_fill_##kind##_##g(const ModelConst&, BfKernelSet*);
+#define BFK_REF(kind, g) bfk_fill_##kind##_##g,
+#define BFK_FOR_1(X, kind) X(kind, 0)
+#define BFK_FOR_2(X, kind) BFK_FOR_1(X, kind) X(kind, 1)
+#define BFK_FOR_3(X, kind) BFK_FOR_2(X, kind) X(kind, 2)
+#define BFK_FOR_4(X, kind) BFK_FOR_3(X, kind) X(kind, 3)
+#define BFK_FOR_5(X, kind) BFK_FOR_4(X, kind) X(kind, 4)
+#define BFK_FOR_6(X, kind) BFK_FOR_5(X, kind) X(kind, 5)
+#define BFK_FOR_7(X, kind) BFK_FOR_6(X, kind) X(kind, 6)
+#define BFK_FOR_8(X, kind) BFK_FOR_7(X, kind) X(kind, 7)
+#define BFK_FOR2(n, X, kind) BFK_FOR_##n(X, kind)
+#define BFK_FOR(n, X, kind) BFK_FOR2(n, X, kind)
+BFK_FOR(BF_NG_FUSED, BFK_DECL, fused)
+BFK_FOR(BF_NG_RESIDENT, BFK_DECL, resident)
+BFK_FOR(BF_NG_GSF, BFK_DECL, gsf)
+BFK_FOR(BF_NG_MISC, BFK_DECL, misc)
+static const bfk_fill_fn g_fill_fused[] = {BFK_FOR(BF_NG_FUSED, BFK_REF, fused)};
+static const bfk_fill_fn g_fill_resident[] = {BFK_FOR(BF_NG_RESIDENT, BFK_REF, resident)};
+static const bfk_fill_fn g_fill_gsf[] = {BFK_FOR(BF_NG_GSF, BFK_REF, gsf)};
+static const bfk_fill_fn g_fill_misc[] = {BFK_FOR(BF_NG_MISC, BFK_REF, misc)};
+
+static int kernels_for(const ModelConst& mc, int kind, BfKernelSet* ks) {
+  const bfk_fill_fn* fns; int n;
+  switch (kind) {
+    case BFK_FUSED: fns = g_fill_fused; n = BF_NG_FUSED; break;
+    case BFK_RESIDENT: fns = g_fill_resident; n = BF_NG_RESIDENT; break;
+    case BFK_GSF: fns = g_fill_gsf; n = BF_NG_GSF; break;
+    default: fns = g_fill_misc; n = BF_NG_MISC; break;
+  }
+  memset(ks, 0, sizeof *ks);
+  for (int i = 0; i < n; ++i) if (fns[i](mc, ks) == 0) return BF_OK;
+  return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", mc.model_id, mc.dx, mc.dy);
+}
 
 // ------------------------------------------------------------------------------------------ model constants
 // fp32 Cholesky, like TFP's MultivariateNormalFullCovariance(cov) -> scale_tril = cholesky(cov).
@@ -427,11 +470,28 @@ extern "C" int bf_pf_kernel_launches(bf_pf_handle h, int64_t* out) {
   *out = h->launches; return BF_OK;
 }
 
+static int launch_init_particles(int dx, int grid, cudaStream_t s, const ModelConst& mc, float* x, int N, unsigned long long seed,
+                                 int trial, int goff) {
+  switch (dx) {
+    case 1: k_init_particles<1><<<grid, 256, 0, s>>>(mc, x, N, seed, trial, goff); break;
+    case 2: k_init_particles<2><<<grid, 256, 0, s>>>(mc, x, N, seed, trial, goff); break;
+    case 3: k_init_particles<3><<<grid, 256, 0, s>>>(mc, x, N, seed, trial, goff); break;
+    case 4: k_init_particles<4><<<grid, 256, 0, s>>>(mc, x, N, seed, trial, goff); break;
+    case 8: k_init_particles<8><<<grid, 256, 0, s>>>(mc, x, N, seed, trial, goff); break;
+    default: return fail(BF_ENOMODEL, "no initial-particle kernel for dx=%d", dx);
+  }
+  LAUNCH_OK();
+  return BF_OK;
+}
+
 namespace {
 struct PfRun {
   bf_pf_s* h; const bf_pf_io* io; cudaStream_t s;
 
-  template <class M> int resident() {
+  int resident() {
+    BfKernelSet ks;
+    int rck = kernels_for(h->mc, BFK_RESIDENT, &ks);
+    if (rck) return rck;
     PfResidentArgs a;
     a.N = h->N; a.T = io->T; a.t_offset = io->t_offset; a.resume = io->resume; a.resampler = h->cfg.resampler;
     a.emissions_per_trial = io->emissions_per_trial; a.ess_threshold = h->cfg.ess_threshold; a.seed = h->cfg.seed;
@@ -442,27 +502,23 @@ struct PfRun {
     a.out_norm_weights = io->out_norm_weights; a.out_ancestors = io->out_ancestors; a.out_mean = io->out_mean;
     a.out_loglik = io->out_loglik; a.out_ess = io->out_ess; a.out_resampled = io->out_resampled;
     a.final_particles = io->final_particles; a.final_weights = io->final_weights;
-    if (h->resident_warps == 8) {
-      CUDA_OK(cudaFuncSetAttribute(k_pf_resident<M, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resident_smem));
-      k_pf_resident<M, 8><<<h->B, 256, h->resident_smem, s>>>(h->mc, a);
-    } else {
-      CUDA_OK(cudaFuncSetAttribute(k_pf_resident<M, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resident_smem));
-      k_pf_resident<M, 32><<<h->B, 1024, h->resident_smem, s>>>(h->mc, a);
-    }
-    LAUNCH_OK();
+    const void* kr = ks.resident[h->resident_warps == 8 ? 0 : 1];
+    CUDA_OK(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resident_smem));
+    void* params[] = {(void*)&h->mc, (void*)&a};
+    CUDA_OK(cudaLaunchKernel(kr, dim3(h->B), dim3(h->resident_warps * 32), params, h->resident_smem, s));
     h->launches += 1;
     return BF_OK;
   }
 
   // large-N path: one persistent cooperative kernel per trial runs all T steps (pf_fused.cuh)
-  template <class M> int streamed() {
-    constexpr int DX = M::DX, DQ = M::DQ, DY = M::DY;
+  int streamed() {
+    BfKernelSet ks;
+    int rck = kernels_for(h->mc, BFK_FUSED, &ks);
+    if (rck) return rck;
+    const int DX = h->mc.dx, DQ = h->mc.dq, DY = h->mc.dy;
     constexpr int NW = PF_FUSED_WARPS, TW = PF_FUSED_TILE_CHUNKS;
     const int N = h->N, B = h->B, T = io->T;
-    // large states (dx > 4) need ~128 registers per thread to keep a particle, its noise and the statistics out of
-    // local memory: one CTA per SM for them
-    constexpr int CPS = (M::DX > 4) ? 1 : PF_FUSED_CTAS_PER_SM;
-    auto kern = (h->world > 1) ? k_pf_fused<M, NW, CPS, true> : k_pf_fused<M, NW, CPS, false>;
+    const void* kern = ks.fused[h->world > 1 ? 1 : 0];       // the sharded instantiation carries the peer-memory code
     const int ntiles = h->ntiles;
     const int ntiles_scan = h->world > 1 ? h->world * ntiles + 1 : ntiles;       // the scan covers the whole filter's tiles
     const int nchunk = (ntiles_scan + 1 + NW * 128 - 1) / (NW * 128); // chunks of the one-CTA scan of the tile sums
@@ -544,8 +600,8 @@ struct PfRun {
       if (io->resume) a.x_init = cx;
       else if (io->init_particles) a.x_init = io->init_particles + (size_t)b * N * DX;
       else {
-        k_init_particles<DX><<<grid_s, 256, 0, s>>>(h->mc, cx, N, h->cfg.seed, b, rank * N);
-        LAUNCH_OK(); h->launches++;
+        if ((rck = launch_init_particles(DX, grid_s, s, h->mc, cx, N, h->cfg.seed, b, rank * N))) return rck;
+        h->launches++;
         a.x_init = cx;
       }
       if (!io->resume && io->init_weights)
@@ -591,7 +647,7 @@ struct PfRun {
       a.tile_off = rank * (world > 1 ? ntiles : 0); a.ntiles_g = ntiles_g; a.phases = PF_PH_ALL;
       if (world == 1) {
         void* params[] = {(void*)&h->mc, (void*)&a};
-        CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, s));
+        CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NW * 32), params, smem, s));
         h->launches++;
         continue;
       }
@@ -604,7 +660,7 @@ struct PfRun {
         // one persistent kernel for the whole run; the ranks meet through peer-memory stores and flags inside it
         a.p2p = 1;
         void* params[] = {(void*)&h->mc, (void*)&a};
-        CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, s));
+        CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NW * 32), params, smem, s));
         h->launches++;
         // the next run reuses the buffers the peers' final gather may still be reading
         NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, s));
@@ -629,7 +685,7 @@ struct PfRun {
         p.out_ess = a.out_ess ? a.out_ess + t : nullptr;
         p.out_resampled = a.out_resampled ? a.out_resampled + t : nullptr;
         void* params[] = {(void*)&h->mc, (void*)&p};
-        CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NW * 32), params, smem, st));
+        CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NW * 32), params, smem, st));
         ++nlaunch;
         return BF_OK;
       };
@@ -704,10 +760,7 @@ struct PfRun {
     return BF_OK;
   }
 
-  template <class M> int run() {
-    if (h->path == BF_PATH_RESIDENT) return resident<M>();
-    return streamed<M>();
-  }
+  int run() { return h->path == BF_PATH_RESIDENT ? resident() : streamed(); }
 };
 }  // namespace
 
@@ -724,8 +777,7 @@ extern "C" int bf_pf_run(bf_pf_handle h, const bf_pf_io* io, void* stream) {
   if (rc) return rc;
   CUDA_OK(cudaSetDevice(h->cfg.device));
   PfRun fn{h, io, (cudaStream_t)stream};
-  rc = bf_dispatch_model(h->mc, fn);
-  if (rc == -3) return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", h->mc.model_id, h->mc.dx, h->mc.dy);
+  rc = fn.run();
   if (rc == BF_OK) h->have_carry = true;
   return rc;
 }
@@ -875,7 +927,10 @@ extern "C" int bf_gsf_kernel_launches(bf_gsf_handle h, int64_t* out) {
 namespace {
 struct GsfRun {
   bf_gsf_s* h; const bf_gsf_io* io; cudaStream_t s;
-  template <class M> int run() {
+  int run() {
+    BfKernelSet ks;
+    int rck = kernels_for(h->mc, BFK_GSF, &ks);
+    if (rck) return rck;
     GsfArgs a;
     a.M = h->cfg.num_components; a.T = io->T; a.resume = io->resume; a.emissions_per_trial = io->emissions_per_trial;
     a.flags = h->cfg.flags;
@@ -887,25 +942,29 @@ struct GsfRun {
     a.out_mix_mean = io->out_mix_mean;
     // one warp per trial when the mixture fits CPL components per lane within the register budget
     // (state words per lane: CPL * (1 + dx + dx^2)); else one CTA per trial, one thread per component
-    constexpr int DXm = M::DX, WORDS = 1 + DXm + DXm * DXm;
+    const int DXm = h->mc.dx, WORDS = 1 + DXm + DXm * DXm;
     const int cpl = (a.M + 31) / 32;
-    const int B = h->cfg.num_trials, gridw = (B + 3) / 4;
+    int B = h->cfg.num_trials;
+    const int gridw = (B + 3) / 4;
     // a warp per trial needs enough trials to fill the machine (B warps in flight); below that, one thread per
     // component keeps more warps resident.  BF_GSF_KERNEL=cta|warp overrides (experiments).
     const char* force = getenv("BF_GSF_KERNEL");
     const bool want_warp = force ? (strcmp(force, "warp") == 0) : (B >= 16 * h->nsm);
-    if (!want_warp) {
-      const int threads = std::max(32, ((a.M + 31) / 32) * 32);
-      k_gsf<M><<<B, threads, 0, s>>>(h->mc, a);
-    } else if (cpl == 1 && WORDS <= 96) k_gsf_warp<M, 1><<<gridw, 128, 0, s>>>(h->mc, a, B);
-    else if (cpl == 2 && 2 * WORDS <= 64) k_gsf_warp<M, 2><<<gridw, 128, 0, s>>>(h->mc, a, B);
-    else if (cpl <= 4 && 4 * WORDS <= 48) k_gsf_warp<M, 4><<<gridw, 128, 0, s>>>(h->mc, a, B);
-    else if (cpl <= 8 && 8 * WORDS <= 32) k_gsf_warp<M, 8><<<gridw, 128, 0, s>>>(h->mc, a, B);
-    else {
-      const int threads = std::max(32, ((a.M + 31) / 32) * 32);
-      k_gsf<M><<<B, threads, 0, s>>>(h->mc, a);
+    int wk = -1;
+    if (want_warp) {
+      if (cpl == 1 && WORDS <= 96) wk = 0;
+      else if (cpl == 2 && 2 * WORDS <= 64) wk = 1;
+      else if (cpl <= 4 && 4 * WORDS <= 48) wk = 2;
+      else if (cpl <= 8 && 8 * WORDS <= 32) wk = 3;
     }
-    LAUNCH_OK();
+    if (wk >= 0) {
+      void* params[] = {(void*)&h->mc, (void*)&a, (void*)&B};
+      CUDA_OK(cudaLaunchKernel(ks.gsf_warp[wk], dim3(gridw), dim3(128), params, 0, s));
+    } else {
+      const int threads = std::max(32, ((a.M + 31) / 32) * 32);
+      void* params[] = {(void*)&h->mc, (void*)&a};
+      CUDA_OK(cudaLaunchKernel(ks.gsf_cta, dim3(B), dim3(threads), params, 0, s));
+    }
     h->launches += 1;
     return BF_OK;
   }
@@ -934,20 +993,15 @@ extern "C" int bf_gsf_run(bf_gsf_handle h, const bf_gsf_io* io, void* stream) {
     a.out_weights = io->out_weights; a.out_means = io->out_means; a.out_covs = io->out_covs; a.out_pred_means = io->out_pred_means;
     a.out_pred_covs = io->out_pred_covs; a.out_loglik = io->out_loglik; a.out_mix_mean = io->out_mix_mean;
     const size_t smem = gsf_large_smem_bytes(h->dx, h->dy, a.M);
-    if (h->dx == 40) {
-      CUDA_OK(cudaFuncSetAttribute(k_gsf_large<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_gsf_large<40><<<h->cfg.num_trials, GL_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
-    } else {
-      CUDA_OK(cudaFuncSetAttribute(k_gsf_large<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_gsf_large<0><<<h->cfg.num_trials, GL_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
-    }
-    LAUNCH_OK();
+    const void* kl = bfk_gsf_large(h->dx == 40 ? 40 : 0);
+    CUDA_OK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* params[] = {(void*)&a};
+    CUDA_OK(cudaLaunchKernel(kl, dim3(h->cfg.num_trials), dim3(GL_WARPS * 32), params, smem, (cudaStream_t)stream));
     h->launches += 1; h->have_carry = true;
     return BF_OK;
   }
   GsfRun fn{h, io, (cudaStream_t)stream};
-  rc = bf_dispatch_model(h->mc, fn);
-  if (rc == -3) return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", h->mc.model_id, h->mc.dx, h->mc.dy);
+  rc = fn.run();
   if (rc == BF_OK) h->have_carry = true;
   return rc;
 }
@@ -1028,27 +1082,6 @@ extern "C" int bf_resample(const float* w, const float* u, int32_t* anc, int64_t
 }
 
 // ========================================================================================== model eval / sampler
-namespace {
-struct EvalRun {
-  const ModelConst* mc; int what; int n; const float* x; const float* aux; float u; float* out; cudaStream_t s;
-  template <class M> int run() {
-    const int grid = std::max(1, std::min((n + 127) / 128, 4096));
-    k_model_eval<M><<<grid, 128, 0, s>>>(*mc, what, n, x, aux, u, out);
-    LAUNCH_OK();
-    return BF_OK;
-  }
-};
-struct SampleRun {
-  const ModelConst* mc; int B, T; const float* inputs; unsigned long long seed; const float *z0, *qn, *rn; float *states, *emissions;
-  cudaStream_t s;
-  template <class M> int run() {
-    k_ssm_sample<M><<<(B + 63) / 64, 64, 0, s>>>(*mc, B, T, inputs, seed, z0, qn, rn, states, emissions);
-    LAUNCH_OK();
-    return BF_OK;
-  }
-};
-}  // namespace
-
 extern "C" int bf_model_eval(const bf_model_desc* model, int32_t what, int64_t n, const float* x, const float* aux, float u,
                              float* out, void* stream) {
   ModelConst mc;
@@ -1057,10 +1090,13 @@ extern "C" int bf_model_eval(const bf_model_desc* model, int32_t what, int64_t n
   if (what < 0 || what > 5) return fail(BF_EINVAL, "what=%d out of range", what);
   if (n < 1 || n > (int64_t)1 << 30 || !x || !out) return fail(BF_EINVAL, "bad n or NULL pointer");
   if (what == 5 && !aux) return fail(BF_EINVAL, "log-prob needs y in aux");
-  EvalRun fn{&mc, what, (int)n, x, aux, u, out, (cudaStream_t)stream};
-  rc = bf_dispatch_model(mc, fn);
-  if (rc == -3) return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", mc.model_id, mc.dx, mc.dy);
-  return rc;
+  BfKernelSet ks;
+  if ((rc = kernels_for(mc, BFK_MISC, &ks))) return rc;
+  int nn = (int)n, wh = what;
+  const int grid = std::max(1, std::min((nn + 127) / 128, 4096));
+  void* params[] = {(void*)&mc, (void*)&wh, (void*)&nn, (void*)&x, (void*)&aux, (void*)&u, (void*)&out};
+  CUDA_OK(cudaLaunchKernel(ks.model_eval, dim3(grid), dim3(128), params, 0, (cudaStream_t)stream));
+  return BF_OK;
 }
 
 extern "C" int bf_ssm_sample(const bf_model_desc* model, int32_t B, int32_t T, const float* inputs, uint64_t seed,
@@ -1070,8 +1106,12 @@ extern "C" int bf_ssm_sample(const bf_model_desc* model, int32_t B, int32_t T, c
   int rc = build_model_const(model, &mc);
   if (rc) return rc;
   if (B < 1 || T < 1 || !states || !emissions) return fail(BF_EINVAL, "bad B/T or NULL output");
-  SampleRun fn{&mc, B, T, inputs, seed, z0, q_noise, r_noise, states, emissions, (cudaStream_t)stream};
-  rc = bf_dispatch_model(mc, fn);
-  if (rc == -3) return fail(BF_ENOMODEL, "model %d with dx=%d dy=%d is not instantiated", mc.model_id, mc.dx, mc.dy);
-  return rc;
+  BfKernelSet ks;
+  if ((rc = kernels_for(mc, BFK_MISC, &ks))) return rc;
+  int Bv = B, Tv = T;
+  unsigned long long sd = seed;
+  void* params[] = {(void*)&mc, (void*)&Bv, (void*)&Tv, (void*)&inputs, (void*)&sd, (void*)&z0, (void*)&q_noise, (void*)&r_noise,
+                    (void*)&states, (void*)&emissions};
+  CUDA_OK(cudaLaunchKernel(ks.ssm_sample, dim3((B + 63) / 64), dim3(64), params, 0, (cudaStream_t)stream));
+  return BF_OK;
 }

@@ -270,32 +270,42 @@ __device__ __forceinline__ float emission_log_prob(const float* x, const float* 
   return -0.5f * ss + c.lp_const;
 }
 
-// Dispatch a generic lambda-like functor over the registry.  F must provide `template<class M> int run()`.
-#define BF_DISPATCH_LG(F, dxv, dyv)                                  \
-  if (mc.dx == dxv && mc.dy == dyv) return F.template run<LgModel<dxv, dyv>>();
+// Dispatch a functor over the registry.  F must provide `template<class M> int run()`.  Returns -3 when the model is
+// not instantiated HERE: the kernel translation units are compiled as BF_NGROUPS slices of the registry (entry k
+// belongs to slice k % BF_NGROUPS), several nvcc processes side by side (csrc/build.sh).  Heavy entries come first so
+// that they land in different slices.
+#ifndef BF_NGROUPS
+#define BF_NGROUPS 1
+#define BF_GROUP 0
+#endif
+#ifdef BF_DEV_MODELS          // fast development builds: only the two bench models
+#define BF_DEV_KEEP(k) ((k) == 1 || (k) == 2)
+#else
+#define BF_DEV_KEEP(k) true
+#endif
+#define BF_ENTRY(k, cond, ...)                                                        \
+  if constexpr (((k) % BF_NGROUPS) == BF_GROUP && BF_DEV_KEEP(k)) {                    \
+    if (cond) return fn.template run<__VA_ARGS__>();                                  \
+  }
 
 template <class F>
 int bf_dispatch_model(const ModelConst& mc, F& fn) {
-#ifdef BF_DEV_MODELS          // fast development builds: only the two bench models
-  if (mc.model_id == 1) return fn.template run<UngmModel>();
-  if (mc.model_id == 2 && mc.dy == 2) return fn.template run<BotModel<2>>();
+  const int id = mc.model_id, dx = mc.dx, dy = mc.dy;
+  BF_ENTRY(0, id == 5 && dx == 8 && dy == 8, LgModel<8, 8>)
+  BF_ENTRY(1, id == 2 && dy == 2, BotModel<2>)
+  BF_ENTRY(2, id == 1, UngmModel)
+  BF_ENTRY(3, id == 3, L63Model)
+  BF_ENTRY(4, id == 5 && dx == 4 && dy == 4, LgModel<4, 4>)
+  BF_ENTRY(5, id == 2 && dy == 1, BotModel<1>)
+  BF_ENTRY(6, id == 5 && dx == 3 && dy == 3, LgModel<3, 3>)
+  BF_ENTRY(7, id == 5 && dx == 4 && dy == 2, LgModel<4, 2>)
+  BF_ENTRY(8, id == 6 && dx == 3, Sin1dModel<3>)
+  BF_ENTRY(9, id == 5 && dx == 2 && dy == 2, LgModel<2, 2>)
+  BF_ENTRY(10, id == 5 && dx == 3 && dy == 1, LgModel<3, 1>)
+  BF_ENTRY(11, id == 6 && dx == 2, Sin1dModel<2>)
+  BF_ENTRY(12, id == 5 && dx == 2 && dy == 1, LgModel<2, 1>)
+  BF_ENTRY(13, id == 5 && dx == 1 && dy == 1, LgModel<1, 1>)
+  BF_ENTRY(14, id == 6 && dx == 1, Sin1dModel<1>)
+  (void)id; (void)dx; (void)dy;
   return -3;
-#else
-  switch (mc.model_id) {
-    case 1: return fn.template run<UngmModel>();
-    case 2: if (mc.dy == 1) return fn.template run<BotModel<1>>();
-            if (mc.dy == 2) return fn.template run<BotModel<2>>();
-            return -3;
-    case 3: return fn.template run<L63Model>();
-    case 5:
-      BF_DISPATCH_LG(fn, 1, 1) BF_DISPATCH_LG(fn, 2, 1) BF_DISPATCH_LG(fn, 2, 2) BF_DISPATCH_LG(fn, 3, 1)
-      BF_DISPATCH_LG(fn, 3, 3) BF_DISPATCH_LG(fn, 4, 2) BF_DISPATCH_LG(fn, 4, 4) BF_DISPATCH_LG(fn, 8, 8)
-      return -3;
-    case 6: if (mc.dx == 1) return fn.template run<Sin1dModel<1>>();
-            if (mc.dx == 2) return fn.template run<Sin1dModel<2>>();
-            if (mc.dx == 3) return fn.template run<Sin1dModel<3>>();
-            return -3;
-    default: return -3;
-  }
-#endif
 }

@@ -1,0 +1,79 @@
+// tu_kernels.cu -- one slice of the model-templated kernels.  Compiled several times by csrc/build.sh with
+//   -DBF_TU_KIND=<BFK_*>  -DBF_NGROUPS=<slices of this kind>  -DBF_GROUP=<this slice>
+// and exports the addresses of the kernels it instantiated (ktable.h).  No host logic lives here.
+#include "ktable.h"
+#include "models.cuh"
+#include "scan.cuh"
+#include "pf_kernels.cuh"
+
+#define BFK_NAME2(kind, g) bfk_fill_##kind##_##g
+#define BFK_NAME(kind, g) BFK_NAME2(kind, g)
+
+#if BF_TU_KIND == 1  // ------------------------------------------------------------------ fused particle filter
+#include "pf_fused.cuh"
+namespace {
+struct Fill {
+  BfKernelSet* k;
+  template <class M> int run() {
+    // large states (dx > 4) need ~128 registers per thread to keep a particle, its noise and the statistics out of
+    // local memory: one CTA per SM for them
+    constexpr int CPS = (M::DX > 4) ? 1 : PF_FUSED_CTAS_PER_SM;
+    k->fused[0] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, false>;
+    k->fused[1] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, true>;
+    return 0;
+  }
+};
+}  // namespace
+int BFK_NAME(fused, BF_GROUP)(const ModelConst& mc, BfKernelSet* k) { Fill f{k}; return bf_dispatch_model(mc, f); }
+
+#elif BF_TU_KIND == 2  // ---------------------------------------------------------------- resident particle filter
+#include "pf_resident.cuh"
+namespace {
+struct Fill {
+  BfKernelSet* k;
+  template <class M> int run() {
+    k->resident[0] = (const void*)k_pf_resident<M, 8>;
+    k->resident[1] = (const void*)k_pf_resident<M, 32>;
+    return 0;
+  }
+};
+}  // namespace
+int BFK_NAME(resident, BF_GROUP)(const ModelConst& mc, BfKernelSet* k) { Fill f{k}; return bf_dispatch_model(mc, f); }
+
+#elif BF_TU_KIND == 3  // ---------------------------------------------------------------- Gaussian-sum filter
+#include "gsf_kernels.cuh"
+namespace {
+struct Fill {
+  BfKernelSet* k;
+  template <class M> int run() {
+    k->gsf_cta = (const void*)k_gsf<M>;
+    k->gsf_warp[0] = (const void*)k_gsf_warp<M, 1>;
+    k->gsf_warp[1] = (const void*)k_gsf_warp<M, 2>;
+    k->gsf_warp[2] = (const void*)k_gsf_warp<M, 4>;
+    k->gsf_warp[3] = (const void*)k_gsf_warp<M, 8>;
+    return 0;
+  }
+};
+}  // namespace
+int BFK_NAME(gsf, BF_GROUP)(const ModelConst& mc, BfKernelSet* k) { Fill f{k}; return bf_dispatch_model(mc, f); }
+
+#elif BF_TU_KIND == 4  // ---------------------------------------------------------------- model evaluation, data generator
+namespace {
+struct Fill {
+  BfKernelSet* k;
+  template <class M> int run() {
+    k->model_eval = (const void*)k_model_eval<M>;
+    k->ssm_sample = (const void*)k_ssm_sample<M>;
+    return 0;
+  }
+};
+}  // namespace
+int BFK_NAME(misc, BF_GROUP)(const ModelConst& mc, BfKernelSet* k) { Fill f{k}; return bf_dispatch_model(mc, f); }
+
+#elif BF_TU_KIND == 5  // ---------------------------------------------------------------- large-state Gaussian-sum filter
+#include "gsf_large.cuh"
+const void* bfk_gsf_large(int dxt) { return dxt == 40 ? (const void*)k_gsf_large<40> : (const void*)k_gsf_large<0>; }
+
+#else
+#error "BF_TU_KIND must be 1..5"
+#endif
