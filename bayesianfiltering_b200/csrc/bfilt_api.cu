@@ -349,8 +349,9 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
       if (h->xchg.ensure_plain(xbytes)) { bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the exchange buffer failed"); }
       cudaMemset(h->xchg.p, 0, xbytes);
     }
-    if (h->phase_ns.ensure(8 * sizeof(unsigned long long))) { bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc failed"); }
-    cudaMemset(h->phase_ns.p, 0, 8 * sizeof(unsigned long long));
+    // 8 phase counters (+ 16 per CTA for the BF_EXP_TRACE experiment build)
+    if (h->phase_ns.ensure((8 + 16 * 1024) * sizeof(unsigned long long))) { bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc failed"); }
+    cudaMemset(h->phase_ns.p, 0, (8 + 16 * 1024) * sizeof(unsigned long long));
   }
   *out = h;
   return BF_OK;
@@ -461,6 +462,13 @@ extern "C" int bf_pf_phase_times(bf_pf_handle h, double* out_ms, int32_t reset) 
   unsigned long long ns[5];
   CUDA_OK(cudaMemcpy(ns, h->phase_ns.p, sizeof ns, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 5; ++i) out_ms[i] = (double)ns[i] * 1e-6;
+#ifdef BF_EXP_TRACE
+  if (const char* path = getenv("BF_TRACE_FILE")) {
+    std::vector<unsigned long long> tr(16 * 1024);
+    CUDA_OK(cudaMemcpy(tr.data(), h->phase_ns.as<unsigned long long>() + 8, tr.size() * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(path, "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
+  }
+#endif
   if (reset) CUDA_OK(cudaMemset(h->phase_ns.p, 0, sizeof ns));
   return BF_OK;
 }
@@ -518,7 +526,14 @@ struct PfRun {
     const int DX = h->mc.dx, DQ = h->mc.dq, DY = h->mc.dy;
     constexpr int NW = PF_FUSED_WARPS, TW = PF_FUSED_TILE_CHUNKS;
     const int N = h->N, B = h->B, T = io->T;
-    const void* kern = ks.fused[h->world > 1 ? 1 : 0];       // the sharded instantiation carries the peer-memory code
+    // three instantiations: general, sharded (carries the peer-memory code), lean (throughput configuration: the
+    // optional inputs / per-particle outputs of the call are all absent, see pf_fused.cuh)
+    const bool pow2 = N >= 8 && (N & (N - 1)) == 0;
+    const char* lenv = getenv("BF_PF_LEAN");
+    const bool lean = h->world == 1 && pow2 && h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC && !io->noise && !io->resample_u &&
+                      !io->out_particles && !io->out_propagated && !io->out_ancestors && !io->out_norm_weights && !io->out_weights &&
+                      !(lenv && lenv[0] == '0');
+    const void* kern = ks.fused[h->world > 1 ? 1 : (lean ? 2 : 0)];
     const int ntiles = h->ntiles;
     const int ntiles_scan = h->world > 1 ? h->world * ntiles + 1 : ntiles;       // the scan covers the whole filter's tiles
     const int nchunk = (ntiles_scan + 1 + NW * 128 - 1) / (NW * 128); // chunks of the one-CTA scan of the tile sums

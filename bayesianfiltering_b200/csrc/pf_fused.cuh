@@ -296,9 +296,19 @@ __device__ __forceinline__ void load_state_cg(const float* base, size_t i, float
 
 // SH: the sharded-filter code paths (peer tables, staging of remote ancestor ranges, cross-GPU barriers) are compiled
 // only into the SH = true instantiation; the one-GPU kernel does not carry their registers.
-template <class M, int CW, int CTAS_PER_SM, bool SH>
+template <class M, int CW, int CTAS_PER_SM, bool SH, bool LEAN>
 __global__ void __launch_bounds__(CW * 32, CTAS_PER_SM)
-k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFusedArgs a) {
+k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFusedArgs a_in) {
+  // LEAN: the throughput configuration -- in-kernel Philox noise and uniforms, systematic resampling on the tau path,
+  // whole run in one launch, summaries only (mean / log-lik / ESS / flag per step, final state).  Its optional
+  // pointers are compile-time NULL here, which removes their code from the hot loop (measured: phase A 298 -> 272 us
+  // at N = 2^24; the kernel is instruction-issue- and instruction-fetch-bound).  The host picks it when the call
+  // qualifies (bfilt_api.cu), otherwise the general instantiation runs.
+  PfFusedArgs a = a_in;
+  if constexpr (LEAN) {
+    a.noise = nullptr; a.res_u = nullptr; a.out_particles = nullptr; a.out_propagated = nullptr; a.out_ancestors = nullptr;
+    a.out_norm_weights = nullptr; a.out_weights = nullptr; a.resampler = 1; a.use_tau = 1; a.phases = PF_PH_ALL;
+  }
   constexpr int DX = M::DX, DQ = M::DQ, DY = M::DY;
   constexpr int TW = PF_FUSED_TILE_CHUNKS;              // chunks per tile: a level of the canonical tree, not a CTA shape
   constexpr int NT = CW * 32, TILE = TW * 128, WINCAP = PF_FUSED_WINCAP;
@@ -525,6 +535,17 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (timer) { const unsigned long long now = globaltimer_ns(); a.phase_ns[phase] += now - tmark; tmark = now; }
   };
 
+#ifdef BF_EXP_TRACE   // experiment: per-CTA arrival / release times at the four grid syncs of step T/2 -> phase_ns[8 + 16 b + k], SM id at k = 8
+  auto trace = [&](int t, int k) {
+    if (tid == 0 && a.phase_ns != nullptr && t == T / 2) {
+      a.phase_ns[8 + 16 * blockIdx.x + k] = globaltimer_ns();
+      if (k == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); a.phase_ns[8 + 16 * blockIdx.x + 8] = sm; }
+    }
+  };
+#else
+  auto trace = [&](int, int) {};
+#endif
+
   // single-phase launches (sharded filter): one step per launch, t_offset is its absolute index; the state that
   // crosses launches lives in two StepStats slots, read at [pt & 1] and written (phase B) at [(pt + 1) & 1]
   if (!all_phases) {
@@ -644,7 +665,9 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
     }
     }  // phase A
+    trace(t, 0);
     if (all_phases) grid.sync();
+    trace(t, 1);
     if (p2p) xbarrier(0, t);
     lap(0);
     if (!(a.phases & (PF_PH_B | PF_PH_C))) break;
@@ -778,14 +801,18 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
     }
     }  // phase B tile sums
+    trace(t, 2);
     if (all_phases) grid.sync();
+    trace(t, 3);
     if (p2p) xbarrier(1, t);
     lap(1);
     if (!(a.phases & PF_PH_C)) break;
 
     // ------------------------------------------------------------------ phase C1 (CTA 0; every rank of a sharded filter)
     if (blockIdx.x == 0) cta_exclusive_scan<CW>(a.tilesum, a.Etile, a.ntiles_g, s_win);
+    trace(t, 4);
     grid.sync();
+    trace(t, 5);
     lap(2);
 
     // ------------------------------------------------------------------ phase C2
@@ -832,8 +859,10 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
     }
     if (SH && blockIdx.x == 0 && tid == 0) *a.total = __ldcg(&a.Etile[a.ntiles_g - 1]);   // E[Ng]
+    trace(t, 6);
     if (all_phases) grid.sync();                       // (gpu-scope fence: tau and the particles of this step are in this GPU's L2,
                                                        //  which is where the peers' NVLink reads are served from)
+    trace(t, 7);
     if (p2p) xbarrier(2, t);
     lap(3);
     w_uni = true; gather = true;

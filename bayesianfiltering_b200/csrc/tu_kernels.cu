@@ -18,8 +18,9 @@ struct Fill {
     // large states (dx > 4) need ~128 registers per thread to keep a particle, its noise and the statistics out of
     // local memory: one CTA per SM for them
     constexpr int CPS = (M::DX > 4) ? 1 : PF_FUSED_CTAS_PER_SM;
-    k->fused[0] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, false>;
-    k->fused[1] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, true>;
+    k->fused[0] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, false, false>;
+    k->fused[1] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, true, false>;
+    k->fused[2] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, false, true>;
     return 0;
   }
 };

@@ -222,6 +222,31 @@ def test_streamed_runs_are_bit_reproducible():
     assert np.all(np.isfinite(ref["log_likelihood"]))
 
 
+@pytest.mark.parametrize("name,N,thr", [("bot2", 1 << 16, 1.0), ("bot2", 1 << 15, 0.5), ("ungm", 1 << 14, 0.5),
+                                        ("lg3", 1 << 13, 0.7), ("l63", 1 << 13, 1.0), ("lg8", 1 << 13, 1.0)])
+def test_lean_instantiation_equals_general_kernel(name, N, thr, monkeypatch):
+    """A call in the throughput configuration (Philox noise, systematic resampling, power-of-two N, summaries only)
+    runs the LEAN instantiation of k_pf_fused, whose optional code paths are compiled out.  It must be the same
+    arithmetic: bit-identical to the general instantiation (BF_PF_LEAN=0), which the step-wise tests tie to the
+    oracle."""
+    c = case(name)
+    T = 14
+    _, ys = c.simulate(T, 9)
+    u = c.inputs(T)
+    outs = ("means", "log_likelihood", "ess", "resampled", "final_particles", "final_weights")
+    res = {}
+    for lean in ("1", "0"):
+        monkeypatch.setenv("BF_PF_LEAN", lean)
+        eng = _engine(c, N, 1, thr, "systematic", "streamed", seed=5)
+        res[lean] = eng.run_host(ys, inputs=u, outputs=outs)
+        eng.close()
+    for k in outs:
+        assert np.array_equal(res["1"][k], res["0"][k]), k
+    assert np.all(np.isfinite(res["1"]["log_likelihood"]))
+    if thr == 1.0:
+        assert np.all(res["1"]["resampled"] == 1)
+
+
 def test_device_tensor_mode_matches_host_mode():
     import torch
     c = case("bot2")
