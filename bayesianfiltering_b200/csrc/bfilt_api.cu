@@ -542,7 +542,8 @@ struct PfRun {
     // shared memory depends on tiles_per_cta, which depends on the grid, which depends on shared memory: iterate
     int grid = 1, tpc = ntiles;
     size_t smem = 0;
-    auto smem_for = [&](int t) { return (size_t)((3 * TW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, nchunk + 1 + NW + 8) +
+    const int stage_ts = (ntiles_scan <= 16384) ? ((ntiles_scan + 3) & ~3) : 0;   // tile sums staged in shared memory by C1
+    auto smem_for = [&](int t) { return (size_t)((3 * TW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, stage_ts + nchunk + 1 + NW + 8) +
                                                 (xstage ? NW * PF_FUSED_XCAP * DX : 0) + 8) * sizeof(float); };
     for (int round = 0; round < 3; ++round) {
       smem = smem_for(round == 0 ? 64 : tpc);
@@ -562,7 +563,8 @@ struct PfRun {
       if (grid > per_sm * h->nsm) return fail(BF_ECUDA, "cooperative grid of %d CTAs does not fit (%d per SM)", grid, per_sm);
     }
     const int world = h->world, rank = h->rank;
-    CUDA_OK(h->partials.ensure((size_t)2 * world * grid * sizeof(PfPartial)));
+    const size_t part_bytes = (((size_t)2 * world * grid * sizeof(PfPartial)) + 63) & ~(size_t)63;   // + ticket counter + folded stats
+    CUDA_OK(h->partials.ensure(part_bytes + 256));
     const int grid_s = (int)std::min<int64_t>(((int64_t)N + 255) / 256, (int64_t)h->nsm * 8);
     const int Ng = N * world;
     int log2n = -1, log2ng = -1;
@@ -592,7 +594,7 @@ struct PfRun {
         const size_t npad = (size_t)ntiles * PF_FUSED_TILE_CHUNKS * 128;
         if (sl.xa.ensure((size_t)N * DX * 4) || sl.xb.ensure((size_t)N * DX * 4) || sl.LL.ensure(npad * 4) || sl.E.ensure(npad * 4) ||
             sl.tilesum.ensure(((size_t)ntiles_g + 4) * 4) || sl.Etile.ensure(((size_t)ntiles_g + 4) * 4) || sl.V.ensure(((size_t)ntiles_g + 4) * 4) ||
-            sl.partials.ensure((size_t)2 * grid * sizeof(PfPartial)))
+            sl.partials.ensure(part_bytes + 256))
           return fail(BF_ENOMEM, "cudaMalloc of the scratch of concurrent trial %d failed", k);
         CUDA_OK(cudaMemsetAsync(sl.LL.p, 0, npad * 4, sl.stream));
         CUDA_OK(cudaStreamWaitEvent(sl.stream, h->ev_fork, 0));
@@ -626,7 +628,10 @@ struct PfRun {
       a.tilesum = (sl ? sl->tilesum : h->tilesum).as<float>(); a.Etile = (sl ? sl->Etile : h->Etile).as<float>();
       a.V = (sl ? sl->V : h->V).as<float>(); a.total = a.V + ntiles_g + 1;
       a.use_tau = (log2ng >= 3 && log2n >= 0) ? 1 : 0;
+      a.stage_ts = stage_ts ? 1 : 0;
       a.partials = (sl ? sl->partials : h->partials).as<PfPartial>();
+      a.fold_ctr = reinterpret_cast<unsigned int*>((sl ? sl->partials : h->partials).as<char>() + part_bytes);
+      a.fold_stats = reinterpret_cast<StepStats*>((sl ? sl->partials : h->partials).as<char>() + part_bytes + 64);
       if (world > 1) {                   // the exchanged arrays live in the IPC-mapped exchange buffer
         char* xb = h->xchg.as<char>();
         if ((size_t)2 * world * grid * sizeof(PfPartial) > h->off_ts - h->off_part) return fail(BF_EINVAL, "cooperative grid of %d CTAs exceeds the exchange buffer", grid);
@@ -661,6 +666,7 @@ struct PfRun {
       a.world = world; a.rank = rank; a.goff = rank * N; a.Ng = Ng; a.log2ng = log2ng; a.log2ns = log2n;
       a.tile_off = rank * (world > 1 ? ntiles : 0); a.ntiles_g = ntiles_g; a.phases = PF_PH_ALL;
       if (world == 1) {
+        CUDA_OK(cudaMemsetAsync(a.fold_ctr, 0, sizeof(unsigned int), s));
         void* params[] = {(void*)&h->mc, (void*)&a};
         CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NW * 32), params, smem, s));
         h->launches++;

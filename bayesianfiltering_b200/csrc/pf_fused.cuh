@@ -74,6 +74,9 @@ struct PfFusedArgs {
   // Every index that leaves the shard (resampling positions, ancestors, tiles of the summation tree, Philox
   // counters) is GLOBAL; tau and the particle state of the peers are read through IPC-mapped pointers.
   int world, rank, goff, Ng, log2ng, log2ns; // world = 1: Ng = N, goff = 0
+  unsigned int* fold_ctr;                    // ticket counter of the one-GPU statistics fold (zeroed by the host per run)
+  StepStats* fold_stats;                     // its result
+  int stage_ts;                              // C1 stages the tile sums in shared memory first (the host sized it for that)
   int tile_off, ntiles_g;                    // global index of local tile 0; tiles of the whole filter (tilesum/Etile/V are global)
   int phases;                                // PF_PH_* mask; PF_PH_ALL = the whole run in one launch (world = 1)
   // device tables [world] (in global memory: indexing a kernel parameter dynamically would spill it to local memory)
@@ -325,7 +328,8 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   float* s_win = reinterpret_cast<float*>(s_lo + TW * tpc + 2);
   float* s_xst = s_win + CW * WINCAP;                           // [CW][XCAP*DX], sharded filters only (host sizes it)
   __shared__ PfPartial s_part[CW];
-  __shared__ StepStats s_stats;
+  __shared__ __align__(16) StepStats s_stats;
+  __shared__ int s_last;                              // this CTA took the last ticket of the step (it folds the statistics)
   __shared__ int s_ctr[4];                            // chunk queues of phases A / B / C2
 
   const int N = a.N, T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -546,6 +550,54 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   auto trace = [&](int, int) {};
 #endif
 
+  // Fold the CTA partials of step t into the step's statistics (s_stats).  The order is fixed -- thread b takes
+  // partial b, b + NT, ...; then lanes, then warps -- so whoever folds gets the same bits.  All threads call it.
+  auto fold_statistics = [&](OnlineAcc<DX>& acc, int t, int pt, bool outputs_by_cta0) {
+    acc.init();
+    for (int b = tid; b < a.world * G; b += NT) {     // same order in every CTA of every rank: bit-identical stats
+      const PfPartial* p = &a.partials[(size_t)(pt & 1) * a.world * G + b];
+      float sx[DX];
+#pragma unroll
+      for (int k = 0; k < DX; ++k) sx[k] = __ldcg(&p->sx[k]);
+      acc.merge(__ldcg(&p->m), __ldcg(&p->s), __ldcg(&p->s2), sx);
+    }
+    acc.warp_reduce();
+    if (lane == 0) {
+      s_part[warp].m = acc.m; s_part[warp].s = acc.s; s_part[warp].s2 = acc.s2;
+#pragma unroll
+      for (int k = 0; k < DX; ++k) s_part[warp].sx[k] = acc.sx[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      acc.init();
+      if (lane < CW) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
+      acc.warp_reduce();
+      if (lane == 0) {
+        StepStats st;
+        st.mx = acc.m; st.Z = acc.s;
+        st.loglik = acc.m + logf(acc.s);                       // SURVEY D3: log p(y_t | y_1:t-1)
+        st.ess = acc.s * acc.s / acc.s2;                       // 1 / sum (e/Z)^2   (inference.py:1356)
+        st.flag = (st.ess < a.ess_threshold * (float)Ng) ? 1 : 0;
+        st.w_uniform = st.flag;
+        st.pad0 = st.pad1 = 0;
+#pragma unroll
+        for (int k = 0; k < BF_MAXD; ++k) st.mean[k] = (k < DX) ? acc.sx[k] / acc.s : 0.0f;
+        s_stats = st;
+        if (blockIdx.x == 0 && !all_phases) a.carry_stats[(pt + 1) & 1] = st;
+        if ((blockIdx.x == 0 || !outputs_by_cta0) && a.rank == 0) {
+          if (a.out_loglik) a.out_loglik[t] = st.loglik;
+          if (a.out_ess) a.out_ess[t] = st.ess;
+          if (a.out_resampled) a.out_resampled[t] = st.flag;
+          if (a.out_mean) {
+#pragma unroll
+            for (int k = 0; k < DX; ++k) a.out_mean[(size_t)t * DX + k] = st.mean[k];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  };
+
   // single-phase launches (sharded filter): one step per launch, t_offset is its absolute index; the state that
   // crosses launches lives in two StepStats slots, read at [pt & 1] and written (phase B) at [(pt + 1) & 1]
   if (!all_phases) {
@@ -662,6 +714,24 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
           }
           __threadfence_system();
         }
+        if (!SH && all_phases) {                     // one-GPU run: take a ticket; the last CTA out folds for everybody
+          __threadfence();
+          const unsigned tk = atomicAdd(a.fold_ctr, 1u);
+          s_last = ((tk + 1u) % (unsigned)G == 0u) ? 1 : 0;
+        }
+      }
+    }
+    if (!SH && all_phases) {
+      // Every CTA folding all G partials itself reads the same 13 KB at the same moment: measured 11 us of phase B
+      // (L2 hot spot).  The last CTA to finish phase A does it once, before the grid leaves the barrier, and the others
+      // fetch the 64-byte result.
+      __syncthreads();
+      if (s_last) {
+        fold_statistics(acc, t, pt, false);
+        if (tid == 0) {
+          *a.fold_stats = s_stats;
+          __threadfence();
+        }
       }
     }
     }  // phase A
@@ -681,47 +751,12 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       if (tid == 0) s_stats = a.carry_stats[(pt + 1) & 1];
       __syncthreads();
     } else {
-    acc.init();
-    for (int b = tid; b < a.world * G; b += NT) {     // same order in every CTA of every rank: bit-identical stats
-      const PfPartial* p = &a.partials[(size_t)(pt & 1) * a.world * G + b];
-      float sx[DX];
+    if (SH || !all_phases) fold_statistics(acc, t, pt, true);
+    else if (tid == 0) {                               // one-GPU run: the last CTA out of phase A folded them (below)
+      const int4* src = reinterpret_cast<const int4*>(a.fold_stats);
+      int4* dst = reinterpret_cast<int4*>(&s_stats);
 #pragma unroll
-      for (int k = 0; k < DX; ++k) sx[k] = __ldcg(&p->sx[k]);
-      acc.merge(__ldcg(&p->m), __ldcg(&p->s), __ldcg(&p->s2), sx);
-    }
-    acc.warp_reduce();
-    if (lane == 0) {
-      s_part[warp].m = acc.m; s_part[warp].s = acc.s; s_part[warp].s2 = acc.s2;
-#pragma unroll
-      for (int k = 0; k < DX; ++k) s_part[warp].sx[k] = acc.sx[k];
-    }
-    __syncthreads();
-    if (warp == 0) {
-      acc.init();
-      if (lane < CW) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
-      acc.warp_reduce();
-      if (lane == 0) {
-        StepStats st;
-        st.mx = acc.m; st.Z = acc.s;
-        st.loglik = acc.m + logf(acc.s);                       // SURVEY D3: log p(y_t | y_1:t-1)
-        st.ess = acc.s * acc.s / acc.s2;                       // 1 / sum (e/Z)^2   (inference.py:1356)
-        st.flag = (st.ess < a.ess_threshold * (float)Ng) ? 1 : 0;
-        st.w_uniform = st.flag;
-        st.pad0 = st.pad1 = 0;
-#pragma unroll
-        for (int k = 0; k < BF_MAXD; ++k) st.mean[k] = (k < DX) ? acc.sx[k] / acc.s : 0.0f;
-        s_stats = st;
-        if (blockIdx.x == 0 && !all_phases) a.carry_stats[(pt + 1) & 1] = st;
-        if (blockIdx.x == 0 && a.rank == 0) {
-          if (a.out_loglik) a.out_loglik[t] = st.loglik;
-          if (a.out_ess) a.out_ess[t] = st.ess;
-          if (a.out_resampled) a.out_resampled[t] = st.flag;
-          if (a.out_mean) {
-#pragma unroll
-            for (int k = 0; k < DX; ++k) a.out_mean[(size_t)t * DX + k] = st.mean[k];
-          }
-        }
-      }
+      for (int k = 0; k < (int)(sizeof(StepStats) / 16); ++k) dst[k] = __ldcg(src + k);
     }
     __syncthreads();
     }  // statistics
@@ -809,7 +844,15 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (!(a.phases & PF_PH_C)) break;
 
     // ------------------------------------------------------------------ phase C1 (CTA 0; every rank of a sharded filter)
-    if (blockIdx.x == 0) cta_exclusive_scan<CW>(a.tilesum, a.Etile, a.ntiles_g, s_win);
+    if (blockIdx.x == 0) {
+      if (a.stage_ts) {                                // all the loads in flight at once: one L2 latency instead of ten
+        for (int i = tid; i < a.ntiles_g; i += NT) s_win[i] = __ldcg(a.tilesum + i);
+        __syncthreads();
+        cta_exclusive_scan<CW>(s_win, a.Etile, a.ntiles_g, s_win + ((a.ntiles_g + 3) & ~3));
+      } else {
+        cta_exclusive_scan<CW>(a.tilesum, a.Etile, a.ntiles_g, s_win);
+      }
+    }
     trace(t, 4);
     grid.sync();
     trace(t, 5);
