@@ -203,19 +203,54 @@ __device__ __forceinline__ float chunk_tree_sum(const float v[4]) {
 //   inside a chunk (half-width 64 .. 4)     : e[1] of the lane that owns leaf m                    -> one shuffle per level
 //   inside a thread (half-width 2, 1)       : e[3], e[2] and the next thread's e[0].
 // (lo, hi) is the clamp interval the levels ABOVE the tile impose; ncap = min(TILE, N) (a power of two).
-template <int NWARPS, bool TAU>
-__device__ __forceinline__ void chunk_scan(const float v[4], int wpos, const float* s_wsum, const float* s_v0, float e_tile,
-                                           float e_next_tile, float lo, float hi, int ncap, float e[4], float tau[4]) {
-  const int lane = threadIdx.x & 31;
-  const float s01 = __fadd_rn(v[0], v[1]);
-  const float s23 = __fadd_rn(v[2], v[3]);
-  float x = __fadd_rn(s01, s23);
-  float recv[5];
+// In-chunk part: `x`/`recv` are the warp's up-sweep (chunk_upsweep), E_chunk the canonical prefix at the chunk's first
+// leaf, nxtw the prefix at the NEXT chunk's first leaf, (lo, hi) the clamp interval every level above the chunk imposes.
+__device__ __forceinline__ void chunk_upsweep(const float v[4], float& s01, float recv[5]) {
+  s01 = __fadd_rn(v[0], v[1]);
+  float x = __fadd_rn(s01, __fadd_rn(v[2], v[3]));
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     recv[j] = __shfl_xor_sync(BF_FULL, x, 1 << j);
     x = __fadd_rn(x, recv[j]);
   }
+}
+template <bool TAU>
+__device__ __forceinline__ void chunk_downsweep(const float v[4], float s01, const float recv[5], float E_chunk, float nxtw,
+                                                float lo, float hi, int ncap, float e[4], float tau[4]) {
+  const int lane = threadIdx.x & 31;
+  float E = E_chunk;
+#pragma unroll
+  for (int j = 4; j >= 0; --j)
+    if ((lane >> j) & 1) E = __fadd_rn(E, recv[j]);
+  e[0] = E;
+  e[1] = __fadd_rn(E, v[0]);
+  const float e23 = __fadd_rn(E, s01);
+  e[2] = e23;
+  e[3] = __fadd_rn(e23, v[2]);
+  if (!TAU) return;
+#pragma unroll
+  for (int sl = 16; sl >= 1; sl >>= 1) {                       // nodes spanning 2*sl lanes
+    const int midl = (lane & ~(2 * sl - 1)) + sl;
+    const float c = clampf(__shfl_sync(BF_FULL, e[1], midl), lo, hi);
+    if (2 * sl * 4 <= ncap) { if (lane < midl) hi = c; else lo = c; }
+  }
+  float nxt = __shfl_down_sync(BF_FULL, e[0], 1);              // E of the next thread's first leaf
+  if (lane == 31) nxt = nxtw;
+  const float c2 = clampf(e[3], lo, hi);                       // node (j0, j0+4), middle j0+2
+  const float c1 = clampf(e[2], lo, c2);                       // node (j0, j0+2), middle j0+1
+  const float c3 = clampf(nxt, c2, hi);                        // node (j0+2, j0+4), middle j0+3
+  tau[0] = clampf(e[1], lo, c1);
+  tau[1] = clampf(e[2], c1, c2);
+  tau[2] = clampf(e[3], c2, c3);
+  tau[3] = clampf(nxt, c3, hi);
+}
+
+template <int NWARPS, bool TAU>
+__device__ __forceinline__ void chunk_scan(const float v[4], int wpos, const float* s_wsum, const float* s_v0, float e_tile,
+                                           float e_next_tile, float lo, float hi, int ncap, float e[4], float tau[4]) {
+  const int lane = threadIdx.x & 31;
+  float s01, recv[5];
+  chunk_upsweep(v, s01, recv);
   constexpr int LW = Log2<NWARPS>::v;
   float y = (lane < NWARPS) ? s_wsum[lane] : 0.0f;
   float rw[LW > 0 ? LW : 1];
@@ -228,39 +263,57 @@ __device__ __forceinline__ void chunk_scan(const float v[4], int wpos, const flo
 #pragma unroll
   for (int j = LW - 1; j >= 0; --j)
     if ((lane >> j) & 1) ew = __fadd_rn(ew, rw[j]);
-  float E = __shfl_sync(BF_FULL, ew, wpos);
+  const float E_chunk = __shfl_sync(BF_FULL, ew, wpos);
+  float nxtw = 0.0f;
+  if (TAU) {
+    const float cw = __fadd_rn(ew, (lane < NWARPS) ? s_v0[lane] : 0.0f);     // lane l: cdf[first boundary of chunk l]
 #pragma unroll
-  for (int j = 4; j >= 0; --j)
-    if ((lane >> j) & 1) E = __fadd_rn(E, recv[j]);
-  e[0] = E;
-  e[1] = __fadd_rn(E, v[0]);
-  const float e23 = __fadd_rn(E, s01);
-  e[2] = e23;
-  e[3] = __fadd_rn(e23, v[2]);
-  if (!TAU) return;
-  const float cw = __fadd_rn(ew, (lane < NWARPS) ? s_v0[lane] : 0.0f);     // lane l: cdf[first boundary of chunk l]
+    for (int swd = NWARPS / 2; swd >= 1; swd >>= 1) {            // nodes spanning 2*swd chunks
+      const int midw = (wpos & ~(2 * swd - 1)) + swd;
+      const float c = clampf(__shfl_sync(BF_FULL, cw, midw & 31), lo, hi);
+      if (2 * swd * 128 <= ncap) { if (wpos < midw) hi = c; else lo = c; }
+    }
+    nxtw = (wpos + 1 < NWARPS) ? __shfl_sync(BF_FULL, ew, (wpos + 1) & 31) : e_next_tile;
+  }
+  chunk_downsweep<TAU>(v, s01, recv, E_chunk, nxtw, lo, hi, ncap, e, tau);
+}
+
+// The tile-level part of chunk_scan<NWARPS, true> for all NWARPS chunks of one tile, by ONE thread (phase C2 does it once
+// per tile instead of once per lane and chunk): the same additions and clamps in the same order.
+//   cE[w] = prefix at the first leaf of chunk w (cE[NWARPS] = e_next_tile), clo/chi[w] = clamp interval of chunk w.
+template <int NWARPS>
+__device__ __forceinline__ void tile_levels(const float* s_wsum, const float* s_v0, float e_tile, float e_next_tile, float lo,
+                                            float hi, int ncap, float* cE, float* clo, float* chi) {
+  constexpr int LW = Log2<NWARPS>::v;
+  float S[LW + 1][NWARPS];                  // S[j][b]: tree sum of block b of 2^j chunks
 #pragma unroll
-  for (int swd = NWARPS / 2; swd >= 1; swd >>= 1) {            // nodes spanning 2*swd chunks
-    const int midw = (wpos & ~(2 * swd - 1)) + swd;
-    const float c = clampf(__shfl_sync(BF_FULL, cw, midw & 31), lo, hi);
-    if (2 * swd * 128 <= ncap) { if (wpos < midw) hi = c; else lo = c; }
+  for (int l = 0; l < NWARPS; ++l) S[0][l] = s_wsum[l];
+#pragma unroll
+  for (int j = 1; j <= LW; ++j)
+#pragma unroll
+    for (int b = 0; b < (NWARPS >> j); ++b) S[j][b] = __fadd_rn(S[j - 1][2 * b], S[j - 1][2 * b + 1]);
+  float ew[NWARPS], cw[NWARPS];
+#pragma unroll
+  for (int l = 0; l < NWARPS; ++l) {
+    float x = e_tile;
+#pragma unroll
+    for (int j = LW - 1; j >= 0; --j)
+      if ((l >> j) & 1) x = __fadd_rn(x, S[j][(l >> j) ^ 1]);
+    ew[l] = x;
+    cw[l] = __fadd_rn(x, s_v0[l]);
   }
 #pragma unroll
-  for (int sl = 16; sl >= 1; sl >>= 1) {                       // nodes spanning 2*sl lanes
-    const int midl = (lane & ~(2 * sl - 1)) + sl;
-    const float c = clampf(__shfl_sync(BF_FULL, e[1], midl), lo, hi);
-    if (2 * sl * 4 <= ncap) { if (lane < midl) hi = c; else lo = c; }
+  for (int w = 0; w < NWARPS; ++w) {
+    float l = lo, h = hi;
+#pragma unroll
+    for (int swd = NWARPS / 2; swd >= 1; swd >>= 1) {
+      const int midw = (w & ~(2 * swd - 1)) + swd;
+      const float c = clampf(cw[midw & (NWARPS - 1)], l, h);
+      if (2 * swd * 128 <= ncap) { if (w < midw) h = c; else l = c; }
+    }
+    cE[w] = ew[w]; clo[w] = l; chi[w] = h;
   }
-  float nxt = __shfl_down_sync(BF_FULL, e[0], 1);              // E of the next thread's first leaf
-  const float nxtw = (wpos + 1 < NWARPS) ? __shfl_sync(BF_FULL, ew, (wpos + 1) & 31) : e_next_tile;
-  if (lane == 31) nxt = nxtw;
-  const float c2 = clampf(e[3], lo, hi);                       // node (j0, j0+4), middle j0+2
-  const float c1 = clampf(e[2], lo, c2);                       // node (j0, j0+2), middle j0+1
-  const float c3 = clampf(nxt, c2, hi);                        // node (j0+2, j0+4), middle j0+3
-  tau[0] = clampf(e[1], lo, c1);
-  tau[1] = clampf(e[2], c1, c2);
-  tau[2] = clampf(e[3], c2, c3);
-  tau[3] = clampf(nxt, c3, hi);
+  cE[NWARPS] = e_next_tile;
 }
 
 // The particle state is read once and written once per step and is far larger than L2: stream it (evict-first), so
@@ -859,11 +912,20 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     lap(2);
 
     // ------------------------------------------------------------------ phase C2
+    // The tile-level part of the scan and of tau (prefix and clamp interval of each chunk) is the same for all 32
+    // lanes of a chunk's warp: one thread per TILE computes it for the tile's 16 chunks (tile_levels) into the
+    // tau-window area of shared memory, idle in this phase.  Phase C2 is bound by the ALU pipe (FMNMX / FSEL / ISETP
+    // of the clamps), so this takes a fifth of its instructions away.  Very large tiles_per_cta: per-lane path.
+    const bool c2_pre = use_tau && (3 * TW + 1) * tpc <= CW * WINCAP;
+    float* s_cE = s_win;                               // [(TW+1)*tpc]
+    float* s_clo = s_cE + (TW + 1) * tpc;              // [TW*tpc]
+    float* s_chi = s_clo + TW * tpc;                   // [TW*tpc]
     if (use_tau) {
       // clamp interval of each owned tile from the bisection levels above it (half-widths N/2 .. TILE); the probe
       // value of a node whose middle is the first boundary of tile m is cdf[m*TILE] = Etile[m] + w[m*TILE]
       for (int i = tid; i < tile1 - tile0; i += NT) {
-        const int jt = (a.tile_off + tile0 + i) * TILE;          // global boundary index
+        const int tile = a.tile_off + tile0 + i;
+        const int jt = tile * TILE;                              // global boundary index
         float lo = -INFINITY, hi = INFINITY;
         if (jt < Ng) {
           for (int s = Ng >> 1; s >= TILE; s >>= 1) {
@@ -873,6 +935,9 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
           }
         }
         s_meta_f[2 * i] = lo; s_meta_f[2 * i + 1] = hi;
+        if (c2_pre)
+          tile_levels<TW>(s_wsum + i * TW, s_v0 + i * TW, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]), lo, hi, min(TILE, Ng),
+                          s_cE + i * (TW + 1), s_clo + i * TW, s_chi + i * TW);
       }
       __syncthreads();
     }
@@ -888,7 +953,13 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         float e[4], tau[4];
         const float v[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};
         float4 out;
-        if (use_tau) {
+        if (c2_pre) {
+          float s01, recv[5];
+          chunk_upsweep(v, s01, recv);
+          const float* ce = s_cE + tl * (TW + 1) + wpos;
+          chunk_downsweep<true>(v, s01, recv, ce[0], ce[1], s_clo[q], s_chi[q], min(TILE, Ng), e, tau);
+          out = make_float4(tau[0], tau[1], tau[2], tau[3]);
+        } else if (use_tau) {
           chunk_scan<TW, true>(v, wpos, s_wsum + tl * TW, s_v0 + tl * TW, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]),
                                    s_meta_f[2 * tl], s_meta_f[2 * tl + 1], min(TILE, Ng), e, tau);
           out = make_float4(tau[0], tau[1], tau[2], tau[3]);
