@@ -97,6 +97,27 @@ def test_pf_stepwise_parity(name, T, N, thr, res, path):
     eng.close()
 
 
+@pytest.mark.parametrize("name,T,N,thr,res", [
+    ("bot2", 8, 16384, 1.0, "systematic"),         # 8 tiles, 8 CTAs: the tau path (N = 2^k) across tiles and CTAs
+    ("lg42", 10, 8192, 0.6, "systematic"),         # resampling and non-resampling steps alternate
+    ("ungm", 10, 4096, 0.5, "multinomial"),        # unsorted positions: bisection of tau in global memory
+    ("bot2", 6, 6000, 1.0, "systematic"),          # several tiles, N not a power of two: literal bisection of the cdf
+    ("l63", 6, 32768, 1.0, "systematic"),
+])
+def test_pf_stepwise_parity_many_tiles(name, T, N, thr, res):
+    """The same step-wise check on filters that span several tiles of the summation tree and several CTAs of the
+    persistent kernel (the cases above fit one tile)."""
+    c = case(name)
+    _, ys = c.simulate(T, 7)
+    u = c.inputs(T)
+    x0, noise, ru = c.pf_randomness(T, N, 8, res)
+    eng = _engine(c, N, 1, thr, res, "streamed")
+    out = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=ALL_OUT)
+    n_res = _stepwise(c, out, ys, u, x0, noise, ru, thr, res)
+    assert n_res > 0
+    eng.close()
+
+
 @pytest.mark.parametrize("path", ["resident", "streamed"])
 @pytest.mark.parametrize("gold", ["pf_ungm", "pf_bot2", "pf_ungm_sys", "pf_lg3"])
 def test_pf_golden_fixtures(gold, path):
