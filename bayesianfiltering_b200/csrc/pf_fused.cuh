@@ -692,46 +692,85 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       if (!a.noise && !RNG_PER_PARTICLE)
         philox_quad_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)a.trial, (uint32_t)((a.goff + base) >> 2),
                                 reinterpret_cast<float(*)[DQ]>(z));
-      float llv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      // The four particles of a lane: their states are fetched together (four gathers in flight), then propagated two at
+      // a time in a loop that is NOT unrolled further -- the body (Philox colouring, f, log-likelihood, statistics) is
+      // ~600 instructions per particle and the phase is instruction-fetch-bound when all four copies are laid out.
+      // The second pair moves into the first pair's registers between the two turns.
+      float xs[4][DX];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (k < nv) {
-          const int i = base + k;
-          float x[DX], qn[DQ], xt[DX];
           if (SH && xs_lo >= 0) {
-            const float* xs = s_xst + ((size_t)warp * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
+            const float* xsrc = s_xst + ((size_t)warp * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
 #pragma unroll
-            for (int c = 0; c < DX; ++c) x[c] = xs[c];
-          } else if (gather) load_prev(anc[k], x_prev, xp_peers, x);
-          else load_state_cg<DX>(x_prev, (size_t)i, x);
-          if (pt > 0 && a.out_particles) store_state<DX>(a.out_particles + ((ptrdiff_t)t - 1) * N * DX, (size_t)i, x);
-          if (a.noise) {
-            const float* np_ = a.noise + (size_t)t * a.B * N * DQ + (size_t)i * DQ;
+            for (int c = 0; c < DX; ++c) xs[k][c] = xsrc[c];
+          } else if (gather) load_prev(anc[k], x_prev, xp_peers, xs[k]);
+          else load_state_cg<DX>(x_prev, (size_t)(base + k), xs[k]);
+        } else {
 #pragma unroll
-            for (int c = 0; c < DQ; ++c) qn[c] = np_[c];
-          } else {
-            if (RNG_PER_PARTICLE)
-              philox_particle_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)a.trial,
-                                          (uint32_t)((a.goff + base) >> 2), (uint32_t)k, z[0]);
-            const float* zk = z[RNG_PER_PARTICLE ? 0 : k];
-#pragma unroll
-            for (int r = 0; r < DQ; ++r) {             // q = q0 + L_Q z  (models.py:83, TFP MVN sample)
-              float s = mc.q0[r];
-#pragma unroll
-              for (int c = 0; c <= r; ++c) s += mc.LQ[r * DQ + c] * zk[c];
-              qn[r] = s;
-            }
-          }
-          M::f(x, qn, u_in, mc, xt);
-          store_state_cs<DX>(x_cur, (size_t)i, xt);
-          if (a.out_propagated) store_state<DX>(a.out_propagated + (size_t)t * N * DX, (size_t)i, xt);
-#ifdef BF_EXP_NOLL
-          const float ll = -0.5f * xt[0] * xt[0];
-#else
-          const float ll = emission_log_prob<M>(xt, y, u_in, mc);
+          for (int c = 0; c < DX; ++c) xs[k][c] = 0.0f;
+        }
+      }
+      float llv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#ifndef PF_FUSED_PU
+#define PF_FUSED_PU 2                        // particles per turn of the propagate loop
 #endif
-          llv[k] = ll;
-          acc.add(ll, w_uni ? invN : a.W[i], xt);
+      constexpr int PU = PF_FUSED_PU;
+#pragma unroll 1
+      for (int h = 0; h < 4 / PU; ++h) {
+        float lh[PU];
+#pragma unroll
+        for (int kk = 0; kk < PU; ++kk) lh[kk] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < PU; ++kk) {
+          const int k = PU * h + kk;
+          if (k < nv) {
+            const int i = base + k;
+            float qn[DQ], xt[DX];
+            const float* x = xs[kk];
+            if (pt > 0 && a.out_particles) store_state<DX>(a.out_particles + ((ptrdiff_t)t - 1) * N * DX, (size_t)i, x);
+            if (a.noise) {
+              const float* np_ = a.noise + (size_t)t * a.B * N * DQ + (size_t)i * DQ;
+#pragma unroll
+              for (int c = 0; c < DQ; ++c) qn[c] = np_[c];
+            } else {
+              if (RNG_PER_PARTICLE)
+                philox_particle_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)a.trial,
+                                            (uint32_t)((a.goff + base) >> 2), (uint32_t)k, z[0]);
+              const float* zk = z[RNG_PER_PARTICLE ? 0 : kk];
+#pragma unroll
+              for (int r = 0; r < DQ; ++r) {             // q = q0 + L_Q z  (models.py:83, TFP MVN sample)
+                float s = mc.q0[r];
+#pragma unroll
+                for (int c = 0; c <= r; ++c) s += mc.LQ[r * DQ + c] * zk[c];
+                qn[r] = s;
+              }
+            }
+            M::f(x, qn, u_in, mc, xt);
+            store_state_cs<DX>(x_cur, (size_t)i, xt);
+            if (a.out_propagated) store_state<DX>(a.out_propagated + (size_t)t * N * DX, (size_t)i, xt);
+#ifdef BF_EXP_NOLL
+            const float ll = -0.5f * xt[0] * xt[0];
+#else
+            const float ll = emission_log_prob<M>(xt, y, u_in, mc);
+#endif
+            lh[kk] = ll;
+            acc.add(ll, w_uni ? invN : a.W[i], xt);
+          }
+        }
+        // shift everything by PU particles: results in at the top, the next particles' state and noise down to slot 0
+#pragma unroll
+        for (int k = 0; k < 4 - PU; ++k) llv[k] = llv[k + PU];
+#pragma unroll
+        for (int kk = 0; kk < PU; ++kk) llv[4 - PU + kk] = lh[kk];
+#pragma unroll
+        for (int k = 0; k < 4 - PU; ++k) {
+#pragma unroll
+          for (int c = 0; c < DX; ++c) xs[k][c] = xs[k + PU][c];
+          if (!RNG_PER_PARTICLE) {
+#pragma unroll
+            for (int c = 0; c < DQ; ++c) z[RNG_PER_PARTICLE ? 0 : k][c] = z[RNG_PER_PARTICLE ? 0 : k + PU][c];
+          }
         }
       }
       *reinterpret_cast<float4*>(a.LL + base) = make_float4(llv[0], llv[1], llv[2], llv[3]);
