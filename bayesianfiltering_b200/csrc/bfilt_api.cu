@@ -524,7 +524,8 @@ struct PfRun {
     int rck = kernels_for(h->mc, BFK_FUSED, &ks);
     if (rck) return rck;
     const int DX = h->mc.dx, DQ = h->mc.dq, DY = h->mc.dy;
-    constexpr int NW = PF_FUSED_WARPS, TW = PF_FUSED_TILE_CHUNKS;
+    constexpr int TW = PF_FUSED_TILE_CHUNKS;
+    const int NW = ks.fused_warps;
     const int N = h->N, B = h->B, T = io->T;
     // three instantiations: general, sharded (carries the peer-memory code), lean (throughput configuration: the
     // optional inputs / per-particle outputs of the call are all absent, see pf_fused.cuh)

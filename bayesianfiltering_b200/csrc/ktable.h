@@ -9,6 +9,7 @@
 
 struct BfKernelSet {
   const void* fused[3];       // k_pf_fused<M, ...>: general / sharded / lean   args (ModelConst, PfFusedArgs)
+  int fused_warps;            // warps per CTA of the fused kernels of this model
   const void* resident[2];    // k_pf_resident<M, 8 / 32>                       args (ModelConst, PfResidentArgs)
   const void* gsf_cta;        // k_gsf<M>                                       args (ModelConst, GsfArgs)
   const void* gsf_warp[4];    // k_gsf_warp<M, 1 / 2 / 4 / 8>                   args (ModelConst, GsfArgs, int B)

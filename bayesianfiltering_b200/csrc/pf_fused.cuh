@@ -39,8 +39,10 @@
 namespace cg = cooperative_groups;
 
 #define PF_FUSED_TILE_CHUNKS 16             // a tile = 16 chunks = 2048 particles: the unit whose sums one CTA scans
-#define PF_FUSED_WARPS 16                   // warps per CTA
-#define PF_FUSED_CTAS_PER_SM 2              // 2 x 512 threads per SM (64 registers per thread)
+#ifndef PF_FUSED_WARPS
+#define PF_FUSED_WARPS 32                   // warps per CTA, one CTA per SM (64 registers per thread)
+#endif
+#define PF_FUSED_WARPS_LARGE 16             // states with dx > 4: 16 warps at 128 registers per thread
 #define PF_FUSED_WINCAP 512                 // floats of tau a warp stages in shared memory for one chunk of 128 slots
 #define PF_FUSED_XCAP 256                   // particles a warp of a SHARDED filter stages when a chunk's ancestors live on a peer
 

@@ -15,12 +15,15 @@ namespace {
 struct Fill {
   BfKernelSet* k;
   template <class M> int run() {
-    // large states (dx > 4) need ~128 registers per thread to keep a particle, its noise and the statistics out of
-    // local memory: one CTA per SM for them
-    constexpr int CPS = (M::DX > 4) ? 1 : PF_FUSED_CTAS_PER_SM;
-    k->fused[0] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, false, false>;
-    k->fused[1] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, true, false>;
-    k->fused[2] = (const void*)k_pf_fused<M, PF_FUSED_WARPS, CPS, false, true>;
+    // small states: ONE CTA of 32 warps per SM at 64 registers per thread.  (Two CTAs of 16 warps do not share an SM
+    // evenly -- the scheduler favours the older one, which then idles ~20 us per phase at the grid barrier while the
+    // younger one finishes with half the SM's warps.)  Large states (dx > 4) need ~128 registers per thread to keep a
+    // particle, its noise and the statistics out of local memory: one CTA of 16 warps per SM.
+    constexpr int NW = (M::DX > 4) ? PF_FUSED_WARPS_LARGE : PF_FUSED_WARPS;
+    k->fused_warps = NW;
+    k->fused[0] = (const void*)k_pf_fused<M, NW, 1, false, false>;
+    k->fused[1] = (const void*)k_pf_fused<M, NW, 1, true, false>;
+    k->fused[2] = (const void*)k_pf_fused<M, NW, 1, false, true>;
     return 0;
   }
 };
