@@ -543,7 +543,7 @@ struct PfRun {
     // shared memory depends on tiles_per_cta, which depends on the grid, which depends on shared memory: iterate
     int grid = 1, tpc = ntiles;
     size_t smem = 0;
-    const int stage_ts = (ntiles_scan <= 16384) ? ((ntiles_scan + 3) & ~3) : 0;   // tile sums staged in shared memory by C1
+    const int stage_ts = (ntiles_scan + 1 <= 16384) ? ((ntiles_scan + 3) & ~3) + 256 : 0;   // tile sums staged in shared memory by C1 (+ scratch)
     auto smem_for = [&](int t) { return (size_t)((3 * TW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, stage_ts + nchunk + 1 + NW + 8) +
                                                 (xstage ? NW * PF_FUSED_XCAP * DX : 0) + 8) * sizeof(float); };
     for (int round = 0; round < 3; ++round) {

@@ -318,6 +318,45 @@ __device__ __forceinline__ void tile_levels(const float* s_wsum, const float* s_
   cE[NWARPS] = e_next_tile;
 }
 
+// Canonical exclusive scan of n (+1 leaf for the total) values already staged in shared memory, n + 1 <= 16384:
+// warps take the 128-leaf blocks in turn (tree sums), warp 0 scans the <= 128 block sums as the leaves of the upper
+// tree, then the blocks are swept down from their prefixes.  Two barriers instead of cta_exclusive_scan's dozens; the
+// same zero-padded binary tree, so the same bits.  s_blk: 256 floats of scratch.  out[0 .. n] (global).
+template <int CW>
+__device__ __forceinline__ void staged_tile_scan(const float* s_in, float* out, int n, float* s_blk) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = (n + 1 + 127) >> 7;                 // <= 128
+  for (int b = warp; b < 128; b += CW) {
+    float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (b < nblk) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int i = b * 128 + lane * 4 + k; v[k] = (i < n) ? s_in[i] : 0.0f; }
+    }
+    const float t = chunk_tree_sum(v);
+    if (lane == 0) s_blk[b] = t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const float v[4] = {s_blk[lane * 4], s_blk[lane * 4 + 1], s_blk[lane * 4 + 2], s_blk[lane * 4 + 3]};
+    float s01, recv[5], e[4], unused[4];
+    chunk_upsweep(v, s01, recv);
+    chunk_downsweep<false>(v, s01, recv, 0.0f, 0.0f, 0.0f, 0.0f, 0, e, unused);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_blk[128 + lane * 4 + k] = e[k];
+  }
+  __syncthreads();
+  for (int b = warp; b < nblk; b += CW) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int i = b * 128 + lane * 4 + k; v[k] = (i < n) ? s_in[i] : 0.0f; }
+    float s01, recv[5], e[4], unused[4];
+    chunk_upsweep(v, s01, recv);
+    chunk_downsweep<false>(v, s01, recv, s_blk[128 + b], 0.0f, 0.0f, 0.0f, 0, e, unused);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int i = b * 128 + lane * 4 + k; if (i <= n) out[i] = e[k]; }
+  }
+}
+
 // The particle state is read once and written once per step and is far larger than L2: stream it (evict-first), so
 // that the per-particle scalars that ARE re-read within a step (log-likelihoods, weights, tau: 4 B each) stay in L2.
 template <int DX>
@@ -942,7 +981,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       if (a.stage_ts) {                                // all the loads in flight at once: one L2 latency instead of ten
         for (int i = tid; i < a.ntiles_g; i += NT) s_win[i] = __ldcg(a.tilesum + i);
         __syncthreads();
-        cta_exclusive_scan<CW>(s_win, a.Etile, a.ntiles_g, s_win + ((a.ntiles_g + 3) & ~3));
+        staged_tile_scan<CW>(s_win, a.Etile, a.ntiles_g, s_win + ((a.ntiles_g + 3) & ~3));
       } else {
         cta_exclusive_scan<CW>(a.tilesum, a.Etile, a.ntiles_g, s_win);
       }
