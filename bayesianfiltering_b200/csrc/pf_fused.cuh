@@ -419,7 +419,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   float* s_v0 = s_wsum + TW * tpc;
   float* s_meta_f = s_v0 + TW * tpc;
   int* s_lo = reinterpret_cast<int*>(s_meta_f + 2 * tpc);       // [TW*tpc + 2] tau window start of each chunk
-  float* s_win = reinterpret_cast<float*>(s_lo + TW * tpc + 2);
+  float* s_win = s_dyn + (((3 * TW + 2) * tpc + 2 + 3) & ~3);   // 16-byte aligned (vector accesses to the histogram)
   float* s_xst = s_win + CW * WINCAP;                           // [CW][XCAP*DX], sharded filters only (host sizes it)
   __shared__ PfPartial s_part[CW];
   __shared__ __align__(16) StepStats s_stats;
@@ -494,7 +494,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   bool w_uni = (a.resume || !all_phases) ? (a.carry_stats->w_uniform != 0) : (a.w_uniform0 != 0);
   bool gather = all_phases ? false : (a.carry_stats->flag != 0);
   const float* x_prev = a.x_init;
-  float res_total = 0.0f, res_u0 = 0.0f;              // of the resampling being gathered
+  float res_total = 0.0f, res_u0 = 0.0f, res_scale = 0.0f;   // of the resampling being gathered (scale = Ng / total)
   const float* const* xp_stage = nullptr;             // peers' copies of the state being gathered (sharded filter)
 
   auto position = [&](int slot, float u) -> float {
@@ -507,6 +507,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   // Once per phase that gathers: total and the systematic uniform.  ts = local step whose resampling is gathered.
   auto begin_gather = [&](int ts) {
     res_total = __ldcg(a.total);
+    res_scale = __fdiv_rn((float)Ng, res_total);
     if (a.resampler == 1)
       res_u0 = a.res_u ? a.res_u[(ptrdiff_t)ts * a.B]
                        : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, 0ull);
@@ -559,6 +560,58 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     for (int k = 0; k < 4; ++k) r[k] = position(a.goff + base + k, u[k]);
     if (use_win) {
       const int lo = s_lo[q], wn = s_lo[q + 1] - lo;             // warp-uniform
+#ifndef PF_FUSED_COUNTING
+#define PF_FUSED_COUNTING 1
+#endif
+#if PF_FUSED_COUNTING
+      if (wn <= 32 * 128) {
+        // Counting instead of searching.  Slot i's answer is lo + #{j in the window : tau_j < r_i}; positions are
+        // non-decreasing in i, so tau_j is below the positions of exactly the slots i >= k_j, k_j = first slot of the
+        // chunk whose position exceeds tau_j.  Every lane turns its share of the window (about one tau per slot) into
+        // k_j -- an estimate from the inverse of the position formula, corrected against the formula itself, so the
+        // result is exact whatever the rounding of the estimate -- and counts it in a 129-bin histogram in shared
+        // memory; a warp prefix sum of the histogram gives all 128 answers.  ~30 instructions per slot where the
+        // bounded bisections took ~75, and no staging of the window.
+        int* hist = reinterpret_cast<int*>(s_win) + warp * 160;
+        const int s0 = a.goff + cta_base + 128 * q;                 // first slot of the chunk (global)
+        *reinterpret_cast<int4*>(hist + lane * 4) = make_int4(0, 0, 0, 0);
+        if (lane == 0) hist[128] = 0;
+        __syncwarp();
+        const float fs0 = (float)s0;                    // a multiple of 128 below 2^31: exact
+        for (int j0 = 0; j0 < wn; j0 += 128) {          // four independent loads in flight per lane
+          float tv[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) { const int i = j0 + lane + 32 * m; tv[m] = (i < wn) ? tauG(lo + i) : 0.0f; }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (j0 + lane + 32 * m < wn) {
+              const float tj = tv[m];
+              // estimate: position(s, u) > tj  <=>  s > tj * Ng / total - u
+              float tr = __fsub_rn(__fsub_rn(__fmul_rn(tj, res_scale), res_u0), fs0);
+              tr = fminf(fmaxf(tr, -1.0f), 128.0f);     // (NaN -> -1)
+              int g = min((int)floorf(tr) + 1, 128);
+              while (g > 0 && position(s0 + g - 1, res_u0) > tj) --g;
+              while (g < 128 && !(position(s0 + g, res_u0) > tj)) ++g;
+              atomicAdd(hist + g, 1);
+            }
+          }
+        }
+        __syncwarp();
+        const int4 h4 = *reinterpret_cast<const int4*>(hist + lane * 4);
+        const int c0 = h4.x, c1 = c0 + h4.y, c2 = c1 + h4.z, c3 = c2 + h4.w;
+        int incl = c3;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(BF_FULL, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const int ex = lo + incl - c3;
+        anc[0] = min(ex + c0, Ng - 1); anc[1] = min(ex + c1, Ng - 1); anc[2] = min(ex + c2, Ng - 1); anc[3] = min(ex + c3, Ng - 1);
+        if (!(res_total == res_total)) {               // NaN total: every comparison of the bisection fails -> last index
+#pragma unroll
+          for (int k = 0; k < 4; ++k) anc[k] = Ng - 1;
+        }
+#else
       if (wn <= WINCAP) {
         float* win = s_win + warp * WINCAP;
         for (int i0 = 0; i0 < wn; i0 += 128) {          // four independent loads in flight per lane
@@ -579,6 +632,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
           p = lower_bound_window(win, p, pn, r[k]);
           anc[k] = min(lo + p, Ng - 1);
         }
+#endif
         // Sharded filter, ancestors (partly) on another rank: x[lo .. lo+wn] is a contiguous range -- fetch it with
         // coalesced 512-byte peer reads into shared memory instead of one 16-byte NVLink round trip per particle.
         if (SH && a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
