@@ -39,9 +39,9 @@ PF_T = int(os.environ.get("BF_BENCH_T", "1000"))
 GSF_M, GSF_B, GSF_T = 100, 1024, 500
 BYTES_PER_PARTICLE_STEP = 84     # 4*(4*dx + 5) for dx=4, in-kernel RNG, resampling step
 # DRAM bytes the fused kernel actually moves per particle-step: ncu --set full, dram__bytes_read+write of one launch /
-# (N*T) (profiles/r1_e_pf_fused_T40_ncu.txt).  Below the algorithmic figure because the resampled copy of the
+# (N*T) (profiles/r1_m_pf_fused_T40_ncu.txt).  Below the algorithmic figure because the resampled copy of the
 # particles is never materialised (the gather is fused into the next step's propagate).
-MOVED_BYTES_PER_PARTICLE_STEP = 52.8
+MOVED_BYTES_PER_PARTICLE_STEP = 52.0
 METRIC, UNIT = "particle-steps/s", "particle-steps/s"
 
 
@@ -313,7 +313,7 @@ def run_ours(args):
                              "traffic": MOVED_BYTES_PER_PARTICLE_STEP * Nloc * T, "traffic_source": "ncu capture of a T=40 launch, scaled to this T",
                              "moved_bytes_per_particle_step": MOVED_BYTES_PER_PARTICLE_STEP,
                              "peak_source": peak_src, "bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
-                             "bound_note": "this model is instruction-issue-bound (~500 SASS instructions per particle-step, issue slots 56% busy, DRAM 25% of peak)",
+                             "bound_note": "this model is instruction-issue-bound (~475 SASS instructions per particle-step, issue slots 65% busy, DRAM 32% of peak: profiles/r1_m_pf_fused_T40_ncu.txt)",
                              "kernel": "k_pf_fused (persistent cooperative kernel, all T steps in one launch)",
                              "phase_us_per_time_step": phases},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "gsf": gsf}
