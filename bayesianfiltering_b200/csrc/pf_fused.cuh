@@ -1,26 +1,26 @@
 // pf_fused.cuh -- bootstrap particle filter, large-N path: ONE persistent cooperative kernel runs all T
 // steps of gaussfiltax/inference.py:1330-1366 with the particle state streamed through HBM (sm_100a).
 //
-// Grid = every co-resident CTA of the device (cooperative launch).  A CTA owns a contiguous range of tiles
-// (2048 particles, the unit of the canonical summation tree); inside it every WARP owns a contiguous run
-// of chunks (128 particles, 4 per lane) and works through them on its own -- the same 4 particles belong to the
-// same thread in every phase, and no phase has a CTA barrier inside its loop.  A step is
+// Grid = one CTA of 32 warps per SM (cooperative launch; 16 warps at 128 registers for dx > 4).  A CTA owns a
+// contiguous range of tiles (2048 particles, the unit of the canonical summation tree); its warps take the chunks
+// (128 particles, 4 per lane) of that range round-robin, in the same order in every phase, so a run is
+// bit-reproducible; no phase has a CTA barrier inside its loop.  A step is
 //
 //   A  ancestor of slot i from the PREVIOUS step's cdf (the resampling gather is fused into the propagate:
 //      x = X[t-1][a_i], never materialised), x~ = f(x, q, u), ll = log p(y | x~), CTA partial of the online
-//      (max, sum e, sum e^2, sum e x~) accumulator                                           -- grid sync --
-//   B  every CTA folds the partials in the same fixed order -> max, Z, log-lik increment, ESS, resample
-//      flag, weighted mean (bit-identical in every CTA: the branch below is grid-uniform);
-//      w = exp(ll - max) w_prev / Z ; no resampling: store w and go to the next step WITHOUT a grid sync;
-//      resampling: canonical tree sum of each tile of w                                      -- grid sync --
+//      (max, sum e, sum e^2, sum e x~) accumulator; the LAST CTA to finish folds all partials in a fixed order ->
+//      max, Z, log-lik increment, ESS, resample flag, weighted mean (a sharded filter: every CTA of every rank folds,
+//      same order, same bits)                                                                -- grid sync --
+//   B  w = exp(ll - max) w_prev / Z ; no resampling: store w and go to the next step WITHOUT a grid sync;
+//      resampling: w -> E, canonical tree sum of each chunk and tile of w                    -- grid sync --
 //   C1 CTA 0: canonical exclusive scan of the tile sums                                      -- grid sync --
-//   C2 w again (recomputed from ll, bit-identical), canonical exclusive scan inside each tile -> E[0..N]
-//      (cdf[j] = E[j+1], lax.associative_scan order: oracle/scan.py); for power-of-two N the cdf is stored
-//      as its EFFECTIVE THRESHOLDS tau (see below)                                           -- grid sync --
+//   C2 one thread per tile: prefix and tau clamp interval of its 16 chunks; then the canonical exclusive scan
+//      inside each chunk -> E[0..N] (cdf[j] = E[j+1], lax.associative_scan order: oracle/scan.py); for
+//      power-of-two N the cdf is stored as its EFFECTIVE THRESHOLDS tau (see below)          -- grid sync --
 //
 // and after the last step one more gather materialises the carry.  HBM traffic of a resampling step with
-// in-kernel Philox noise, per particle: A read x 4DX + write x~ 4DX + write ll 4 (+ cdf probes, cached);
-// B read ll 4; C2 read ll 4 + write E 4  ->  8 DX + 16 bytes (48 B for DX = 4).
+// in-kernel Philox noise, per particle: A read x 4DX + write x~ 4DX + write ll 4 (+ tau window, cached);
+// B read ll 4 + write w 4; C2 read w 4 + write tau 4  ->  8 DX + 20 bytes (52 B for DX = 4, as measured).
 //
 // The ancestor search is jnp.searchsorted's fixed bisection (oracle/scan.py searchsorted_bisect); its probe
 // sequence is part of the contract because the tree-ordered fp32 cdf is not monotone in its last bit.  Running
@@ -28,10 +28,10 @@
 // N = 2^k, phase C2 stores tau_j = the monotone thresholds with  bisect(cdf, r) == lower_bound(tau, r)  for every
 // r (oracle/scan.py effective_thresholds_pow2: walking down the bisection tree, tau = min(v, .) under a left
 // turn and max(v, .) under a right turn of the probe value v): the same 4 bytes per particle, after which ANY
-// lower-bound search returns the reference's ancestors bit for bit.  Systematic positions are sorted and a
-// warp's chunks are consecutive, so a warp stages the next few hundred bytes of tau (starting at its previous
-// answer) in shared memory and every lane searches that window; multinomial positions bisect tau in global
-// memory.  Other N keep the literal bisection on E.
+// lower-bound search returns the reference's ancestors bit for bit.  Systematic positions are sorted: a chunk of
+// 128 slots owns a window of tau (found by one bisection per chunk boundary at the start of the phase) and its
+// answers are the running count of window entries below each slot's position (histogram + warp prefix sum, see
+// ancestors4); multinomial positions bisect tau in global memory.  Other N keep the literal bisection on E.
 #pragma once
 #include <cooperative_groups.h>
 #include "pf_kernels.cuh"
