@@ -149,20 +149,32 @@ def smoke_check():
     """One small PF run (resident path) + one small streamed PF run + one small GSF run vs the oracle."""
     from oracle import pf as opf, gsf as ogsf, scan as oscan
     from bayesianfiltering_b200.engine import ParticleFilterEngine, GaussianSumFilterEngine
+    # The PF check is step-wise (every step re-derived by the oracle from the kernel's own previous state, ancestors
+    # bit-exact): UNGM amplifies rounding (slope up to 25), so whole trajectories of two correct fp32 implementations
+    # drift apart within a few steps.
+    from tests.test_gpu_pf import _stepwise, ALL_OUT
     c = case("ungm")
-    T, N, M = 20, 1000, 16
+    T, N, M = 12, 1000, 16
     _, ys = c.simulate(T, 0)
     u = c.inputs(T)
     x0, noise, ru = c.pf_randomness(T, N, 1)
-    ref = opf.bootstrap_particle_filter(c.omodel, ys, u, x0, noise, ru, c.r0, c.R, 0.5, "multinomial")
     for path in ("resident", "streamed"):
         eng = ParticleFilterEngine(c.host_model(), N, 1, 0.5, "multinomial", path, 0, 0)
-        out = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru,
-                           outputs=("log_likelihood", "means", "resampled", "ess"))
-        assert np.array_equal(out["resampled"][0], ref["resampled"]), path
-        close(out["log_likelihood"][0], ref["loglik_inc"], rtol=1e-4, atol_scale=1e-4, what=path + " loglik")
-        close(out["means"][0], ref["means"], rtol=2e-2, atol_scale=2e-2, what=path + " means")
+        out = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=ALL_OUT)
+        assert _stepwise(c, out, ys, u, x0, noise, ru, 0.5, "multinomial") > 0, path
         eng.close()
+    # the large-N kernel in its throughput configuration (Philox noise, systematic resampling): finite, resamples every
+    # step, and bit-reproducible
+    cb = case("bot2")
+    _, yb = cb.simulate(6, 3)
+    ub = cb.inputs(6)
+    runs = []
+    for _ in range(2):
+        eng = ParticleFilterEngine(cb.host_model(), 1 << 16, 1, 1.0, "systematic", "streamed", 7, 0)
+        runs.append(eng.run_host(yb, inputs=ub, outputs=("means", "log_likelihood", "resampled")))
+        eng.close()
+    assert np.all(np.isfinite(runs[0]["log_likelihood"])) and np.all(runs[0]["resampled"] == 1)
+    assert np.array_equal(runs[0]["log_likelihood"], runs[1]["log_likelihood"]) and np.array_equal(runs[0]["means"], runs[1]["means"])
     means0 = c.gsf_means0(M, 2)
     g = ogsf.gaussian_sum_filter(c.omodel, ys, u, means0, c.P0, c.Q, c.q0, c.R, c.r0)
     eng = GaussianSumFilterEngine(c.host_model(), M, 1, 0)
