@@ -50,7 +50,7 @@ class GsfIO(C.Structure):
                 ("init_weights", C.c_void_p),
                 ("out_weights", C.c_void_p), ("out_means", C.c_void_p), ("out_covs", C.c_void_p),
                 ("out_pred_means", C.c_void_p), ("out_pred_covs", C.c_void_p), ("out_loglik", C.c_void_p),
-                ("out_mix_mean", C.c_void_p)]
+                ("out_mix_mean", C.c_void_p), ("Q_t", C.c_void_p), ("R_t", C.c_void_p)]
 
 
 # every symbol include/bfilt.h declares: (name, restype, argtypes)

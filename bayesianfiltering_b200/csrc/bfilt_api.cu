@@ -962,6 +962,7 @@ struct GsfRun {
     a.out_weights = io->out_weights; a.out_means = io->out_means; a.out_covs = io->out_covs;
     a.out_pred_means = io->out_pred_means; a.out_pred_covs = io->out_pred_covs; a.out_loglik = io->out_loglik;
     a.out_mix_mean = io->out_mix_mean;
+    a.Q_t = io->Q_t; a.R_t = io->R_t;
     // one warp per trial when the mixture fits CPL components per lane within the register budget
     // (state words per lane: CPL * (1 + dx + dx^2)); else one CTA per trial, one thread per component
     const int DXm = h->mc.dx, WORDS = 1 + DXm + DXm * DXm;
@@ -971,7 +972,8 @@ struct GsfRun {
     // a warp per trial needs enough trials to fill the machine (B warps in flight); below that, one thread per
     // component keeps more warps resident.  BF_GSF_KERNEL=cta|warp overrides (experiments).
     const char* force = getenv("BF_GSF_KERNEL");
-    const bool want_warp = force ? (strcmp(force, "warp") == 0) : (B >= 16 * h->nsm);
+    // (time-varying covariances: the CTA kernel only)
+    const bool want_warp = (io->Q_t || io->R_t) ? false : (force ? (strcmp(force, "warp") == 0) : (B >= 16 * h->nsm));
     int wk = -1;
     if (want_warp) {
       if (cpl == 1 && WORDS <= 96) wk = 0;
@@ -985,7 +987,7 @@ struct GsfRun {
     } else {
       const int threads = std::max(32, ((a.M + 31) / 32) * 32);
       void* params[] = {(void*)&h->mc, (void*)&a};
-      CUDA_OK(cudaLaunchKernel(ks.gsf_cta, dim3(B), dim3(threads), params, 0, s));
+      CUDA_OK(cudaLaunchKernel((io->Q_t || io->R_t) ? ks.gsf_cta_tv : ks.gsf_cta, dim3(B), dim3(threads), params, 0, s));
     }
     h->launches += 1;
     return BF_OK;
@@ -1014,6 +1016,7 @@ extern "C" int bf_gsf_run(bf_gsf_handle h, const bf_gsf_io* io, void* stream) {
     a.carry_w = h->carry_w.as<float>(); a.carry_m = h->carry_m.as<float>(); a.carry_P = h->carry_P.as<float>(); a.post_m = h->post_m.as<float>();
     a.out_weights = io->out_weights; a.out_means = io->out_means; a.out_covs = io->out_covs; a.out_pred_means = io->out_pred_means;
     a.out_pred_covs = io->out_pred_covs; a.out_loglik = io->out_loglik; a.out_mix_mean = io->out_mix_mean;
+    a.Q_t = io->Q_t; a.R_t = io->R_t;                   // (their off-diagonal elements are ignored on this path)
     const size_t smem = gsf_large_smem_bytes(h->dx, h->dy, a.M);
     const void* kl = bfk_gsf_large(h->dx == 40 ? 40 : 0);
     CUDA_OK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1043,6 +1046,15 @@ extern "C" int bf_gsf_run_host(bf_gsf_handle h, const bf_gsf_io* hio) {
   IN(init_means, B * M * dx)
   IN(init_covs, B * M * dx * dx)
   IN(init_weights, B * M)
+  if (h->large) {                      // the large-state path keeps diagonals only: refuse anything else here, where we can see it
+    const size_t dq = h->mc.dq, dr = h->mc.dr;
+    for (size_t t = 0; hio->Q_t && t < T; ++t) for (size_t i = 0; i < dq; ++i) for (size_t j = 0; j < dq; ++j)
+      if (i != j && hio->Q_t[(t * dq + i) * dq + j] != 0.0f) return fail(BF_ENOMODEL, "L96: Q_t must be diagonal");
+    for (size_t t = 0; hio->R_t && t < T; ++t) for (size_t i = 0; i < dr; ++i) for (size_t j = 0; j < dr; ++j)
+      if (i != j && hio->R_t[(t * dr + i) * dr + j] != 0.0f) return fail(BF_ENOMODEL, "L96: R_t must be diagonal");
+  }
+  IN(Q_t, T * h->mc.dq * h->mc.dq)
+  IN(R_t, T * h->mc.dr * h->mc.dr)
   OUT(out_weights, B * T * M) OUT(out_means, B * T * M * dx) OUT(out_covs, B * T * M * dx * dx)
   OUT(out_pred_means, B * T * M * dx) OUT(out_pred_covs, B * T * M * dx * dx) OUT(out_loglik, B * T) OUT(out_mix_mean, B * T * dx)
 #undef IN

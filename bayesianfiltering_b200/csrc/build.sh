@@ -15,7 +15,7 @@ mkdir -p "$obj"
 ONLY=${BF_ONLY:-}
 if [[ -z "$ONLY" ]]; then rm -f "$obj"/*.o "$obj"/*.log "$obj"/*.ok; fi
 
-NG_FUSED=${BF_NG_FUSED:-8}; NG_RESIDENT=${BF_NG_RESIDENT:-4}; NG_GSF=${BF_NG_GSF:-4}; NG_MISC=${BF_NG_MISC:-1}
+NG_FUSED=${BF_NG_FUSED:-8}; NG_RESIDENT=${BF_NG_RESIDENT:-4}; NG_GSF=${BF_NG_GSF:-8}; NG_MISC=${BF_NG_MISC:-1}
 JOBS=${BF_JOBS:-$(nproc)}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O2
        --expt-relaxed-constexpr "$@")

@@ -26,6 +26,7 @@ struct GsfArgs {
   float* carry_w; float* carry_m; float* carry_P;       // handle-owned carry [B,M], [B,M,DX], [B,M,DX,DX]
   float* out_weights; float* out_means; float* out_covs; float* out_pred_means; float* out_pred_covs;
   float* out_loglik; float* out_mix_mean;
+  const float* Q_t; const float* R_t;                   // [T,DQ,DQ] / [T,DY,DY] time-varying covariances or NULL (k_gsf only)
 };
 
 // C[RxC] = A[RxK] @ B[KxC]
@@ -129,7 +130,8 @@ __device__ __forceinline__ float mvn_logpdf_chol(const float* S, const float* d)
 
 // one component: `_condition_on` (inference.py:72-105).  m,P in/out; returns ll.
 template <class Mo>
-__device__ __forceinline__ float ekf_condition(float* m, float* P, const float* y, float u, const ModelConst& mc, float jitter) {
+__device__ __forceinline__ float ekf_condition(float* m, float* P, const float* y, float u, const ModelConst& mc, float jitter,
+                                               const float* Rm) {
   constexpr int DX = Mo::DX, DY = Mo::DY;
   float H[DY * DX], HP[DY * DX], S[DY * DY], Sj[DY * DY], X[DY * DX];
   Mo::Hx(m, mc.r0, u, mc, H);
@@ -139,7 +141,7 @@ __device__ __forceinline__ float ekf_condition(float* m, float* P, const float* 
   for (int i = 0; i < DY; ++i)
 #pragma unroll
     for (int j = 0; j < DY; ++j) {
-      S[i * DY + j] = mc.R[i * DY + j] + S[i * DY + j];      // H_r R H_r^T + H_x P H_x^T  (:99), H_r = I
+      S[i * DY + j] = Rm[i * DY + j] + S[i * DY + j];        // H_r R H_r^T + H_x P H_x^T  (:99), H_r = I
       Sj[i * DY + j] = S[i * DY + j] + jitter;               // psd_solve: + 1e-6 on EVERY element
     }
 #pragma unroll
@@ -214,7 +216,9 @@ __device__ __forceinline__ void store_vec(float* dst, const float* v) {
   }
 }
 
-template <class Mo>
+// TV: time-varying noise covariances (a.Q_t / a.R_t).  A separate instantiation: with the per-step reload in the one
+// kernel the constant case ran 18 % slower (BASELINE configs[1]).
+template <class Mo, bool TV>
 __global__ void k_gsf(const __grid_constant__ ModelConst mc, const __grid_constant__ GsfArgs a) {
   constexpr int DX = Mo::DX, DQ = Mo::DQ, DY = Mo::DY;
   __shared__ float s_red[32 * (1 + BF_MAXD)];
@@ -224,17 +228,27 @@ __global__ void k_gsf(const __grid_constant__ ModelConst mc, const __grid_consta
   const bool active = tid < M;
   const size_t bm = (size_t)b * M + (active ? tid : 0);
 
-  if (tid == 0) {                     // F_q Q F_q^T, F_q constant for every registered model
-    float x0[DX], Fq[DX * DQ], FQ[DX * DQ];
+  __shared__ float s_R[BF_MAXD * BF_MAXD];
+  // noise covariances of a step into shared memory: F_q Q F_q^T (F_q constant for every registered model) and R.
+  // Constant ones are set once; `_get_params` (inference.py:21, :337-340) indexes covariances with a leading T axis.
+  auto set_noise = [&](const float* Qsrc, const float* Rsrc) {       // NULL: keep
+    if (tid == 0 && Qsrc) {
+      float x0[DX], Fq[DX * DQ], Ql[DQ * DQ], FQ[DX * DQ];
 #pragma unroll
-    for (int i = 0; i < DX; ++i) x0[i] = mc.m0[i];
-    Mo::Fq(x0, mc.q0, 0.0f, mc, Fq);
-    mm<DX, DQ, DQ>(Fq, mc.Q, FQ);
-    float G[DX * DX];
-    mmt<DX, DQ, DX>(FQ, Fq, G);
+      for (int i = 0; i < DX; ++i) x0[i] = mc.m0[i];
 #pragma unroll
-    for (int i = 0; i < DX * DX; ++i) s_gqg[i] = G[i];
-  }
+      for (int i = 0; i < DQ * DQ; ++i) Ql[i] = Qsrc[i];
+      Mo::Fq(x0, mc.q0, 0.0f, mc, Fq);
+      mm<DX, DQ, DQ>(Fq, Ql, FQ);
+      float G[DX * DX];
+      mmt<DX, DQ, DX>(FQ, Fq, G);
+#pragma unroll
+      for (int i = 0; i < DX * DX; ++i) s_gqg[i] = G[i];
+    }
+    if (Rsrc)
+      for (int i = tid; i < DY * DY; i += blockDim.x) s_R[i] = Rsrc[i];
+  };
+  set_noise(mc.Q, mc.R);
   __syncthreads();
   float GQG[DX * DX];
 #pragma unroll
@@ -269,8 +283,19 @@ __global__ void k_gsf(const __grid_constant__ ModelConst mc, const __grid_consta
     for (int k = 0; k < DY; ++k) y[k] = yp[k];
     const float u = a.inputs ? a.inputs[t] : 0.0f;
     const size_t btm = ((size_t)b * T + t) * M + (active ? tid : 0);
+    if (TV && (a.Q_t || a.R_t)) {      // block-uniform; both the update and the predict of step t use index t
+      __syncthreads();
+      set_noise(a.Q_t ? a.Q_t + (size_t)t * DQ * DQ : nullptr, a.R_t ? a.R_t + (size_t)t * DY * DY : nullptr);
+      __syncthreads();
+      if (a.Q_t) {
+#pragma unroll
+        for (int i = 0; i < DX * DX; ++i) GQG[i] = s_gqg[i];
+      }
+    }
 
-    float ll = ekf_condition<Mo>(m, P, y, u, mc, jitter);
+    float ll;
+    if constexpr (TV) ll = ekf_condition<Mo>(m, P, y, u, mc, jitter, s_R);
+    else ll = ekf_condition<Mo>(m, P, y, u, mc, jitter, mc.R);
     if (!active) ll = -INFINITY;
     if (active) {
       if (a.out_means) store_vec<DX>(a.out_means + btm * DX, m);
@@ -385,7 +410,7 @@ k_gsf_warp(const __grid_constant__ ModelConst mc, const __grid_constant__ GsfArg
     float ll[CPL], mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-      ll[j] = ekf_condition<Mo>(m[j], P[j], y, u, mc, jitter);
+      ll[j] = ekf_condition<Mo>(m[j], P[j], y, u, mc, jitter, mc.R);
       if (!act[j]) ll[j] = -INFINITY;
       mx = fmaxf(mx, ll[j]);
       if (act[j]) {

@@ -40,6 +40,7 @@ struct GsfLargeArgs {
   float* post_m;                                         // [B,M,dx] scratch: posterior means of the current step
   float* out_weights; float* out_means; float* out_covs; float* out_pred_means; float* out_pred_covs;
   float* out_loglik; float* out_mix_mean;
+  const float* Q_t; const float* R_t;                    // [T,dx,dx] / [T,dy,dy] time-varying (diagonal) covariances or NULL
 };
 
 static inline size_t gsf_large_smem_bytes(int dx, int dy, int M) {
@@ -78,6 +79,8 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
   const float dt = lc.dt, onemdt = 1.0f - lc.dt;
 
   auto wrap = [&](int i) { return i < 0 ? i + dx : (i >= dx ? i - dx : i); };
+  const float* qdp = lc.qd; int qds = 1;               // diagonal of Q / R of the current step: element i at [i * stride]
+  const float* rdp = lc.rd; int rds = 1;
 
   // ---- EKF predict of the component in (mv, P): mv <- f(mv), P <- F P F^T + Q     (inference.py:51-70)
   auto predict = [&](float u) {
@@ -100,7 +103,7 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
       const int i = idx / dx, c = idx - i * dx;
       const int j2 = wrap(c - 2), j1 = wrap(c - 1), jp = wrap(c + 1);
       const float v = -fa[c] * FP[i * dx + j2] + fb[c] * FP[i * dx + j1] + onemdt * FP[i * dx + c] + fa[c] * FP[i * dx + jp];
-      const float add = cov_plus_p ? P[idx] : ((i == c) ? lc.qd[i] : 0.0f);     // this loop reads FP only, P[idx] is this lane's own
+      const float add = cov_plus_p ? P[idx] : ((i == c) ? qdp[i * qds] : 0.0f);     // this loop reads FP only, P[idx] is this lane's own
       P[idx] = v + add;
     }
     for (int i = lane; i < dx; i += 32) mv[i] = mn[i];
@@ -108,6 +111,8 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
   };
 
   for (int t = 0; t < T; ++t) {
+    if (a.Q_t) { qdp = a.Q_t + (size_t)t * dx * dx; qds = dx + 1; }       // `_get_params` (inference.py:21): step t's matrices
+    if (a.R_t) { rdp = a.R_t + (size_t)t * dy * dy; rds = dy + 1; }
     const float* y = a.emissions + ((size_t)(a.emissions_per_trial ? b : 0) * T + t) * dy;
     const float u = a.inputs ? a.inputs[t] : 0.0f;
     const size_t bt = (size_t)b * T + t;
@@ -139,7 +144,7 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
       __syncwarp();
       for (int idx = lane; idx < dy * dy; idx += 32) {           // S = H_r R H_r^T + H P H^T ; S' = S + 1e-6
         const int j = idx / dy, k = idx - j * dy;
-        const float s = ((j == k) ? lc.rd[j] : 0.0f) + X[j * dx + 2 * k] * hv[k];
+        const float s = ((j == k) ? rdp[j * rds] : 0.0f) + X[j * dx + 2 * k] * hv[k];
         S[idx] = s; Sj[idx] = s + jitter;
       }
       __syncwarp();

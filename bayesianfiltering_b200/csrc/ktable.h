@@ -11,7 +11,8 @@ struct BfKernelSet {
   const void* fused[3];       // k_pf_fused<M, ...>: general / sharded / lean   args (ModelConst, PfFusedArgs)
   int fused_warps;            // warps per CTA of the fused kernels of this model
   const void* resident[2];    // k_pf_resident<M, 8 / 32>                       args (ModelConst, PfResidentArgs)
-  const void* gsf_cta;        // k_gsf<M>                                       args (ModelConst, GsfArgs)
+  const void* gsf_cta;        // k_gsf<M, TV = false>                           args (ModelConst, GsfArgs)
+  const void* gsf_cta_tv;     // k_gsf<M, TV = true>: time-varying Q_t / R_t
   const void* gsf_warp[4];    // k_gsf_warp<M, 1 / 2 / 4 / 8>                   args (ModelConst, GsfArgs, int B)
   const void* model_eval;     // k_model_eval<M>
   const void* ssm_sample;     // k_ssm_sample<M>

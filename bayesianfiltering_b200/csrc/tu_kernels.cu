@@ -50,7 +50,8 @@ namespace {
 struct Fill {
   BfKernelSet* k;
   template <class M> int run() {
-    k->gsf_cta = (const void*)k_gsf<M>;
+    k->gsf_cta = (const void*)k_gsf<M, false>;
+    k->gsf_cta_tv = (const void*)k_gsf<M, true>;
     k->gsf_warp[0] = (const void*)k_gsf_warp<M, 1>;
     k->gsf_warp[1] = (const void*)k_gsf_warp<M, 2>;
     k->gsf_warp[2] = (const void*)k_gsf_warp<M, 4>;

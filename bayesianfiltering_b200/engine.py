@@ -272,8 +272,9 @@ class GaussianSumFilterEngine:
 
     def _in_shapes(self, T, per_trial):
         B, M, dx = self.B, self.M, self.dx
+        dq, dr = self.hm.desc.dq, self.hm.desc.dr
         return dict(emissions=((B, T, self.dy) if per_trial else (T, self.dy)), inputs=(T,), init_means=(B, M, dx),
-                    init_covs=(B, M, dx, dx), init_weights=(B, M))
+                    init_covs=(B, M, dx, dx), init_weights=(B, M), Q_t=(T, dq, dq), R_t=(T, dr, dr))
 
     def _io(self, T, per_trial, resume, ins, outs):
         io = _lib.GsfIO()
@@ -285,13 +286,16 @@ class GaussianSumFilterEngine:
         return io
 
     def run_host(self, emissions, inputs=None, init_means=None, init_covs=None, init_weights=None,
-                 outputs=("weights", "means", "covariances", "predicted_means", "predicted_covariances"), resume=False):
+                 outputs=("weights", "means", "covariances", "predicted_means", "predicted_covariances"), resume=False,
+                 Q_t=None, R_t=None):
+        """Q_t [T,dq,dq] / R_t [T,dr,dr]: time-varying noise covariances (`_get_params`, inference.py:21)."""
         em = np.asarray(emissions, dtype=np.float32)
         per_trial = em.ndim == 3
         T = em.shape[-2]
         shp = self._in_shapes(T, per_trial)
         ins = {k: _np32(v, shp[k], k) for k, v in dict(emissions=em, inputs=inputs, init_means=init_means,
-                                                        init_covs=init_covs, init_weights=init_weights).items()}
+                                                        init_covs=init_covs, init_weights=init_weights,
+                                                        Q_t=Q_t, R_t=R_t).items()}
         res, outs = {}, {}
         for name in outputs:
             if name not in GSF_OUTPUTS:
@@ -305,7 +309,7 @@ class GaussianSumFilterEngine:
 
     def run(self, emissions, inputs=None, init_means=None, init_covs=None, init_weights=None,
             outputs=("weights", "means", "covariances", "predicted_means", "predicted_covariances"), resume=False,
-            out_buffers=None):
+            out_buffers=None, Q_t=None, R_t=None):
         import torch
         dev = torch.device("cuda", self.device)
         per_trial = emissions.dim() == 3
@@ -314,7 +318,7 @@ class GaussianSumFilterEngine:
         t32 = ParticleFilterEngine._t32
         ins = {k: (None if v is None else t32(v, shp[k], k, dev))
                for k, v in dict(emissions=emissions, inputs=inputs, init_means=init_means, init_covs=init_covs,
-                                init_weights=init_weights).items()}
+                                init_weights=init_weights, Q_t=Q_t, R_t=R_t).items()}
         res, outs = {}, {}
         for name in outputs:
             if name not in GSF_OUTPUTS:

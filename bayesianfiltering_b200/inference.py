@@ -125,7 +125,7 @@ def gaussian_sum_filter(params: ParamsNLSSM, emissions, num_components: int = 1,
     with return_extras=True also a dict with 'log_likelihood_increments', 'marginal_log_likelihood',
     'mixture_mean' when those were requested in `outputs`.
     """
-    m, hm = zoo.host_model_from_params(params)
+    m, hm, Q_t, R_t = zoo.host_model_from_params(params, time_varying=True)
     B = 1 if num_trials is None else int(num_trials)
     batched = num_trials is not None
     M = int(num_components)
@@ -139,7 +139,7 @@ def gaussian_sum_filter(params: ParamsNLSSM, emissions, num_components: int = 1,
         engine = GaussianSumFilterEngine(hm, M, B, device)
     run = engine.run if _is_torch(emissions) else engine.run_host
     raw = run(emissions, inputs=inputs, init_means=init_means, init_covs=init_covariances, init_weights=init_weights,
-              outputs=tuple(outputs))
+              outputs=tuple(outputs), Q_t=Q_t, R_t=R_t)          # covariances with a leading T axis (:21, :337-340)
     fields = {k: _swap(raw[k], batched) for k in PosteriorGaussianSumFiltered._fields if k in raw}
     post = PosteriorGaussianSumFiltered(**fields)
     extras = {}

@@ -143,11 +143,23 @@ def resolve(params):
     return mf
 
 
-def host_model_from_params(params):
+def host_model_from_params(params, time_varying=False):
+    """Registry model + its host description from a ParamsNLSSM / ParamsBPF.  With time_varying=True (Gaussian-sum
+    filter) a noise covariance may carry a leading T axis (`_get_params`, inference.py:21): the description then holds
+    its first matrix and the [T,d,d] arrays come back as the third / fourth value (None when constant)."""
     m = resolve(params)
-    for name in ("dynamics_noise_covariance", "dynamics_noise_bias", "emission_noise_covariance", "emission_noise_bias"):
-        if np.asarray(getattr(params, name)).ndim > (2 if name.endswith("covariance") else 1):
-            raise NotImplementedError(f"time-varying {name} (leading T axis, inference.py:21) is not supported yet")
-    return m, m.host_model(q0=params.dynamics_noise_bias, Q=params.dynamics_noise_covariance,
-                           r0=params.emission_noise_bias, R=params.emission_noise_covariance,
-                           m0=params.initial_mean, P0=params.initial_covariance)
+    Q = np.asarray(params.dynamics_noise_covariance)
+    R = np.asarray(params.emission_noise_covariance)
+    for name in ("dynamics_noise_bias", "emission_noise_bias"):
+        if np.asarray(getattr(params, name)).ndim > 1:        # the reference never time-indexes a bias (ndim 2 != dim + 1)
+            raise NotImplementedError(f"{name} with a leading axis is not supported (the reference does not index it either)")
+    Q_t = Q if Q.ndim == 3 else None
+    R_t = R if R.ndim == 3 else None
+    if (Q_t is not None or R_t is not None) and not time_varying:
+        raise NotImplementedError("time-varying noise covariances (leading T axis, inference.py:21) are supported by "
+                                  "gaussian_sum_filter only: the reference's particle filter fetches them but samples from "
+                                  "params.* as given")
+    hm = m.host_model(q0=params.dynamics_noise_bias, Q=(Q[0] if Q_t is not None else Q),
+                      r0=params.emission_noise_bias, R=(R[0] if R_t is not None else R),
+                      m0=params.initial_mean, P0=params.initial_covariance)
+    return (m, hm, Q_t, R_t) if time_varying else (m, hm)

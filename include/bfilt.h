@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BF_ABI_VERSION 2
+#define BF_ABI_VERSION 3
 
 typedef enum bf_status {
   BF_OK = 0, BF_EINVAL = -1, BF_ECUDA = -2, BF_ENOMODEL = -3, BF_ENOMEM = -4, BF_ECOMM = -5
@@ -172,6 +172,11 @@ typedef struct bf_gsf_io {
   float* out_pred_covs;         /* [B,T,M,dx,dx]  */
   float* out_loglik;            /* [B,T]          */
   float* out_mix_mean;          /* [B,T,dx]  sum_m w_m mu_m (posterior mean of the mixture) */
+  /* time-varying noise covariances: `_get_params` (inference.py:21, :337-340) indexes a covariance that carries a
+     leading T axis by the step.  NULL = the constant matrix of the model description.  (The biases are never
+     time-indexed by the reference: `_get_params(x, 2, t)` needs ndim 3.) */
+  const float* Q_t;             /* [T,dq,dq] or NULL */
+  const float* R_t;             /* [T,dr,dr] or NULL */
 } bf_gsf_io;
 
 int bf_gsf_create(const bf_model_desc* model, const bf_gsf_config* cfg, bf_gsf_handle* out);

@@ -69,9 +69,12 @@ def gaussian_sum_filter(model, emissions, inputs, means0, P0, Q, q0, R, r0):
     keys = ("weights", "means", "covariances", "predicted_means", "predicted_covariances")
     acc = {k: [] for k in keys}
     ll = np.zeros(T, dtype=dt)
+    # `_get_params = lambda x, dim, t: x[t] if x.ndim == dim + 1 else x` (inference.py:21), called with dim = 2 for all
+    # four (:337-340): a covariance with a leading T axis is time-varying; a bias never is (1-D has ndim 1, 2-D has 2).
+    get = lambda x, t: x[t] if np.ndim(x) == 3 else x
     for t in range(T):
         u = inputs[t] if inputs is not None else 0.0
-        out = gsf_step(model, w, pm, pP, emissions[t], u, Q, q0, R, r0)
+        out = gsf_step(model, w, pm, pP, emissions[t], u, get(Q, t), q0, get(R, t), r0)
         w, pm, pP = out["weights"], out["predicted_means"], out["predicted_covariances"]
         for k in keys:
             acc[k].append(out[k])
@@ -85,14 +88,18 @@ def gaussian_sum_filter(model, emissions, inputs, means0, P0, Q, q0, R, r0):
 def kalman_filter_exact(A, H, Q, R, m0, P0, emissions):
     """Closed-form Kalman filter in float64 for f=Ax+q, h=Hx+r, in the reference's convention:
     the prior N(m0,P0) is the prediction for y_0 (update first, then predict; inference.py:345,353,367-369).
-    Returns filtered means/covs and per-step log-likelihood increments."""
+    Q and R may carry a leading T axis (time-varying).  Returns filtered means/covs and per-step log-likelihood
+    increments."""
     A, H, Q, R = (np.asarray(a, dtype=np.float64) for a in (A, H, Q, R))
+    Qs, Rs = Q, R
     m = np.asarray(m0, dtype=np.float64); P = np.asarray(P0, dtype=np.float64)
     T = emissions.shape[0]
     dy = H.shape[0]
     ms, Ps, ll = [], [], np.zeros(T)
     for t in range(T):
         y = np.asarray(emissions[t], dtype=np.float64)
+        Q = Qs[t] if Qs.ndim == 3 else Qs
+        R = Rs[t] if Rs.ndim == 3 else Rs
         S = H @ P @ H.T + R
         K = np.linalg.solve(S, H @ P).T
         e = y - H @ m

@@ -98,6 +98,80 @@ def test_gsf_single_component_on_linear_model_is_the_kalman_filter():
         assert np.all(out["weights"] == 1.0)
 
 
+def _tv(c, T, seed):
+    """Time-varying noise covariances [T,d,d]: the case's matrices scaled by a per-step factor in [0.5, 2]."""
+    rng = np.random.default_rng(seed)
+    fq = rng.uniform(0.5, 2.0, T).astype(np.float32)
+    fr = rng.uniform(0.5, 2.0, T).astype(np.float32)
+    return fq[:, None, None] * c.Q[None], fr[:, None, None] * c.R[None]
+
+
+def test_gsf_time_varying_covariances_single_component_is_the_kalman_filter():
+    """`_get_params` (inference.py:21, :337-340): a noise covariance with a leading T axis is indexed by the step.
+    GSF(M=1) on a linear-Gaussian model with time-varying Q_t, R_t equals the closed-form time-varying Kalman filter."""
+    for name in ("lg3", "lg42"):
+        c = case(name)
+        T = 30
+        _, ys = c.simulate(T, 43)
+        Qt, Rt = _tv(c, T, 44)
+        eng = _engine(c, 1)
+        out = eng.run_host(ys, init_means=c.m0[None], outputs=ALL_OUT, Q_t=Qt, R_t=Rt)
+        const = eng.run_host(ys, init_means=c.m0[None], outputs=ALL_OUT)
+        tiled = eng.run_host(ys, init_means=c.m0[None], outputs=ALL_OUT, Q_t=np.broadcast_to(c.Q, (T,) + c.Q.shape),
+                             R_t=np.broadcast_to(c.R, (T,) + c.R.shape))
+        eng.close()
+        ms, Ps, ll = ogsf.kalman_filter_exact(c.omodel.A, c.omodel.H, Qt, Rt, c.m0, c.P0, ys)
+        close(out["means"][0, :, 0], ms, rtol=2e-4, atol_scale=2e-4, what=name + " means")
+        close(out["covariances"][0, :, 0], Ps, rtol=2e-4, atol_scale=2e-4, what=name + " covs")
+        close(out["log_likelihood"][0], ll, rtol=2e-4, atol_scale=2e-4, what=name + " loglik")
+        for k in ALL_OUT:                                   # constant matrices repeated T times: the same filter, bit for bit
+            assert np.array_equal(tiled[k], const[k]), k
+
+
+@pytest.mark.parametrize("name,T,M", [("ungm", 12, 20), ("bot2", 10, 5), ("l96s", 8, 4)])
+def test_gsf_time_varying_covariances_stepwise(name, T, M):
+    """One call with Q_t / R_t over T steps against the oracle's whole run with the same per-step matrices, compared
+    step by step from the kernel's OWN carry (teacher-forced, as everywhere else)."""
+    c = case(name)
+    _, ys = c.simulate(T, 45)
+    u = c.inputs(T)
+    Qt, Rt = _tv(c, T, 46)
+    means0 = c.gsf_means0(M, 47)
+    eng = _engine(c, M)
+    out = eng.run_host(ys, inputs=u, init_means=means0, outputs=ALL_OUT, Q_t=Qt, R_t=Rt)
+    eng.close()
+    w = np.full(M, np.float32(1.0) / np.float32(M), np.float32)
+    pm, pP = means0, np.broadcast_to(c.P0, (M,) + c.P0.shape).copy()
+    f8 = lambda v: np.asarray(v, dtype=np.float64)
+    for t in range(T):
+        ut = 0.0 if u is None else u[t]
+        o = ogsf.gsf_step(c.omodel, w, pm, pP, ys[t], ut, Qt[t], c.q0, Rt[t], c.r0)
+        o8 = ogsf.gsf_step(c.omodel, f8(w), f8(pm), f8(pP), f8(ys[t]), ut, f8(Qt[t]), f8(c.q0), f8(Rt[t]), f8(c.r0))
+        for k in FIELDS:
+            close_cond(out[k][0, t], o[k], o8[k], what=f"{name} {k} t={t}")
+        w, pm, pP = out["weights"][0, t], out["predicted_means"][0, t], out["predicted_covariances"][0, t]
+
+
+def test_gsf_time_varying_covariances_through_the_reference_entry_point():
+    from bayesianfiltering_b200 import inference as gf
+    from bayesianfiltering_b200.models import ParamsNLSSM
+    c = case("lg3")
+    T = 12
+    _, ys = c.simulate(T, 48)
+    Qt, Rt = _tv(c, T, 49)
+    m = c.zmodel_fn()
+    params = ParamsNLSSM(c.m0, c.P0, m.dynamics_function, c.q0, Qt, m.emission_function, c.r0, Rt)
+    post, ex = gf.gaussian_sum_filter(params, ys, 1, init_means=c.m0[None], return_extras=True,
+                                      outputs=FIELDS + ("log_likelihood",))
+    ms, Ps, ll = ogsf.kalman_filter_exact(c.omodel.A, c.omodel.H, Qt, Rt, c.m0, c.P0, ys)
+    close(post.means[0], ms, rtol=2e-4, atol_scale=2e-4, what="means")
+    close(ex["log_likelihood_increments"], ll, rtol=2e-4, atol_scale=2e-4, what="loglik")
+    with pytest.raises(NotImplementedError):              # the particle filter: not indexed by the reference either
+        from bayesianfiltering_b200.models import ParamsBPF
+        pb = ParamsBPF(c.m0, c.P0, m.dynamics_function, c.q0, Qt, m.emission_function, c.r0, c.R, m.emission_log_prob)
+        gf.bootstrap_particle_filter(pb, ys, 64)
+
+
 def test_gsf_trial_batch_and_chunked_resume():
     c = case("ungm")
     T, M, B = 25, 100, 5

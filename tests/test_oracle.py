@@ -149,3 +149,27 @@ def test_oracle_reproduces_committed_golden(fname):
             np.testing.assert_allclose(fresh[k], g[k], rtol=1e-6, atol=1e-7, err_msg=f"{fname}:{k}")
         else:
             assert np.array_equal(fresh[k], g[k]), f"{fname}:{k}"
+
+
+def test_oracle_time_varying_covariances():
+    """`_get_params` (inference.py:21): covariances with a leading T axis are indexed by the step; constant matrices
+    repeated T times give the same filter; GSF(M=1) on a linear-Gaussian model is the time-varying Kalman filter."""
+    from oracle import gsf as ogsf
+    from tests.parity_cases import case
+    c = case("lg3")
+    T = 15
+    _, ys = c.simulate(T, 5)
+    f8 = lambda v: np.asarray(v, dtype=np.float64)
+    a = ogsf.gaussian_sum_filter(c.omodel, f8(ys), None, f8(c.m0[None]), f8(c.P0), f8(c.Q), f8(c.q0), f8(c.R), f8(c.r0))
+    b = ogsf.gaussian_sum_filter(c.omodel, f8(ys), None, f8(c.m0[None]), f8(c.P0), np.broadcast_to(f8(c.Q), (T, 3, 3)), f8(c.q0),
+                                 np.broadcast_to(f8(c.R), (T, 3, 3)), f8(c.r0))
+    for k in ("means", "covariances", "loglik_inc"):
+        assert np.array_equal(a[k], b[k]), k
+    rng = np.random.default_rng(0)
+    Qt = rng.uniform(0.5, 2.0, T)[:, None, None] * f8(c.Q)[None]
+    Rt = rng.uniform(0.5, 2.0, T)[:, None, None] * f8(c.R)[None]
+    g = ogsf.gaussian_sum_filter(c.omodel, f8(ys), None, f8(c.m0[None]), f8(c.P0), Qt, f8(c.q0), Rt, f8(c.r0))
+    ms, Ps, ll = ogsf.kalman_filter_exact(c.omodel.A, c.omodel.H, Qt, Rt, c.m0, c.P0, ys)
+    np.testing.assert_allclose(g["means"][0], ms, rtol=1e-4, atol=1e-5)      # psd_solve's 1e-6 jitter is the difference
+    np.testing.assert_allclose(g["loglik_inc"], ll, rtol=1e-4, atol=1e-5)
+    assert np.max(np.abs(g["means"][0] - a["means"][0])) > 1e-3               # and it is not the constant filter
