@@ -332,7 +332,7 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
     cudaError_t ea = sh ? h->xa.ensure_plain(xb_) : h->xa.ensure(xb_);
     if (!ea) ea = sh ? h->xb.ensure_plain(xb_) : h->xb.ensure(xb_);
     if (!ea) ea = sh ? h->E.ensure_plain(npad * 4) : h->E.ensure(npad * 4);
-    if (ea || h->LL.ensure(npad * 4) || h->tilesum.ensure((ntg + 4) * 4) || h->Etile.ensure((ntg + 4) * 4) || h->V.ensure((ntg + 4) * 4) ||
+    if (ea || h->LL.ensure(npad * 4) || h->tilesum.ensure((ntg + 4) * 4) || h->Etile.ensure(2 * (ntg + 4) * 4) || h->V.ensure((ntg + 4) * 4) ||
         (sh && (h->peer_tab.ensure(4 * 8 * sizeof(void*)) || h->barrier_buf.ensure(64)))) {
       bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the streamed scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -594,7 +594,7 @@ struct PfRun {
         if (!sl.stream) { CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
         const size_t npad = (size_t)ntiles * PF_FUSED_TILE_CHUNKS * 128;
         if (sl.xa.ensure((size_t)N * DX * 4) || sl.xb.ensure((size_t)N * DX * 4) || sl.LL.ensure(npad * 4) || sl.E.ensure(npad * 4) ||
-            sl.tilesum.ensure(((size_t)ntiles_g + 4) * 4) || sl.Etile.ensure(((size_t)ntiles_g + 4) * 4) || sl.V.ensure(((size_t)ntiles_g + 4) * 4) ||
+            sl.tilesum.ensure(((size_t)ntiles_g + 4) * 4) || sl.Etile.ensure(2 * ((size_t)ntiles_g + 4) * 4) || sl.V.ensure(((size_t)ntiles_g + 4) * 4) ||
             sl.partials.ensure(part_bytes + 256))
           return fail(BF_ENOMEM, "cudaMalloc of the scratch of concurrent trial %d failed", k);
         CUDA_OK(cudaMemsetAsync(sl.LL.p, 0, npad * 4, sl.stream));
@@ -629,6 +629,14 @@ struct PfRun {
       a.tilesum = (sl ? sl->tilesum : h->tilesum).as<float>(); a.Etile = (sl ? sl->Etile : h->Etile).as<float>();
       a.V = (sl ? sl->V : h->V).as<float>(); a.total = a.V + ntiles_g + 1;
       a.use_tau = (log2ng >= 3 && log2n >= 0) ? 1 : 0;
+      {   // two-level search for unsorted positions: needs whole tiles and the table in the tau-window area
+        constexpr int FT = PF_FUSED_TILE_CHUNKS * 128;
+        const bool coarse = world == 1 && a.use_tau && h->cfg.resampler == BF_RESAMPLE_MULTINOMIAL && N >= 2 * FT &&
+                            N / FT <= NW * PF_FUSED_WINCAP;
+        a.coarse_log2 = -1;
+        if (coarse) { a.coarse_log2 = 0; while ((FT << a.coarse_log2) < N) ++a.coarse_log2; }
+        a.tau_tile = a.Etile + ntiles_g + 4;
+      }
       a.stage_ts = stage_ts ? 1 : 0;
       a.partials = (sl ? sl->partials : h->partials).as<PfPartial>();
       a.fold_ctr = reinterpret_cast<unsigned int*>((sl ? sl->partials : h->partials).as<char>() + part_bytes);

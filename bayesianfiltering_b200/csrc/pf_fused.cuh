@@ -78,6 +78,8 @@ struct PfFusedArgs {
   int world, rank, goff, Ng, log2ng, log2ns; // world = 1: Ng = N, goff = 0
   unsigned int* fold_ctr;                    // ticket counter of the one-GPU statistics fold (zeroed by the host per run)
   StepStats* fold_stats;                     // its result
+  float* tau_tile;                           // [N / 2048] last tau of each tile (one GPU, multinomial: two-level search)
+  int coarse_log2;                           // log2 of its length, or -1: off
   int stage_ts;                              // C1 stages the tile sums in shared memory first (the host sized it for that)
   int tile_off, ntiles_g;                    // global index of local tile 0; tiles of the whole filter (tilesum/Etile/V are global)
   int phases;                                // PF_PH_* mask; PF_PH_ALL = the whole run in one launch (world = 1)
@@ -166,6 +168,41 @@ __device__ __forceinline__ void bisect4_left_exclusive_pow2(const float* ex, int
   anc[1] = (int)min(low1 + ((r[1] <= v1) ? 0u : 1u), nm1);
   anc[2] = (int)min(low2 + ((r[2] <= v2) ? 0u : 1u), nm1);
   anc[3] = (int)min(low3 + ((r[3] <= v3) ? 0u : 1u), nm1);
+}
+
+// Unsorted (multinomial) positions on one GPU: two-level lower bound.  `s_last[k]` (shared memory) = the last tau of tile
+// k, so the tile of the answer is found without touching global memory, and only the 11 levels inside that tile
+// (2048 entries) are dependent global loads -- instead of log2(N) = 24.  tau is monotone, so any search order returns
+// the reference's ancestor; the comparisons keep the bisection's form ("go right unless r <= v"), NaN included.
+__device__ __forceinline__ void lower_bound4_two_level(const float* s_last, int log2nt, const float* tau, const float r[4],
+                                                       int nm1, int anc[4]) {
+  unsigned k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+  for (unsigned s = 1u << (log2nt - 1); s != 0; s >>= 1) {
+    const float v0 = s_last[k0 + s], v1 = s_last[k1 + s], v2 = s_last[k2 + s], v3 = s_last[k3 + s];
+    if (!(r[0] <= v0)) k0 += s;
+    if (!(r[1] <= v1)) k1 += s;
+    if (!(r[2] <= v2)) k2 += s;
+    if (!(r[3] <= v3)) k3 += s;
+  }
+  k0 += (r[0] <= s_last[k0]) ? 0u : 1u; k1 += (r[1] <= s_last[k1]) ? 0u : 1u;
+  k2 += (r[2] <= s_last[k2]) ? 0u : 1u; k3 += (r[3] <= s_last[k3]) ? 0u : 1u;
+  const unsigned nt = 1u << log2nt;
+  constexpr unsigned TILE = PF_FUSED_TILE_CHUNKS * 128;
+  // a position above every tile's last threshold: the in-tile search runs on the last tile and the clamp gives N - 1
+  const float* t0 = tau + (size_t)min(k0, nt - 1) * TILE; const float* t1 = tau + (size_t)min(k1, nt - 1) * TILE;
+  const float* t2 = tau + (size_t)min(k2, nt - 1) * TILE; const float* t3 = tau + (size_t)min(k3, nt - 1) * TILE;
+  unsigned l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+  for (unsigned s = TILE / 2; s != 0; s >>= 1) {
+    const float v0 = t0[l0 + s], v1 = t1[l1 + s], v2 = t2[l2 + s], v3 = t3[l3 + s];
+    if (!(r[0] <= v0)) l0 += s;
+    if (!(r[1] <= v1)) l1 += s;
+    if (!(r[2] <= v2)) l2 += s;
+    if (!(r[3] <= v3)) l3 += s;
+  }
+  l0 += (r[0] <= t0[l0]) ? 0u : 1u; l1 += (r[1] <= t1[l1]) ? 0u : 1u;
+  l2 += (r[2] <= t2[l2]) ? 0u : 1u; l3 += (r[3] <= t3[l3]) ? 0u : 1u;
+  anc[0] = min((int)(min(k0, nt - 1) * TILE + l0), nm1); anc[1] = min((int)(min(k1, nt - 1) * TILE + l1), nm1);
+  anc[2] = min((int)(min(k2, nt - 1) * TILE + l2), nm1); anc[3] = min((int)(min(k3, nt - 1) * TILE + l3), nm1);
 }
 
 // fixed bisection / lower bound of ONE query on the monotone thresholds tau[0..2^log2n); result in [0, n]
@@ -511,6 +548,10 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (a.resampler == 1)
       res_u0 = a.res_u ? a.res_u[(ptrdiff_t)ts * a.B]
                        : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, 0ull);
+    if (!SH && !use_win && use_tau && a.coarse_log2 >= 0) {        // the tiles' last thresholds into shared memory
+      for (int k = tid; k < (1 << a.coarse_log2); k += NT) s_win[k] = __ldcg(a.tau_tile + k);
+      __syncthreads();
+    }
     if (!use_win) return;
     // Sorted positions: every answer of chunk q lies in [lower_bound(first slot of q), lower_bound(first slot of q+1)].
     // One bisection per chunk, all of them in flight together (one latency per step instead of one per chunk).
@@ -664,7 +705,8 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     }
     if (nv <= 0) return;
     if (use_tau) {
-      if (!SH) bisect4_left_exclusive_pow2(a.E - 1, a.log2ng, r, anc);       // ex[j+1] == tau[j]
+      if (!SH && a.coarse_log2 >= 0) lower_bound4_two_level(s_win, a.coarse_log2, a.E, r, Ng - 1, anc);
+      else if (!SH) bisect4_left_exclusive_pow2(a.E - 1, a.log2ng, r, anc);       // ex[j+1] == tau[j]
       else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) anc[k] = min(lb_global(r[k]), Ng - 1);
@@ -1104,6 +1146,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #pragma unroll
         for (int k = 0; k < 4; ++k) if (base + k == N) *a.total = e[k];          // E[N], the canonical total
         if (!use_tau || base < N) *reinterpret_cast<float4*>(a.E + base) = out;
+        if (!SH && a.coarse_log2 >= 0 && wpos == TW - 1 && lane == 31 && base < N) a.tau_tile[tile] = tau[3];
       }
     }
     if (SH && blockIdx.x == 0 && tid == 0) *a.total = __ldcg(&a.Etile[a.ntiles_g - 1]);   // E[Ng]

@@ -103,6 +103,7 @@ def test_pf_stepwise_parity(name, T, N, thr, res, path):
     ("ungm", 10, 4096, 0.5, "multinomial"),        # unsorted positions: bisection of tau in global memory
     ("bot2", 6, 6000, 1.0, "systematic"),          # several tiles, N not a power of two: literal bisection of the cdf
     ("l63", 6, 32768, 1.0, "systematic"),
+    ("bot2", 6, 32768, 1.0, "multinomial"),        # 16 tiles: two-level search (tile table in shared memory, then in-tile)
 ])
 def test_pf_stepwise_parity_many_tiles(name, T, N, thr, res):
     """The same step-wise check on filters that span several tiles of the summation tree and several CTAs of the
