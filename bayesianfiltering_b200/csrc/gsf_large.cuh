@@ -165,11 +165,15 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
         const float piv = Sj[k * dy + k];
         for (int r = k + 1 + lane; r < dy; r += 32) lr[r] = Sj[r * dy + k] / piv;
         __syncwarp();
-        const int nr = dy - k - 1, ncs = dy - k - 1;
-        for (int idx = lane; idx < nr * (ncs + dx); idx += 32) {
-          const int r = k + 1 + idx / (ncs + dx), cc = idx % (ncs + dx);
-          if (cc < ncs) Sj[r * dy + k + 1 + cc] -= lr[r] * Sj[k * dy + k + 1 + cc];
-          else X[r * dx + (cc - ncs)] -= lr[r] * X[k * dx + (cc - ncs)];
+        // rank-1 update of the trailing block of S' and of all of X: a lane owns COLUMNS of the concatenation
+        // [S'(:, k+1:) | X] and walks down the rows -- no index division in the loop (it was 38 % of the kernel's
+        // instructions when the block was flattened over (row, column)), the pivot-row element stays in a register
+        const int ncs = dy - k - 1;
+        for (int cc = lane; cc < ncs + dx; cc += 32) {
+          float* col = (cc < ncs) ? (Sj + k + 1 + cc) : (X + (cc - ncs));
+          const int stride = (cc < ncs) ? dy : dx;
+          const float top = col[k * stride];
+          for (int r = k + 1; r < dy; ++r) col[r * stride] -= lr[r] * top;
         }
         __syncwarp();
       }
@@ -253,17 +257,16 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
       __syncwarp();
       // log N(y; h(m), S): Cholesky of the un-jittered S (TFP), column by column, in Sj
       float logdet = 0.0f;
-      for (int j = 0; j < dy; ++j) {
-        float s = S[j * dy + j];
-        for (int k = 0; k < j; ++k) s -= Sj[j * dy + k] * Sj[j * dy + k];
-        const float ljj = sqrtf(s);
-        logdet += logf(ljj);
-        __syncwarp();
-        for (int i = j + lane; i < dy; i += 32) {
-          float v = S[i * dy + j];
+      for (int j = 0; j < dy; ++j) {                             // dy <= 32: lane l owns row j + l of column j
+        const int i = j + lane;
+        float v = 0.0f;
+        if (i < dy) {
+          v = S[i * dy + j];
           for (int k = 0; k < j; ++k) v -= Sj[i * dy + k] * Sj[j * dy + k];
-          Sj[i * dy + j] = (i == j) ? ljj : v / ljj;
         }
+        const float ljj = sqrtf(__shfl_sync(BF_FULL, v, 0));     // lane 0 holds the diagonal element
+        logdet += logf(ljj);
+        if (i < dy) Sj[i * dy + j] = (i == j) ? ljj : v / ljj;
         __syncwarp();
       }
       float ss = 0.0f;
