@@ -323,6 +323,22 @@ def test_tiny_particle_counts(N):
         eng.close()
 
 
+@pytest.mark.parametrize("N", [8, 16, 64, 128, 256, 2048, 4096])
+@pytest.mark.parametrize("res", ["systematic", "multinomial"])
+def test_small_power_of_two_counts_on_the_large_n_kernel(N, res):
+    """Power-of-two N takes the tau path of the large-N kernel (counting search for systematic positions, two-level
+    search for multinomial ones from two tiles up): partially filled chunks and tiles, one tile exactly, two tiles."""
+    c = case("bot2")
+    T = 6
+    _, ys = c.simulate(T, 1)
+    u = c.inputs(T)
+    x0, noise, ru = c.pf_randomness(T, N, 2, res)
+    eng = _engine(c, N, 1, 1.0, res, "streamed")
+    out = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=ALL_OUT)
+    assert _stepwise(c, out, ys, u, x0, noise, ru, 1.0, res) == T
+    eng.close()
+
+
 def test_errors_are_loud():
     from bayesianfiltering_b200.engine import ParticleFilterEngine
     c = case("ungm")
