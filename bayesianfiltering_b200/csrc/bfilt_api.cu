@@ -269,7 +269,7 @@ struct bf_pf_s {
   void* peer_ptr[4][8] = {};          // imported tau / xa / xb / exchange buffer of every rank (own entries = own buffers)
   DevBuf peer_tab, barrier_buf;       // device tables [4][8] of the pointers above; 1 float for the step barrier
   DevBuf xchg;                        // exchange buffer: flags [3][8] u64 | epoch | err | partials | tilesum | V  (pf_fused.cuh)
-  size_t off_part = 0, off_ts = 0, off_V = 0, off_tt = 0;
+  size_t off_part = 0, off_ts = 0, off_V = 0;
   // the T x (4 launches + 4 collectives) of a sharded run, captured once per distinct call and replayed
   cudaStream_t gstream = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t gexec = nullptr; size_t gkey = 0; int64_t glaunches = 0;
@@ -345,8 +345,7 @@ extern "C" int bf_pf_create(const bf_model_desc* model, const bf_pf_config* cfg,
       h->off_part = 512;
       h->off_ts = h->off_part + (((size_t)2 * 8 * gmax * sizeof(PfPartial) + 255) & ~(size_t)255);
       h->off_V = h->off_ts + (((ntg + 4) * 4 + 255) & ~(size_t)255);
-      h->off_tt = h->off_V + (((ntg + 4) * 4 + 255) & ~(size_t)255);
-      const size_t xbytes = h->off_tt + (((ntg + 4) * 4 + 255) & ~(size_t)255);
+      const size_t xbytes = h->off_V + (((ntg + 4) * 4 + 255) & ~(size_t)255);
       if (h->xchg.ensure_plain(xbytes)) { bf_pf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc of the exchange buffer failed"); }
       cudaMemset(h->xchg.p, 0, xbytes);
     }
@@ -648,7 +647,7 @@ struct PfRun {
         a.partials = reinterpret_cast<PfPartial*>(xb + h->off_part);
         a.tilesum = reinterpret_cast<float*>(xb + h->off_ts);
         a.V = reinterpret_cast<float*>(xb + h->off_V); a.total = h->V.as<float>();
-        a.off_part = (int)h->off_part; a.off_ts = (int)h->off_ts; a.off_V = (int)h->off_V; a.off_tt = (int)h->off_tt;
+        a.off_part = (int)h->off_part; a.off_ts = (int)h->off_ts; a.off_V = (int)h->off_V;
         a.xchg_peers = reinterpret_cast<char* const*>(h->peer_tab.as<char*>() + 24);
         a.flags = reinterpret_cast<unsigned long long*>(xb);
         a.epoch = reinterpret_cast<unsigned long long*>(xb + 256);
@@ -690,13 +689,6 @@ struct PfRun {
       if (!(smode && strcmp(smode, "nccl") == 0)) {
         // one persistent kernel for the whole run; the ranks meet through peer-memory stores and flags inside it
         a.p2p = 1;
-        {   // two-level window search: the table of all tiles' last thresholds must fit behind the histograms
-          const int ntv = world * ntiles;
-          if (a.use_tau && h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC && ntv <= NW * (PF_FUSED_WINCAP - 160)) {
-            a.coarse_log2 = 0;
-            while ((1 << a.coarse_log2) < ntv) ++a.coarse_log2;
-          }
-        }
         void* params[] = {(void*)&h->mc, (void*)&a};
         CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NW * 32), params, smem, s));
         h->launches++;

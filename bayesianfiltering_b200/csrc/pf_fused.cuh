@@ -90,7 +90,6 @@ struct PfFusedArgs {
   // [flags 3 x 8 u64 | epoch | err | partials | tilesum | V]; a rank STORES its contribution straight into every peer's
   // buffer over NVLink and raises a sequence-numbered flag there; the readers spin on their own (local) flags.
   int p2p, off_part, off_ts, off_V;          // byte offsets of partials / tilesum / V inside an exchange buffer
-  int off_tt;                                // ... and of the last tau of every tile of the whole filter (coarse_log2 >= 0)
   int xstage;                                // stage remote ancestor ranges in shared memory (needs the extra dynamic shared memory)
   char* const* xchg_peers;                   // device table [world] of the exchange buffers (own entry = own buffer)
   unsigned long long* flags;                 // own flags [3][8]
@@ -554,16 +553,6 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       __syncthreads();
     }
     if (!use_win) return;
-    // Sharded filter: the last tau of every tile of every rank was stored into this rank's exchange buffer by its owner
-    // (phase C2).  With that table in shared memory the tile of a chunk's window is found locally and only the 11 levels
-    // inside one tile are NVLink round trips (~2.5 us each) -- not all log2(N) levels of the bisection.
-    float* s_tt = s_win + CW * 160;                    // behind the histograms of the counting search
-    const bool two_level = SH && a.coarse_log2 >= 0;
-    if (two_level) {
-      const float* tt = reinterpret_cast<const float*>(a.xchg_peers[a.rank] + a.off_tt);
-      for (int k = tid; k < (1 << a.coarse_log2); k += NT) s_tt[k] = __ldcg(tt + k);
-      __syncthreads();
-    }
     // Sorted positions: every answer of chunk q lies in [lower_bound(first slot of q), lower_bound(first slot of q+1)].
     // One bisection per chunk, all of them in flight together (one latency per step instead of one per chunk).
     for (int q = tid; q <= nchunk_valid; q += NT) {
@@ -572,14 +561,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       if (nchunk_valid > 0) {
         const float r = position(slot, res_u0);
         if (!SH) lb = lower_bound_tau_pow2(a.E, a.log2ng, r);
-        else if (two_level) {
-          const int kt = min(lower_bound_tau_pow2(s_tt, a.coarse_log2, r), (1 << a.coarse_log2) - 1);
-          const unsigned j0 = (unsigned)kt * TILE;
-          unsigned low = 0;
-          for (unsigned sft = TILE / 2; sft != 0; sft >>= 1)
-            if (!(r <= tauG((int)(j0 + low + sft)))) low += sft;
-          lb = (int)(j0 + low + ((r <= tauG((int)(j0 + low))) ? 0u : 1u));
-        } else {                                      // same bisection over the ranks' shards (peer loads)
+        else {                                        // same bisection over the ranks' shards (peer loads)
           unsigned low = 0;
           for (unsigned sft = 1u << (a.log2ng - 1); sft != 0; sft >>= 1)
             if (!(r <= tauG((int)(low + sft)))) low += sft;
@@ -1165,16 +1147,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         for (int k = 0; k < 4; ++k) if (base + k == N) *a.total = e[k];          // E[N], the canonical total
         if (!use_tau || base < N) *reinterpret_cast<float4*>(a.E + base) = out;
         if (!SH && a.coarse_log2 >= 0 && wpos == TW - 1 && lane == 31 && base < N) a.tau_tile[tile] = tau[3];
-        if (SH && a.coarse_log2 >= 0 && wpos == TW - 1 && lane == 31) reinterpret_cast<float*>(s_lo)[tl] = tau[3];   // (s_lo: phase A's)
       }
-    }
-    if (SH && a.coarse_log2 >= 0) {      // the last tau of every owned tile to every rank (this one included), one fence per thread
-      __syncthreads();
-      for (int i = tid; i < tile1 - tile0; i += NT) {
-        const float v = reinterpret_cast<const float*>(s_lo)[i];
-        for (int r = 0; r < a.world; ++r) reinterpret_cast<float*>(a.xchg_peers[r] + a.off_tt)[a.tile_off + tile0 + i] = v;
-      }
-      __threadfence_system();
     }
     if (SH && blockIdx.x == 0 && tid == 0) *a.total = __ldcg(&a.Etile[a.ntiles_g - 1]);   // E[Ng]
     trace(t, 6);
