@@ -173,3 +173,47 @@ def test_oracle_time_varying_covariances():
     np.testing.assert_allclose(g["means"][0], ms, rtol=1e-4, atol=1e-5)      # psd_solve's 1e-6 jitter is the difference
     np.testing.assert_allclose(g["loglik_inc"], ll, rtol=1e-4, atol=1e-5)
     assert np.max(np.abs(g["means"][0] - a["means"][0])) > 1e-3               # and it is not the constant filter
+
+
+def test_unscented_oracle_sigma_points_and_linear_exactness():
+    """oracle/ugsf.py (oracle first): the sigma points reproduce (m, P); on a linear-Gaussian model
+    the unscented transform is exact, so UGSF(M=1) is the Kalman filter -- for ParamsUKF(1, 0, 0) (the setting of
+    BOT_Experiment_script.py:108) and, in float64, for the default alpha = 1e-3 whose weights are ~1e6."""
+    from oracle import gsf as ogsf, ugsf as ou
+    from tests.parity_cases import case
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((3, 5, 5))
+    P = A @ np.swapaxes(A, 1, 2) + 0.1 * np.eye(5)
+    m = rng.standard_normal((3, 5))
+    for lam in (0.0, 1.5, -4.99):
+        sp = ou.get_sigma_points(m, P, lam)
+        assert sp.shape == (3, 10, 5)
+        np.testing.assert_allclose(sp.mean(axis=1), m, atol=1e-10)
+        d = sp - m[:, None, :]
+        np.testing.assert_allclose(np.einsum('mij,mik->mjk', d, d) / (2 * (5 + lam)), P, rtol=1e-9, atol=1e-10)
+    root = ou.sym_sqrtm(P)
+    np.testing.assert_allclose(root @ root, P, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(root, np.swapaxes(root, 1, 2), atol=1e-12)
+    for name in ("lg3", "lg42"):
+        c = case(name)
+        T = 25
+        _, ys = c.simulate(T, 7)
+        f8 = lambda v: np.asarray(v, dtype=np.float64)
+        ms, Ps, ll = ogsf.kalman_filter_exact(c.omodel.A, c.omodel.H, c.Q, c.R, c.m0, c.P0, ys)
+        for up in (ou.ParamsUKF(1.0, 0.0, 0.0), ou.ParamsUKF()):
+            g = ou.unscented_gaussian_sum_filter(c.omodel, f8(ys), None, f8(c.m0[None]), f8(c.P0), f8(c.Q), f8(c.q0), f8(c.R),
+                                                 f8(c.r0), up)
+            # psd_solve's 1e-6 jitter (utils.py:258) is the only difference from the closed form
+            np.testing.assert_allclose(g["means"][0], ms, rtol=2e-4, atol=2e-5, err_msg=f"{name} {up}")
+            np.testing.assert_allclose(g["covariances"][0], Ps, rtol=2e-4, atol=2e-5, err_msg=f"{name} {up}")
+            np.testing.assert_allclose(g["loglik_inc"], ll, rtol=2e-4, atol=2e-5, err_msg=f"{name} {up}")
+            assert np.all(g["weights"] == 1.0)
+    # a nonlinear model, several components: finite, normalised weights, symmetric covariances
+    c = case("ungm")
+    T, M = 15, 6
+    _, ys = c.simulate(T, 8)
+    g = ou.unscented_gaussian_sum_filter(c.omodel, ys.astype(np.float64), c.inputs(T), c.gsf_means0(M, 9).astype(np.float64),
+                                         c.P0.astype(np.float64), c.Q.astype(np.float64), c.q0.astype(np.float64),
+                                         c.R.astype(np.float64), c.r0.astype(np.float64), ou.ParamsUKF(1.0, 0.0, 0.0))
+    assert np.all(np.isfinite(g["means"])) and np.all(np.isfinite(g["loglik_inc"]))
+    np.testing.assert_allclose(g["weights"].sum(axis=0), 1.0, rtol=1e-12)
