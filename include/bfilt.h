@@ -69,7 +69,7 @@ typedef struct bf_pf_config {
   float ess_threshold;       /* resample when 1/sum(w^2) < ess_threshold*N  (inference.py:1356) */
   int32_t resampler;         /* bf_resampler                                                   */
   int32_t path;              /* bf_pf_path: RESIDENT = one CTA per trial, state in shared memory;
-                                STREAMED = multi-kernel pipeline over HBM                      */
+                                STREAMED = one persistent cooperative kernel, state in HBM      */
   uint64_t seed;             /* Philox key for every random input that is not supplied          */
   int32_t device;            /* CUDA device ordinal                                             */
   int32_t reserved;
