@@ -78,3 +78,27 @@ def test_time_varying_params_are_rejected_loudly():
                            m.emission_function, np.zeros(1), np.eye(1))
     with pytest.raises(NotImplementedError):
         zoo.host_model_from_params(p)
+
+
+def test_time_varying_covariances_are_routed_like_get_params():
+    """`_get_params` (inference.py:21): a covariance with a leading T axis is per-step; the description handed to the
+    library holds its first matrix, the [T,d,d] arrays travel separately; biases are never time-indexed; the particle
+    filter entry point refuses (the reference fetches the per-step matrices there and then does not use them)."""
+    import numpy as np
+    from bayesianfiltering_b200 import zoo
+    from tests.parity_cases import case
+    c = case("lg3")
+    T = 7
+    p = c.params_nlssm()
+    Qt = np.stack([(1.0 + t) * c.Q for t in range(T)])
+    Rt = np.stack([(2.0 + t) * c.R for t in range(T)])
+    m, hm, q, r = zoo.host_model_from_params(p._replace(dynamics_noise_covariance=Qt, emission_noise_covariance=Rt), time_varying=True)
+    assert q.shape == (T, 3, 3) and r.shape == (T, 3, 3)
+    assert np.allclose(np.ctypeslib.as_array(hm.desc.Q, (9,)).reshape(3, 3), Qt[0])
+    assert np.allclose(np.ctypeslib.as_array(hm.desc.R, (9,)).reshape(3, 3), Rt[0])
+    m, hm, q, r = zoo.host_model_from_params(p, time_varying=True)
+    assert q is None and r is None
+    with pytest.raises(NotImplementedError):
+        zoo.host_model_from_params(p._replace(dynamics_noise_covariance=Qt))
+    with pytest.raises(NotImplementedError):
+        zoo.host_model_from_params(p._replace(dynamics_noise_bias=np.zeros((T, 3), np.float32)), time_varying=True)
