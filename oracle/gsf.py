@@ -43,6 +43,12 @@ def condition_on(model, m, P, R, r0, u, y):
     return ll, mp, Pp
 
 
+def kalman_step(model, m, P, Q, q0, R, r0, u, y):
+    """vmapped `_kalman_step` (inference.py:107-120): predict from (m, P), then condition the prediction on y."""
+    pm, pP = predict(model, m, P, Q, q0, u)
+    return condition_on(model, pm, pP, R, r0, u, y)
+
+
 def gsf_step(model, w, pm, pP, y, u, Q, q0, R, r0):
     """One `_step` (inference.py:333-365): update on the carried prediction, reweight, then predict."""
     dt = pm.dtype

@@ -95,3 +95,111 @@ def ekf_run(model, ys, Q, R, m0, P0):
         m, P, l = _ekf_step(model, m, P, ys[t], Q, R, False)
         ll[t] = l[0]; ms.append(m[0]); Ps.append(P[0])
     return ll, np.stack(ms), np.stack(Ps)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# gaussfilt.py moment approximations beyond the EKF (UKF :133-170, MCF :173-198) and the filters built on them.
+def split_to_sigma_points(mean, cov, lamda):
+    """gaussfiltax/utils.py:52-65: [mean, mean +- sqrt(dx+lamda) * columns of chol(cov)] (dx = 1: sqrt(cov))."""
+    dx = mean.shape[0]
+    pts = np.zeros((2 * dx + 1, dx))
+    pts[0] = mean
+    c = np.sqrt(dx + lamda)
+    L = np.sqrt(cov) if dx == 1 else np.linalg.cholesky(cov)
+    for i in range(dx):
+        pts[i + 1] = mean + c * L.T[i]
+        pts[dx + i + 1] = mean - c * L.T[i]
+    return pts
+
+
+def _step_fn(model, kw, Q, R):
+    """GaussFilt.which_step (gaussfilt.py:132-143)"""
+    if kw == 'pred':
+        return (lambda X: _f(model, X)), np.asarray(Q, np.float64)
+    return (lambda X: _g(model, X)), np.asarray(R, np.float64)
+
+
+def ukf_moments(model, m, P, kw, Q, R, alpha=1e-3, beta=2.0, kappa=0.0):
+    """UKF.moment_approx (gaussfilt.py:146-170) -> (mean_out [do], var_out [do,do], cov_out [dx,do])."""
+    func, cov = _step_fn(model, kw, Q, R)
+    dx = m.shape[0]
+    lam = alpha ** 2 * (dx + kappa) - dx
+    sp = split_to_sigma_points(m, P, lam)
+    nsp = func(sp)
+    wm0 = lam / (dx + lam)
+    wi = 1.0 / (2 * (dx + lam))
+    wc0 = wm0 + 1 - alpha ** 2 + beta
+    mean_out = wm0 * nsp[0] + wi * np.sum(nsp[1:], axis=0)
+    var_out = cov + wc0 * np.outer(nsp[0] - mean_out, nsp[0] - mean_out) + wi * (nsp[1:] - mean_out).T @ (nsp[1:] - mean_out)
+    cov_out = wc0 * np.outer(sp[0] - m, nsp[0] - mean_out) + wi * (sp[1:] - m).T @ (nsp[1:] - mean_out)
+    return mean_out, var_out, cov_out
+
+
+def mcf_moments(model, m, P, kw, Q, R, draws):
+    """MCF.moment_approx (gaussfilt.py:186-198) with particles = m + draws, draws [NP,dx] ~ N(0,P) supplied."""
+    func, cov = _step_fn(model, kw, Q, R)
+    particles = m + draws
+    tp = func(particles)
+    n = draws.shape[0]
+    mean_out = np.sum(tp, axis=0) / n
+    var_out = cov + (tp - mean_out).T @ (tp - mean_out) / n
+    cov_out = (particles - m).T @ (tp - mean_out) / n
+    return mean_out, var_out, cov_out
+
+
+def ekf_moments(model, m, P, kw, Q, R):
+    """EKF.moment_approx (gaussfilt.py:217-252), first order (the second-order terms are commented out there)."""
+    func, cov = _step_fn(model, kw, Q, R)
+    J = (_Fx if kw == 'pred' else _Gx)(model, m)[0]
+    return func(m)[0], cov + J @ P @ J.T, P @ J.T
+
+
+def _gaussfilt_step(moments, m, P, y, draws_t=None):
+    """one turn of GaussFilt.run / gaussfilt.GaussSumFilt.run: moment_approx('pred'), moment_approx('upd'), gain."""
+    pm, pP, _ = moments(m, P, 'pred', None if draws_t is None else draws_t[0])
+    mu_y, Sy, Cxy = moments(pm, pP, 'upd', None if draws_t is None else draws_t[1])
+    K = Cxy @ np.linalg.inv(Sy)
+    fm = pm + (y - mu_y) @ K.T
+    fP = pP - K @ Sy @ K.T
+    ll = gaussian_logpdf(np.reshape(y, [1, -1]), mu_y, Sy)
+    return fm, fP, ll
+
+
+def _moments_of(model, kind, Q, R, **kw):
+    if kind == "EKF":
+        return lambda m, P, step, d: ekf_moments(model, m, P, step, Q, R)
+    if kind == "UKF":
+        return lambda m, P, step, d: ukf_moments(model, m, P, step, Q, R, **kw)
+    if kind == "MCF":
+        return lambda m, P, step, d: mcf_moments(model, m, P, step, Q, R, d)
+    raise ValueError(kind)
+
+
+def gaussfilt_run(model, ys, Q, R, m0, P0, kind="EKF", draws=None, **kw):
+    """GaussFilt.run (gaussfilt.py:88-130) over a moment approximation -> (ll [T], means [T,dx], covs [T,dx,dx]).
+    draws [T,2,NP,dx] for the MCF (prediction draws ~ N(0, P_{t-1}), update draws ~ N(0, P_pred))."""
+    mom = _moments_of(model, kind, Q, R, **kw)
+    m, P = np.asarray(m0, np.float64).reshape(-1), np.asarray(P0, np.float64)
+    ll, ms, Ps = [], [], []
+    for t in range(ys.shape[0]):
+        m, P, l = _gaussfilt_step(mom, m, P, ys[t], None if draws is None else draws[t])
+        ll.append(l); ms.append(m); Ps.append(P)
+    return np.asarray(ll), np.stack(ms), np.stack(Ps)
+
+
+def bank_run(model, ys, Q, R, P0, init_means, kind="EKF", draws=None, **kw):
+    """gaussfilt.GaussSumFilt.run (gaussfilt.py:325-361): weights multiply by exp(loglik) WITHOUT a max shift (:356)."""
+    mom = _moments_of(model, kind, Q, R, **kw)
+    T, (M, dx) = ys.shape[0], init_means.shape
+    means = np.zeros((T + 1, dx, M)); covs = np.zeros((T + 1, dx, dx, M)); weights = np.zeros((T + 1, M))
+    means[T] = init_means.T; covs[T] = np.asarray(P0, np.float64)[:, :, None]; weights[T] = 1.0 / M
+    point = np.zeros((T, dx))
+    for t in range(T):
+        for m in range(M):
+            fm, fP, l = _gaussfilt_step(mom, means[t - 1, :, m], covs[t - 1, :, :, m], ys[t],
+                                        None if draws is None else draws[t, m])
+            means[t, :, m] = fm; covs[t, :, :, m] = fP
+            weights[t, m] = np.exp(l) * weights[t - 1, m]
+        weights[t] /= np.sum(weights[t])
+        point[t] = np.sum(np.multiply(means[t, :], weights[t]))
+    return means, covs, weights, point

@@ -375,6 +375,65 @@ class SIN1D(Model):
         return (x.dtype.type(2.0 * self.c) * x)[:, None, :].astype(x.dtype)
 
 
+class MSV(Model):
+    """Multivariate stochastic volatility with a switch (adaptive_experiment.py:47-57, `fmsv`, `glmsv`, `lmsvlp`):
+        f = Phi x + q                                   (Phi diagonal)
+        h = u beta exp(x/sigma) * r + (1-u) (H0 x + r)  (H0 diagonal; the emission noise enters MULTIPLICATIVELY when u = 1)
+        log p(y|x) = MVN(h(x, r0, u), M R M^T).log_prob(y),  M = u diag(beta exp(x/sigma)) + (1-u) I
+    theta = [Phi diag (d) | beta (d) | sigma | H0 diag (d)], dx = dq = dy = dr = d."""
+    name = "msv"
+    additive_r = False
+
+    def __init__(self, phi, beta, sigma, h0):
+        self.phi, self.beta, self.h0 = (np.atleast_1d(np.asarray(a, np.float64)) for a in (phi, beta, h0))
+        self.sigma = float(sigma)
+        self.dx = self.dq = self.dy = self.dr = self.phi.shape[0]
+
+    def theta(self):
+        return np.concatenate([self.phi, self.beta, [self.sigma], self.h0]).astype(np.float32)
+
+    def f(self, x, q, u):
+        return (self.phi.astype(x.dtype) * x + q).astype(x.dtype)
+
+    def Fx(self, x, q, u):
+        return np.broadcast_to(np.diag(self.phi).astype(x.dtype), (x.shape[0], self.dx, self.dx)).copy()
+
+    def Fq(self, x, q, u):
+        return np.broadcast_to(np.eye(self.dx, dtype=x.dtype), (x.shape[0], self.dx, self.dx)).copy()
+
+    def _d(self, x, u):
+        """diagonal of M = dh/dr"""
+        t = x.dtype.type
+        return (t(u) * self.beta.astype(x.dtype) * np.exp(x / t(self.sigma)) + (t(1) - t(u))).astype(x.dtype)
+
+    def h(self, x, r, u):
+        t = x.dtype.type
+        return (t(u) * self.beta.astype(x.dtype) * np.exp(x / t(self.sigma)) * r
+                + (t(1) - t(u)) * (self.h0.astype(x.dtype) * x + r)).astype(x.dtype)
+
+    def Hx(self, x, r, u):
+        t = x.dtype.type
+        d = t(u) * self.beta.astype(x.dtype) * np.exp(x / t(self.sigma)) * r / t(self.sigma) + (t(1) - t(u)) * self.h0.astype(x.dtype)
+        J = np.zeros((x.shape[0], self.dy, self.dx), dtype=x.dtype)
+        i = np.arange(self.dx)
+        J[:, i, i] = d
+        return J
+
+    def Hr(self, x, r, u):
+        J = np.zeros((x.shape[0], self.dy, self.dr), dtype=x.dtype)
+        i = np.arange(self.dx)
+        J[:, i, i] = self._d(x, u)
+        return J
+
+    def emission_log_prob(self, x, y, u, r0, R):
+        dt = x.dtype
+        n = x.shape[0]
+        loc = self.h(x, np.broadcast_to(_f(dt, r0), (n, self.dr)), u)
+        d = self._d(x, u)
+        cov = (d[:, :, None] * _f(dt, R)[None] * d[:, None, :]).astype(dt)       # M R M^T, state-dependent
+        return mvn_log_prob(loc, cov, _f(dt, y))
+
+
 def numerical_jacobian(fun, x, eps=1e-6):
     """float64 central differences of fun: [n,d] -> [n,k]; returns [n,k,d]."""
     x = np.asarray(x, dtype=np.float64)
