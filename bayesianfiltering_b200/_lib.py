@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BFILT_LIB", os.path.join(_HERE, "libbfilt.so"))
 
 BF_OK, BF_EINVAL, BF_ECUDA, BF_ENOMODEL, BF_ENOMEM, BF_ECOMM = 0, -1, -2, -3, -4, -5
-MODEL_UNGM, MODEL_BOT, MODEL_L63, MODEL_L96, MODEL_LG, MODEL_SIN1D = 1, 2, 3, 4, 5, 6
+MODEL_UNGM, MODEL_BOT, MODEL_L63, MODEL_L96, MODEL_LG, MODEL_SIN1D, MODEL_MSV = 1, 2, 3, 4, 5, 6, 7
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 PATH_AUTO, PATH_RESIDENT, PATH_STREAMED = 0, 1, 2
 GSF_PREDICT_FIRST, GSF_NO_JITTER, GSF_COV_PLUS_P = 1, 2, 4
@@ -53,6 +53,19 @@ class GsfIO(C.Structure):
                 ("out_mix_mean", C.c_void_p), ("Q_t", C.c_void_p), ("R_t", C.c_void_p)]
 
 
+class AgsfConfig(C.Structure):
+    _fields_ = [("num_components", C.c_int32), ("num_branch1", C.c_int32), ("num_branch2", C.c_int32), ("num_trials", C.c_int32),
+                ("device", C.c_int32), ("reserved", C.c_int32), ("alpha1", C.c_float), ("alpha2", C.c_float), ("seed", C.c_uint64)]
+
+
+class AgsfIO(C.Structure):
+    _fields_ = [("T", C.c_int32), ("emissions_per_trial", C.c_int32), ("rand_per_step", C.c_int32), ("reserved", C.c_int32),
+                ("emissions", C.c_void_p), ("inputs", C.c_void_p), ("init_means", C.c_void_p), ("init_covs", C.c_void_p),
+                ("z_iid", C.c_void_p), ("s_iid", C.c_void_p), ("res_u", C.c_void_p),
+                ("out_weights", C.c_void_p), ("out_means", C.c_void_p), ("out_covs", C.c_void_p), ("out_loglik", C.c_void_p),
+                ("out_pre_weights", C.c_void_p), ("out_updated_means", C.c_void_p), ("out_ancestors", C.c_void_p)]
+
+
 # every symbol include/bfilt.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("bf_pf_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(PfConfig), C.POINTER(C.c_void_p)]),
@@ -69,9 +82,16 @@ SYMBOLS = [
     ("bf_pf_shard_comm_ready", C.c_int, [C.c_void_p]),
     ("bf_gsf_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(GsfConfig), C.POINTER(C.c_void_p)]),
     ("bf_gsf_run", C.c_int, [C.c_void_p, C.POINTER(GsfIO), C.c_void_p]),
+    ("bf_gsf_step", C.c_int, [C.c_void_p, C.POINTER(GsfIO), C.c_void_p]),
     ("bf_gsf_run_host", C.c_int, [C.c_void_p, C.POINTER(GsfIO)]),
+    ("bf_gsf_set_unscented", C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
     ("bf_gsf_kernel_launches", C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("bf_gsf_destroy", C.c_int, [C.c_void_p]),
+    ("bf_agsf_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(AgsfConfig), C.POINTER(C.c_void_p)]),
+    ("bf_agsf_run", C.c_int, [C.c_void_p, C.POINTER(AgsfIO), C.c_void_p]),
+    ("bf_agsf_run_host", C.c_int, [C.c_void_p, C.POINTER(AgsfIO)]),
+    ("bf_agsf_destroy", C.c_int, [C.c_void_p]),
+    ("bf_optimal_resampling", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("bf_cumsum", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("bf_resample", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     ("bf_model_eval", C.c_int, [C.POINTER(ModelDesc), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,

@@ -32,3 +32,42 @@ def _gaussian_sum_to_components(gaussian_sum: GaussianSum):
 def _components_to_gaussian_sum(components) -> GaussianSum:
     """containers.py:46-61"""
     return GaussianSum([c.mean for c in components], [c.covariance for c in components], [c.weight for c in components])
+
+
+num_prt1 = 2      # containers.py:13-14: the branch counts the reference hard-codes for its tree version
+num_prt2 = 2
+
+
+def _branches_from_node1(node_component: GaussianComponent, splitting_cov, num_particles, key, *, normals=None):
+    """containers.py:63-90: split a Gaussian component into `num_particles` Gaussian particles of covariance `splitting_cov`
+    whose means are drawn from N(mean, covariance - splitting_cov); each gets weight / num_particles.  Host arithmetic (a
+    handful of flops per component); inside the filters the same split runs in the kernel (csrc/agsf_kernels.cuh).
+    `normals` [num_particles, dx] replaces the standard-normal draws behind jr.multivariate_normal."""
+    from .random import key_to_seed
+    mean = np.asarray(node_component.mean, np.float32)
+    samp = np.asarray(node_component.covariance, np.float32) - np.asarray(splitting_cov, np.float32)
+    n = int(num_particles)
+    if normals is None:
+        normals = np.random.default_rng(key_to_seed(key)).standard_normal((n, mean.shape[0]))
+    with np.errstate(invalid="ignore"):
+        try:
+            L = np.linalg.cholesky(samp.astype(np.float64))
+        except np.linalg.LinAlgError:
+            L = np.full(samp.shape, np.nan)
+    new_means = (mean + np.asarray(normals) @ L.T).astype(np.float32)
+    new_means = np.where(np.isnan(new_means), mean, new_means)               # containers.py:85
+    w = np.float32(node_component.weight) / np.float32(n)
+    return [GaussianComponent(new_means[i], np.asarray(splitting_cov, np.float32), w) for i in range(n)]
+
+
+_branches_from_node2 = _branches_from_node1          # containers.py:114-141: the same function with the second branch count
+
+
+def _branches_from_tree1(components, split_covs_array, num_branch_array, key=0):
+    """containers.py:92-112: branch out every component of a mixture -> list (one per component) of lists of components."""
+    from .random import split
+    keys = split(key, len(num_branch_array))
+    return [_branches_from_node1(c, d, n, k) for c, d, n, k in zip(components, split_covs_array, num_branch_array, keys)]
+
+
+_branches_from_tree2 = _branches_from_tree1          # containers.py:143-163

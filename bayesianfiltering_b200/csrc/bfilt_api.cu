@@ -24,6 +24,8 @@
 #include "pf_resident.cuh"
 #include "pf_fused.cuh"
 #include "gsf_kernels.cuh"
+#include "ugsf_kernels.cuh"
+#include "agsf_kernels.cuh"
 #include "gsf_large.cuh"
 
 // ------------------------------------------------------------------------------------------ errors
@@ -120,6 +122,8 @@ static int build_model_const(const bf_model_desc* d, ModelConst* mc) {
     case BF_MODEL_LG: want_dx = d->dx; want_dq = d->dx; want_dy = d->dy; want_theta = d->dx * d->dx + d->dy * d->dx; break;
     case BF_MODEL_SIN1D: want_dx = d->dx; want_dq = d->dx; want_dy = 1; want_theta = 2;
       if (d->dx > 3) return fail(BF_ENOMODEL, "SIN1D needs dx <= 3"); break;
+    case BF_MODEL_MSV: want_dx = d->dx; want_dq = d->dx; want_dy = d->dx; want_theta = 3 * d->dx + 1;
+      if (d->dx > 3) return fail(BF_ENOMODEL, "MSV needs dx <= 3"); break;
     case BF_MODEL_L96: return fail(BF_ENOMODEL, "L96 runs through the large-state path (not built in this library version)");
     default: return fail(BF_ENOMODEL, "unknown model_id %d", d->model_id);
   }
@@ -881,6 +885,9 @@ struct bf_gsf_s {
   DevBuf lconst, post_m;
   int64_t launches;
   bool have_carry;
+  bool unscented = false;   // bf_gsf_set_unscented: sigma points instead of Jacobians (k_ugsf)
+  float uk_alpha = 1e-3f, uk_beta = 2.0f, uk_kappa = 0.0f;
+  DevBuf uk_sqrt;           // [sqrtm(Q) | sqrtm(R)], BF_MAXD^2 floats each
   DevBuf carry_w, carry_m, carry_P;
   DevBuf hbuf[16];
   int nsm;
@@ -943,7 +950,7 @@ extern "C" int bf_gsf_destroy(bf_gsf_handle h) {
   if (!h) return BF_OK;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
-  h->carry_w.release(); h->carry_m.release(); h->carry_P.release(); h->lconst.release(); h->post_m.release();
+  h->carry_w.release(); h->carry_m.release(); h->carry_P.release(); h->lconst.release(); h->post_m.release(); h->uk_sqrt.release();
   for (DevBuf& b : h->hbuf) b.release();
   delete h;
   return BF_OK;
@@ -989,7 +996,16 @@ struct GsfRun {
       else if (cpl <= 4 && 4 * WORDS <= 48) wk = 2;
       else if (cpl <= 8 && 8 * WORDS <= 32) wk = 3;
     }
-    if (wk >= 0) {
+    if (h->unscented) {      // unscented_gaussian_sum_filter (inference.py:379-456): one thread per component
+      if (io->Q_t || io->R_t) return fail(BF_EINVAL, "the unscented filter takes constant noise covariances (their square roots are computed once)");
+      if (!ks.ugsf) return fail(BF_ENOMODEL, "the unscented filter is not instantiated for this model");
+      UkfArgs uk;
+      uk.alpha = h->uk_alpha; uk.beta = h->uk_beta; uk.kappa = h->uk_kappa;
+      uk.sqrtQ = h->uk_sqrt.as<float>(); uk.sqrtR = h->uk_sqrt.as<float>() + BF_MAXD * BF_MAXD;
+      const int threads = std::max(32, ((a.M + 31) / 32) * 32);
+      void* params[] = {(void*)&h->mc, (void*)&a, (void*)&uk};
+      CUDA_OK(cudaLaunchKernel(ks.ugsf, dim3(B), dim3(threads), params, 0, s));
+    } else if (wk >= 0) {
       void* params[] = {(void*)&h->mc, (void*)&a, (void*)&B};
       CUDA_OK(cudaLaunchKernel(ks.gsf_warp[wk], dim3(gridw), dim3(128), params, 0, s));
     } else {
@@ -1039,6 +1055,53 @@ extern "C" int bf_gsf_run(bf_gsf_handle h, const bf_gsf_io* io, void* stream) {
   return rc;
 }
 
+// principal square root of a symmetric PSD n x n matrix (float64 cyclic Jacobi; negative eigenvalues clamped to 0)
+static void sym_sqrt_host(const float* A32, int n, float* out) {
+  double A[BF_MAXD * BF_MAXD], V[BF_MAXD * BF_MAXD];
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { A[i * n + j] = 0.5 * ((double)A32[i * n + j] + (double)A32[j * n + i]); V[i * n + j] = (i == j); }
+  for (int sw = 0; sw < 30; ++sw) {
+    double off = 0.0;
+    for (int p = 0; p < n; ++p) for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n - 1; ++p) for (int q = p + 1; q < n; ++q) {
+      const double apq = A[p * n + q];
+      if (apq == 0.0) continue;
+      const double th = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+      const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+      for (int k = 0; k < n; ++k) { const double a0 = A[k * n + p], a1 = A[k * n + q]; A[k * n + p] = c * a0 - sn * a1; A[k * n + q] = sn * a0 + c * a1; }
+      for (int k = 0; k < n; ++k) { const double a0 = A[p * n + k], a1 = A[q * n + k]; A[p * n + k] = c * a0 - sn * a1; A[q * n + k] = sn * a0 + c * a1; }
+      for (int k = 0; k < n; ++k) { const double v0 = V[k * n + p], v1 = V[k * n + q]; V[k * n + p] = c * v0 - sn * v1; V[k * n + q] = sn * v0 + c * v1; }
+    }
+  }
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) {
+    double sacc = 0.0;
+    for (int k = 0; k < n; ++k) sacc += V[i * n + k] * sqrt(std::max(A[k * n + k], 0.0)) * V[j * n + k];
+    out[i * n + j] = (float)sacc;
+  }
+}
+
+extern "C" int bf_gsf_set_unscented(bf_gsf_handle h, float alpha, float beta, float kappa) {
+  if (!h) return fail(BF_EINVAL, "NULL argument");
+  if (h->large) return fail(BF_ENOMODEL, "the unscented filter runs on the register-resident models only");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  float host[2 * BF_MAXD * BF_MAXD];
+  memset(host, 0, sizeof host);
+  sym_sqrt_host(h->mc.Q, h->mc.dq, host);
+  sym_sqrt_host(h->mc.R, h->mc.dr, host + BF_MAXD * BF_MAXD);
+  if (h->uk_sqrt.ensure(sizeof host)) return fail(BF_ENOMEM, "cudaMalloc failed");
+  CUDA_OK(cudaMemcpy(h->uk_sqrt.p, host, sizeof host, cudaMemcpyHostToDevice));
+  h->unscented = true; h->uk_alpha = alpha; h->uk_beta = beta; h->uk_kappa = kappa;
+  return BF_OK;
+}
+
+extern "C" int bf_gsf_step(bf_gsf_handle h, const bf_gsf_io* io, void* stream) {
+  if (!io) return fail(BF_EINVAL, "NULL argument");
+  bf_gsf_io one = *io;
+  one.T = 1;
+  return bf_gsf_run(h, &one, stream);
+}
+
 extern "C" int bf_gsf_run_host(bf_gsf_handle h, const bf_gsf_io* hio) {
   int rc = gsf_check_io(h, hio);
   if (rc) return rc;
@@ -1074,6 +1137,117 @@ extern "C" int bf_gsf_run_host(bf_gsf_handle h, const bf_gsf_io* hio) {
   BACK(out_pred_means, B * T * M * dx) BACK(out_pred_covs, B * T * M * dx * dx) BACK(out_loglik, B * T) BACK(out_mix_mean, B * T * dx)
 #undef BACK
   CUDA_OK(cudaStreamSynchronize(s));
+  return BF_OK;
+}
+
+// ========================================================================================== augmented Gaussian-sum filter
+struct bf_agsf_s {
+  ModelConst mc;
+  bf_agsf_config cfg;
+  int64_t launches;
+  DevBuf leaf_m, leaf_P;
+  DevBuf hbuf[16];
+};
+
+static size_t agsf_smem_bytes(int M, int L, int dx) {
+  const int nchunk = (L + 1 + AGSF_WARPS * 128 - 1) / (AGSF_WARPS * 128);
+  return (size_t)(M * dx + M * dx * dx + ((L + 4) & ~3) + ((L + 5) & ~3) + nchunk + 1 + AGSF_WARPS + 8) * sizeof(float);
+}
+
+extern "C" int bf_agsf_create(const bf_model_desc* model, const bf_agsf_config* cfg, bf_agsf_handle* out) {
+  if (!cfg || !out) return fail(BF_EINVAL, "NULL argument");
+  if (cfg->num_components < 1 || cfg->num_branch1 < 1 || cfg->num_branch2 < 1 || cfg->num_trials < 1)
+    return fail(BF_EINVAL, "num_components, num_branch1, num_branch2, num_trials must be >= 1");
+  const long long L = (long long)cfg->num_components * cfg->num_branch1 * cfg->num_branch2;
+  if (L > (1 << 20)) return fail(BF_EINVAL, "M*N1*N2 = %lld leaves is out of range", L);
+  if (!(cfg->alpha1 >= 0.0f && cfg->alpha1 < 1.0f && cfg->alpha2 >= 0.0f && cfg->alpha2 < 1.0f))
+    return fail(BF_EINVAL, "opt_args must lie in [0,1): P - a P has to stay positive definite (got %g, %g)", cfg->alpha1, cfg->alpha2);
+  bf_agsf_s* h = new (std::nothrow) bf_agsf_s();
+  if (!h) return fail(BF_ENOMEM, "out of host memory");
+  int rc = build_model_const(model, &h->mc);
+  if (rc) { delete h; return rc; }
+  h->cfg = *cfg; h->launches = 0;
+  if (agsf_smem_bytes(cfg->num_components, (int)L, h->mc.dx) > 200 * 1024) { delete h; return fail(BF_EINVAL, "the mixture does not fit one CTA's shared memory"); }
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) { delete h; return fail(BF_ECUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e)); }
+  if ((e = pool_setup(cfg->device)) != cudaSuccess) { delete h; return fail(BF_ECUDA, "memory pool setup: %s", cudaGetErrorString(e)); }
+  const size_t BL = (size_t)cfg->num_trials * L, dx = h->mc.dx;
+  if (h->leaf_m.ensure(BL * dx * 4) || h->leaf_P.ensure(BL * dx * dx * 4)) { bf_agsf_destroy(h); return fail(BF_ENOMEM, "cudaMalloc failed"); }
+  *out = h;
+  return BF_OK;
+}
+
+extern "C" int bf_agsf_destroy(bf_agsf_handle h) {
+  if (!h) return BF_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  h->leaf_m.release(); h->leaf_P.release();
+  for (DevBuf& b : h->hbuf) b.release();
+  delete h;
+  return BF_OK;
+}
+
+extern "C" int bf_agsf_run(bf_agsf_handle h, const bf_agsf_io* io, void* stream) {
+  if (!h || !io) return fail(BF_EINVAL, "NULL argument");
+  if (io->T < 1 || !io->emissions || !io->init_means) return fail(BF_EINVAL, "T < 1, or emissions / init_means is NULL");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  BfKernelSet ks;
+  int rc = kernels_for(h->mc, BFK_GSF, &ks);
+  if (rc) return rc;
+  if (!ks.agsf) return fail(BF_ENOMODEL, "the augmented filter is not instantiated for this model (dx <= 4)");
+  AgsfArgs a;
+  memset(&a, 0, sizeof a);
+  a.M = h->cfg.num_components; a.N1 = h->cfg.num_branch1; a.N2 = h->cfg.num_branch2; a.T = io->T;
+  a.emissions_per_trial = io->emissions_per_trial; a.rand_per_step = io->rand_per_step; a.a0 = h->cfg.alpha1; a.a1 = h->cfg.alpha2;
+  a.seed = h->cfg.seed; a.emissions = io->emissions; a.inputs = io->inputs; a.init_means = io->init_means; a.init_covs = io->init_covs;
+  a.z_iid = io->z_iid; a.s_iid = io->s_iid; a.res_u = io->res_u;
+  a.leaf_m = h->leaf_m.as<float>(); a.leaf_P = h->leaf_P.as<float>();
+  a.out_weights = io->out_weights; a.out_means = io->out_means; a.out_covs = io->out_covs; a.out_loglik = io->out_loglik;
+  a.out_pre_weights = io->out_pre_weights; a.out_updated_means = io->out_updated_means; a.out_ancestors = io->out_ancestors;
+  const size_t smem = agsf_smem_bytes(a.M, a.M * a.N1 * a.N2, h->mc.dx);
+  CUDA_OK(cudaFuncSetAttribute(ks.agsf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {(void*)&h->mc, (void*)&a};
+  CUDA_OK(cudaLaunchKernel(ks.agsf, dim3(h->cfg.num_trials), dim3(AGSF_WARPS * 32), params, smem, (cudaStream_t)stream));
+  h->launches += 1;
+  return BF_OK;
+}
+
+extern "C" int bf_agsf_run_host(bf_agsf_handle h, const bf_agsf_io* hio) {
+  if (!h || !hio) return fail(BF_EINVAL, "NULL argument");
+  if (hio->T < 1) return fail(BF_EINVAL, "T must be >= 1");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = 0;
+  const size_t M = h->cfg.num_components, N1 = h->cfg.num_branch1, N2 = h->cfg.num_branch2, L = M * N1 * N2, B = h->cfg.num_trials;
+  const size_t T = hio->T, dx = h->mc.dx, dy = h->mc.dy, TR = hio->rand_per_step ? T : 1;
+  bf_agsf_io d = *hio;
+  int k = 0, rc;
+#define IN(field, count) if ((rc = stage_in(h->hbuf[k++], hio->field, (size_t)(count) * 4, s, (const void**)&d.field))) return rc;
+#define OUT(field, count) if ((rc = stage_out(h->hbuf[k++], hio->field, (size_t)(count) * 4, (void**)&d.field))) return rc;
+  IN(emissions, (hio->emissions_per_trial ? B : 1) * T * dy) IN(inputs, T) IN(init_means, B * M * dx) IN(init_covs, B * M * dx * dx)
+  IN(z_iid, TR * M * dx * N1) IN(s_iid, TR * M * N1 * dx * N2) IN(res_u, TR * M)
+  OUT(out_weights, B * T * M) OUT(out_means, B * T * M * dx) OUT(out_covs, B * T * M * dx * dx) OUT(out_loglik, B * T)
+  OUT(out_pre_weights, B * T * L) OUT(out_updated_means, B * T * L * dx) OUT(out_ancestors, B * T * M)
+#undef IN
+#undef OUT
+  rc = bf_agsf_run(h, &d, s);
+  if (rc) return rc;
+#define BACK(field, count) if (hio->field) CUDA_OK(cudaMemcpyAsync(hio->field, d.field, (size_t)(count) * 4, cudaMemcpyDeviceToHost, s));
+  BACK(out_weights, B * T * M) BACK(out_means, B * T * M * dx) BACK(out_covs, B * T * M * dx * dx) BACK(out_loglik, B * T)
+  BACK(out_pre_weights, B * T * L) BACK(out_updated_means, B * T * L * dx) BACK(out_ancestors, B * T * M)
+#undef BACK
+  CUDA_OK(cudaStreamSynchronize(s));
+  return BF_OK;
+}
+
+extern "C" int bf_optimal_resampling(const float* w, int32_t M, int32_t N, const float* u, int32_t* idx_out, float* w_out, void* stream) {
+  if (!w || !u || !idx_out || !w_out) return fail(BF_EINVAL, "NULL argument");
+  if (M < 2 || M > OPTRES_MAX || N < 2 || N > M) return fail(BF_EINVAL, "need 2 <= N <= M <= %d (got M=%d, N=%d)", OPTRES_MAX, M, N);
+  int P2 = 1;
+  while (P2 < M) P2 <<= 1;
+  const size_t smem = (size_t)(2 * P2 + 3 * (M + 8) + 64) * 4;
+  CUDA_OK(cudaFuncSetAttribute(k_optimal_resampling, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_optimal_resampling<<<1, AGSF_WARPS * 32, smem, (cudaStream_t)stream>>>(w, M, N, u, idx_out, w_out);
+  LAUNCH_OK();
   return BF_OK;
 }
 

@@ -22,12 +22,16 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 
 # job list: "<object> <source> <defines...>", heaviest first
 jobs=()
-for ((g = 0; g < NG_FUSED; ++g)); do jobs+=("fused_$g tu_kernels.cu -DBF_TU_KIND=1 -DBF_NGROUPS=$NG_FUSED -DBF_GROUP=$g"); done
+# The particle-filter translation units are compiled with -fmad=false: every fused multiply-add in them is one the source
+# spells out (fmaf), so the general / lean / sharded instantiations of a kernel cannot contract a product-sum differently
+# and one filter gives the same bits whichever of them ran it (tests: lean == general, sharded == one GPU).
+PF="-fmad=false"
+for ((g = 0; g < NG_FUSED; ++g)); do jobs+=("fused_$g tu_kernels.cu $PF -DBF_TU_KIND=1 -DBF_NGROUPS=$NG_FUSED -DBF_GROUP=$g"); done
 jobs+=("large tu_kernels.cu -DBF_TU_KIND=5")
 for ((g = 0; g < NG_GSF; ++g)); do jobs+=("gsf_$g tu_kernels.cu -DBF_TU_KIND=3 -DBF_NGROUPS=$NG_GSF -DBF_GROUP=$g"); done
-for ((g = 0; g < NG_RESIDENT; ++g)); do jobs+=("resident_$g tu_kernels.cu -DBF_TU_KIND=2 -DBF_NGROUPS=$NG_RESIDENT -DBF_GROUP=$g"); done
-for ((g = 0; g < NG_MISC; ++g)); do jobs+=("misc_$g tu_kernels.cu -DBF_TU_KIND=4 -DBF_NGROUPS=$NG_MISC -DBF_GROUP=$g"); done
-jobs+=("api bfilt_api.cu -DBF_NG_FUSED=$NG_FUSED -DBF_NG_RESIDENT=$NG_RESIDENT -DBF_NG_GSF=$NG_GSF -DBF_NG_MISC=$NG_MISC")
+for ((g = 0; g < NG_RESIDENT; ++g)); do jobs+=("resident_$g tu_kernels.cu $PF -DBF_TU_KIND=2 -DBF_NGROUPS=$NG_RESIDENT -DBF_GROUP=$g"); done
+for ((g = 0; g < NG_MISC; ++g)); do jobs+=("misc_$g tu_kernels.cu $PF -DBF_TU_KIND=4 -DBF_NGROUPS=$NG_MISC -DBF_GROUP=$g"); done
+jobs+=("api bfilt_api.cu $PF -DBF_NG_FUSED=$NG_FUSED -DBF_NG_RESIDENT=$NG_RESIDENT -DBF_NG_GSF=$NG_GSF -DBF_NG_MISC=$NG_MISC")
 
 compile_one() {   # $1 = job line
   set -- $1

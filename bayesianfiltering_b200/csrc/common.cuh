@@ -59,13 +59,20 @@ __host__ __device__ __forceinline__ float u01_open0(uint32_t r) { return ((float
 enum { BF_STREAM_INIT = 1, BF_STREAM_NOISE = 2, BF_STREAM_RESAMPLE = 3 };
 
 #ifdef __CUDACC__
-// two standard normals from two 32-bit words (Box-Muller)
+// two standard normals from two 32-bit words (Box-Muller).  Every operation is spelled out (one MUFU each for lg2, sqrt,
+// sin, cos; explicit fma / mul) so that all kernels and all template instantiations draw bit-identical noise from the same
+// counter, whatever the compiler would have contracted: a filter's result must not depend on which kernel variant ran it.
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  float u1 = u01_open0(a), u2 = u01(b);
-  float r = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.28318530717958647692f * u2, &s, &c);
-  z0 = r * c; z1 = r * s;
+  const float k = 1.0f / 16777216.0f;
+  const float u1 = __fmaf_rn((float)(a >> 8), k, k);                 // (0,1]
+  const float th = __fmul_rn((float)(b >> 8), 6.28318530717958647692f * k);   // [0, 2 pi)
+  const float r = mufu_sqrt(__fmul_rn(mufu_lg2(u1), -1.38629436111989061883f));   // sqrt(-2 ln u1), ln = lg2 * ln 2
+  z0 = __fmul_rn(r, mufu_cos(th)); z1 = __fmul_rn(r, mufu_sin(th));
 }
 
 // DQ standard normals for (trial b, particle i, step t): counter = (i_lo, i_hi | b<<8.., t, stream)

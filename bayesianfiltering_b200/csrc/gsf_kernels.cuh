@@ -12,8 +12,8 @@
 //   P+ = P - (K S) K^T with the UN-jittered S            inference.py:101
 //   ll = MVN(h(m), S).log_prob(y), Cholesky of the un-jittered S   inference.py:104 (TFP)
 //   no re-symmetrisation of P+.
-// All registered models have additive emission noise (H_r = I, so H_r R H_r^T = R) and a constant F_q,
-// so F_q Q F_q^T is computed once per CTA.
+// Emission noise is additive (H_r = I) for every registered model except MSV, whose H_r(x, u) is diagonal (models.cuh);
+// F_q is constant for all of them, so F_q Q F_q^T is computed once per CTA.
 #pragma once
 #include "common.cuh"
 #include "models.cuh"
@@ -137,11 +137,16 @@ __device__ __forceinline__ float ekf_condition(float* m, float* P, const float* 
   Mo::Hx(m, mc.r0, u, mc, H);
   mm<DY, DX, DX>(H, P, HP);                         // H_x @ P
   mmt<DY, DX, DY>(HP, H, S);                        // (H_x P) H_x^T
+  float hr[DY];
+#pragma unroll
+  for (int i = 0; i < DY; ++i) hr[i] = 1.0f;
+  if constexpr (nonadditive_r<Mo>::value) Mo::Hr_diag(m, u, mc, hr);   // H_r = dh/dr at (m, r0, u): diagonal in the registry
 #pragma unroll
   for (int i = 0; i < DY; ++i)
 #pragma unroll
     for (int j = 0; j < DY; ++j) {
-      S[i * DY + j] = Rm[i * DY + j] + S[i * DY + j];        // H_r R H_r^T + H_x P H_x^T  (:99), H_r = I
+      const float rr = nonadditive_r<Mo>::value ? hr[i] * Rm[i * DY + j] * hr[j] : Rm[i * DY + j];
+      S[i * DY + j] = rr + S[i * DY + j];                    // H_r R H_r^T + H_x P H_x^T  (:99)
       Sj[i * DY + j] = S[i * DY + j] + jitter;               // psd_solve: + 1e-6 on EVERY element
     }
 #pragma unroll

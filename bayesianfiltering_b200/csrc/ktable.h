@@ -14,6 +14,8 @@ struct BfKernelSet {
   const void* gsf_cta;        // k_gsf<M, TV = false>                           args (ModelConst, GsfArgs)
   const void* gsf_cta_tv;     // k_gsf<M, TV = true>: time-varying Q_t / R_t
   const void* gsf_warp[4];    // k_gsf_warp<M, 1 / 2 / 4 / 8>                   args (ModelConst, GsfArgs, int B)
+  const void* ugsf;           // k_ugsf<M>: unscented Gaussian-sum filter       args (ModelConst, GsfArgs, UkfArgs)
+  const void* agsf;           // k_agsf<M>: augmented Gaussian-sum filter       args (ModelConst, AgsfArgs)
   const void* model_eval;     // k_model_eval<M>
   const void* ssm_sample;     // k_ssm_sample<M>
 };

@@ -15,10 +15,10 @@ struct UngmModel {
   __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
     const float xx = x[0];
     const float inv = __frcp_rn(1.0f + xx * xx);          // correctly rounded reciprocal, shared with Fx below
-    o[0] = c.theta[0] * xx + c.theta[1] * xx * inv + c.theta[2] * u + q[0];
+    o[0] = fmaf(c.theta[2], u, fmaf(c.theta[1] * xx, inv, c.theta[0] * xx)) + q[0];
   }
   __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
-    o[0] = c.theta[3] * x[0] + c.theta[4] * x[0] * x[0] + r[0];
+    o[0] = fmaf(c.theta[4] * x[0], x[0], c.theta[3] * x[0]) + r[0];
   }
   __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
     const float x2 = x[0] * x[0], inv = __frcp_rn(1.0f + x2);
@@ -31,11 +31,15 @@ struct UngmModel {
 };
 
 // sin and cos to ~1 ulp: minimax polynomials (Cephes sinf/cosf kernels) for |x| <= pi/4, libm otherwise.
+// (fma / mul spelled out here and below: the particle-filter translation units are compiled with -fmad=false, so that
+// the general, lean and sharded instantiations of a kernel cannot round a product-sum differently.)
 __device__ __forceinline__ void sincos_small(float x, float* sn, float* cs) {
   if (fabsf(x) <= 0.78539816f) {
     const float z = x * x;
-    *sn = x + x * z * (-1.6666654611e-1f + z * (8.3321608736e-3f + z * -1.9515295891e-4f));
-    *cs = 1.0f - 0.5f * z + z * z * (4.166664568298827e-2f + z * (-1.388731625493765e-3f + z * 2.443315711809948e-5f));
+    const float ps = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+    *sn = fmaf(x * z, ps, x);
+    const float pc = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+    *cs = fmaf(z * z, pc, fmaf(-0.5f, z, 1.0f));
   } else {
     sincosf(x, sn, cs);
   }
@@ -48,9 +52,9 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
   const bool mid = mn > 0.41421356f * mx;               // atan(mn/mx) = pi/4 + atan((mn-mx)/(mn+mx))
   const float num = mid ? mn - mx : mn, den = mid ? mn + mx : mx;
-  const float t = (den == 0.0f) ? 0.0f : num / den;
+  const float t = (den == 0.0f) ? 0.0f : __fdividef(num, den);
   const float z = t * t;
-  const float p = ((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f;
+  const float p = fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f);
   float r = fmaf(p * z, t, t);
   if (mid) r = (r + -2.18556941e-8f) + 0.785398185253143310546875f;     // pi/4 as hi + lo
   if (ay > ax) r = 1.57079632679489662f - r;
@@ -68,13 +72,13 @@ struct BotModel {
   __device__ __forceinline__ static Turn turn(const float* x, const ModelConst& c) {
     Turn t;
     // one rsqrt instead of sqrt + three divisions (each result within 2 ulp of the reference's expression)
-    const float v2 = x[1] * x[1] + x[3] * x[3];
+    const float v2 = fmaf(x[1], x[1], x[3] * x[3]);
     const float rs = rsqrtf(v2);
     const float k = c.theta[2] * c.theta[1];
     t.s = v2 * rs;
     t.om = k * rs;
     sincos_small(c.theta[0] * t.om, &t.sn, &t.cs);
-    const float iom = t.s * (1.0f / k);                 // k is uniform: the reciprocal is hoisted
+    const float iom = t.s * __frcp_rn(k);               // k is uniform: the reciprocal is hoisted
     t.A = t.sn * iom;
     t.B = (1.0f - t.cs) * iom;
     return t;
@@ -82,29 +86,38 @@ struct BotModel {
   __device__ __forceinline__ static void coef(float u, float& c0, float& c1, float& c2) {
     c0 = 0.5f * (u - 1.0f) * (u - 2.0f); c1 = -u * (u - 2.0f); c2 = 0.5f * u * (u - 1.0f);
   }
+  // (c0 FCV + c1 FCT(x, acc) + c2 FCT(x, -acc)) x + G q, accumulated as fma(c2, ., fma(c1, ., fma(c0, ., G q))).  The
+  // manoeuvre input u is the same for every particle of a step, and for u in {0, 1, 2} two of the three coefficients are
+  // exactly 0: a term whose coefficient is 0 contributes exactly 0 and is skipped (a uniform branch) -- unless the speed is
+  // 0, where the reference's 0 * NaN poisons the result and so does this.
   __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
     float c0, c1, c2; coef(u, c0, c1, c2);
     const float T = c.theta[0];
-    const float gq0 = 0.5f * q[0], gq2 = 0.5f * q[1];
-    // u = 0 (constant velocity): the two turn models enter with coefficient exactly 0 -- skip them unless the
-    // speed is 0, where the reference's 0 * NaN still poisons the result
-    if (c0 == 1.0f && c1 == 0.0f && c2 == 0.0f && (x[1] != 0.0f || x[3] != 0.0f)) {
-      o[0] = x[0] + T * x[1] + gq0; o[1] = x[1] + q[0]; o[2] = x[2] + T * x[3] + gq2; o[3] = x[3] + q[1];
-      return;
+    float r0 = 0.5f * q[0], r1 = q[0], r2 = 0.5f * q[1], r3 = q[1];
+    const bool still = (x[1] == 0.0f && x[3] == 0.0f);
+    if (c0 != 0.0f) {
+      r0 = fmaf(c0, fmaf(T, x[1], x[0]), r0); r1 = fmaf(c0, x[1], r1);
+      r2 = fmaf(c0, fmaf(T, x[3], x[2]), r2); r3 = fmaf(c0, x[3], r3);
     }
-    Turn t = turn(x, c);
-    // FCT(x,+acc) x and FCT(x,-acc) x share sin/cos: Omega -> -Omega flips sn and B only
-    float p0 = x[0] + t.A * x[1], p2 = x[2] + t.A * x[3];
-    float ct1[4] = {p0 - t.B * x[3], t.cs * x[1] - t.sn * x[3], p2 + t.B * x[1], t.sn * x[1] + t.cs * x[3]};
-    float ct2[4] = {p0 + t.B * x[3], t.cs * x[1] + t.sn * x[3], p2 - t.B * x[1], -t.sn * x[1] + t.cs * x[3]};
-    float cv[4] = {x[0] + T * x[1], x[1], x[2] + T * x[3], x[3]};
-    float gq[4] = {0.5f * q[0], q[0], 0.5f * q[1], q[1]};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = c0 * cv[i] + c1 * ct1[i] + c2 * ct2[i] + gq[i];
+    if (c1 != 0.0f || c2 != 0.0f || still) {
+      const Turn t = turn(x, c);
+      // FCT(x,+acc) x and FCT(x,-acc) x share sin/cos: Omega -> -Omega flips sn and B only
+      const float p0 = fmaf(t.A, x[1], x[0]), p2 = fmaf(t.A, x[3], x[2]);
+      const float cc1 = t.cs * x[1], cc3 = t.cs * x[3], ss1 = t.sn * x[1], ss3 = t.sn * x[3];
+      if (c1 != 0.0f || still) {
+        r0 = fmaf(c1, fmaf(-t.B, x[3], p0), r0); r1 = fmaf(c1, cc1 - ss3, r1);
+        r2 = fmaf(c1, fmaf(t.B, x[1], p2), r2); r3 = fmaf(c1, ss1 + cc3, r3);
+      }
+      if (c2 != 0.0f || still) {
+        r0 = fmaf(c2, fmaf(t.B, x[3], p0), r0); r1 = fmaf(c2, cc1 + ss3, r1);
+        r2 = fmaf(c2, fmaf(-t.B, x[1], p2), r2); r3 = fmaf(c2, cc3 - ss1, r3);
+      }
+    }
+    o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3;
   }
   __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
     o[0] = atan2_fast(x[2], x[0]) + r[0];
-    if (DY == 2) o[1] = sqrtf(x[0] * x[0] + x[2] * x[2]) + r[1];
+    if (DY == 2) o[1] = sqrtf(fmaf(x[0], x[0], x[2] * x[2])) + r[1];
   }
   // d(FCT(x,a) x)/dx for a = +acc (sgn=+1) or -acc (sgn=-1), accumulated into J with weight cw
   __device__ __forceinline__ static void fct_jac(const float* x, const Turn& t, float T, float sgn, float cw, float* J) {
@@ -158,12 +171,12 @@ struct L63Model {
   static constexpr int DX = 3, DQ = 3, DY = 1, DR = 1;
   __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
     const float sg = c.theta[0], rho = c.theta[1], be = c.theta[2], dt = c.theta[3];
-    o[0] = dt * sg * (x[1] - x[0]) + x[0] + q[0];
-    o[1] = dt * (x[0] * rho - x[1] - x[0] * x[2]) + x[1] + q[1];
-    o[2] = dt * (x[0] * x[1] - be * x[2]) + x[2] + q[2];
+    o[0] = fmaf(dt * sg, x[1] - x[0], x[0]) + q[0];
+    o[1] = fmaf(dt, fmaf(-x[0], x[2], fmaf(x[0], rho, -x[1])), x[1]) + q[1];
+    o[2] = fmaf(dt, fmaf(x[0], x[1], -be * x[2]), x[2]) + q[2];
   }
   __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
-    o[0] = c.theta[4] * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) + r[0];
+    o[0] = fmaf(c.theta[4], fmaf(x[2], x[2], fmaf(x[1], x[1], x[0] * x[0])), r[0]);
   }
   __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
     const float sg = c.theta[0], rho = c.theta[1], be = c.theta[2], dt = c.theta[3];
@@ -191,7 +204,7 @@ struct LgModel {
     for (int i = 0; i < DX; ++i) {
       float a = 0.0f;
 #pragma unroll
-      for (int j = 0; j < DX; ++j) a += c.theta[i * DX + j] * x[j];
+      for (int j = 0; j < DX; ++j) a = fmaf(c.theta[i * DX + j], x[j], a);
       o[i] = a + q[i];
     }
   }
@@ -200,7 +213,7 @@ struct LgModel {
     for (int i = 0; i < DY; ++i) {
       float a = 0.0f;
 #pragma unroll
-      for (int j = 0; j < DX; ++j) a += c.theta[DX * DX + i * DX + j] * x[j];
+      for (int j = 0; j < DX; ++j) a = fmaf(c.theta[DX * DX + i * DX + j], x[j], a);
       o[i] = a + r[i];
     }
   }
@@ -230,8 +243,8 @@ struct Sin1dModel {
   __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
     float a = 0.0f;
 #pragma unroll
-    for (int i = 0; i < DX; ++i) a += x[i] * x[i];
-    o[0] = c.theta[1] * a + r[0];
+    for (int i = 0; i < DX; ++i) a = fmaf(x[i], x[i], a);
+    o[0] = fmaf(c.theta[1], a, r[0]);
   }
   __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
 #pragma unroll
@@ -250,6 +263,54 @@ struct Sin1dModel {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Multivariate stochastic volatility with a switch (adaptive_experiment.py:47-57, fmsv / glmsv / lmsvlp):
+//   f = Phi x + q (Phi diagonal);  h = u beta exp(x/sigma) * r + (1-u) (H0 x + r) (H0 diagonal): with u = 1 the emission
+//   noise enters MULTIPLICATIVELY, so dh/dr = M(x,u) = diag(u beta exp(x/sigma) + (1-u)) is not the identity -- the
+//   Gaussian-sum update uses S = M R M^T + H P H^T (inference.py:99) and the particle filter's log-prob has the
+//   state-dependent covariance M R M^T.  theta = [Phi (D) | beta (D) | sigma | H0 (D)].
+template <int D>
+struct MsvModel {
+  static constexpr int DX = D, DQ = D, DY = D, DR = D;
+  static constexpr bool NONADDITIVE_R = true;
+  __device__ __forceinline__ static void f(const float* x, const float* q, float u, const ModelConst& c, float* o) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = fmaf(c.theta[i], x[i], q[i]);
+  }
+  // diagonal of dh/dr at (x, u)
+  __device__ __forceinline__ static void Hr_diag(const float* x, float u, const ModelConst& c, float* d) {
+    const float isg = __frcp_rn(c.theta[2 * D]);
+#pragma unroll
+    for (int i = 0; i < D; ++i) d[i] = fmaf(u * c.theta[D + i], expf(x[i] * isg), 1.0f - u);
+  }
+  __device__ __forceinline__ static void h(const float* x, const float* r, float u, const ModelConst& c, float* o) {
+    const float isg = __frcp_rn(c.theta[2 * D]);
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+      o[i] = fmaf(u * c.theta[D + i] * expf(x[i] * isg), r[i], (1.0f - u) * fmaf(c.theta[2 * D + 1 + i], x[i], r[i]));
+  }
+  __device__ __forceinline__ static void Fx(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) J[i] = (i % (D + 1) == 0) ? c.theta[i / (D + 1)] : 0.0f;
+  }
+  __device__ __forceinline__ static void Fq(const float* x, const float* q, float u, const ModelConst& c, float* J) {
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) J[i] = (i % (D + 1) == 0) ? 1.0f : 0.0f;
+  }
+  __device__ __forceinline__ static void Hx(const float* x, const float* r, float u, const ModelConst& c, float* J) {
+    const float isg = __frcp_rn(c.theta[2 * D]);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) J[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+      J[i * D + i] = fmaf(u * c.theta[D + i] * expf(x[i] * isg) * isg, r[i], (1.0f - u) * c.theta[2 * D + 1 + i]);
+  }
+};
+
+// does the model's emission noise enter non-additively (dh/dr != I)?
+template <class M, class = void> struct nonadditive_r { static constexpr bool value = false; };
+template <class M> struct nonadditive_r<M, decltype((void)M::NONADDITIVE_R)> { static constexpr bool value = M::NONADDITIVE_R; };
+
+// ---------------------------------------------------------------------------------------------
 // MVN(loc = h(x, r0, u), covariance_matrix = R).log_prob(y) -- the `*lp` callables of the reference's
 // drivers (e.g. BOT_Experiment_script.py:45) with TFP's formula: z = L^-1 (y - loc) by forward
 // substitution, -0.5 z.z - sum(log diag L) - 0.5 k log(2 pi).
@@ -258,16 +319,25 @@ __device__ __forceinline__ float emission_log_prob(const float* x, const float* 
   float loc[M::DY];
   M::h(x, c.r0, u, c, loc);
   float z[M::DY];
-  float ss = 0.0f;
+  float ss = 0.0f, lp = c.lp_const;
+  float dd[M::DY];
+  if constexpr (nonadditive_r<M>::value) {
+    // covariance M R M^T with M = diag(d) > 0: its Cholesky factor is diag(d) L_R, so the whitened residual is
+    // L_R^-1 diag(d)^-1 (y - loc) and log det gains sum(log d)   (adaptive_experiment.py:55-57 `lmsvlp`)
+    M::Hr_diag(x, u, c, dd);
+#pragma unroll
+    for (int i = 0; i < M::DY; ++i) lp -= logf(dd[i]);
+  }
 #pragma unroll
   for (int i = 0; i < M::DY; ++i) {
     float d = y[i] - loc[i];
+    if constexpr (nonadditive_r<M>::value) d = __fdiv_rn(d, dd[i]);
 #pragma unroll
-    for (int j = 0; j < i; ++j) d -= c.LR[i * M::DR + j] * z[j];
+    for (int j = 0; j < i; ++j) d = fmaf(-c.LR[i * M::DR + j], z[j], d);
     z[i] = d * c.iLR[i];
-    ss += z[i] * z[i];
+    ss = fmaf(z[i], z[i], ss);
   }
-  return -0.5f * ss + c.lp_const;
+  return fmaf(-0.5f, ss, lp);
 }
 
 // Dispatch a functor over the registry.  F must provide `template<class M> int run()`.  Returns -3 when the model is
@@ -306,6 +376,9 @@ int bf_dispatch_model(const ModelConst& mc, F& fn) {
   BF_ENTRY(12, id == 5 && dx == 2 && dy == 1, LgModel<2, 1>)
   BF_ENTRY(13, id == 5 && dx == 1 && dy == 1, LgModel<1, 1>)
   BF_ENTRY(14, id == 6 && dx == 1, Sin1dModel<1>)
+  BF_ENTRY(15, id == 7 && dx == 3, MsvModel<3>)
+  BF_ENTRY(16, id == 7 && dx == 2, MsvModel<2>)
+  BF_ENTRY(17, id == 7 && dx == 1, MsvModel<1>)
   (void)id; (void)dx; (void)dy;
   return -3;
 }

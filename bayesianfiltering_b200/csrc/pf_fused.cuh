@@ -855,15 +855,16 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       constexpr int PU = PF_FUSED_PU;
 #pragma unroll 1
       for (int h = 0; h < 4 / PU; ++h) {
-        float lh[PU];
-#pragma unroll
-        for (int kk = 0; kk < PU; ++kk) lh[kk] = 0.0f;
+        float lh[PU], wv[PU], xt[PU][DX];
 #pragma unroll
         for (int kk = 0; kk < PU; ++kk) {
           const int k = PU * h + kk;
-          if (k < nv) {
+          lh[kk] = -INFINITY; wv[kk] = 0.0f;           // a slot past N: weight exp(-inf) * 0, never stored
+#pragma unroll
+          for (int c = 0; c < DX; ++c) xt[kk][c] = 0.0f;
+          if (LEAN || k < nv) {
             const int i = base + k;
-            float qn[DQ], xt[DX];
+            float qn[DQ];
             const float* x = xs[kk];
             if (pt > 0 && a.out_particles) store_state<DX>(a.out_particles + ((ptrdiff_t)t - 1) * N * DX, (size_t)i, x);
             if (a.noise) {
@@ -879,22 +880,22 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
               for (int r = 0; r < DQ; ++r) {             // q = q0 + L_Q z  (models.py:83, TFP MVN sample)
                 float s = mc.q0[r];
 #pragma unroll
-                for (int c = 0; c <= r; ++c) s += mc.LQ[r * DQ + c] * zk[c];
+                for (int c = 0; c <= r; ++c) s = fmaf(mc.LQ[r * DQ + c], zk[c], s);
                 qn[r] = s;
               }
             }
-            M::f(x, qn, u_in, mc, xt);
-            store_state_cs<DX>(x_cur, (size_t)i, xt);
-            if (a.out_propagated) store_state<DX>(a.out_propagated + (size_t)t * N * DX, (size_t)i, xt);
+            M::f(x, qn, u_in, mc, xt[kk]);
+            store_state_cs<DX>(x_cur, (size_t)i, xt[kk]);
+            if (a.out_propagated) store_state<DX>(a.out_propagated + (size_t)t * N * DX, (size_t)i, xt[kk]);
 #ifdef BF_EXP_NOLL
-            const float ll = -0.5f * xt[0] * xt[0];
+            lh[kk] = -0.5f * xt[kk][0] * xt[kk][0];
 #else
-            const float ll = emission_log_prob<M>(xt, y, u_in, mc);
+            lh[kk] = emission_log_prob<M>(xt[kk], y, u_in, mc);
 #endif
-            lh[kk] = ll;
-            acc.add(ll, w_uni ? invN : a.W[i], xt);
+            wv[kk] = w_uni ? invN : a.W[i];
           }
         }
+        acc.template add_group<PU>(lh, wv, xt);
         // shift everything by PU particles: results in at the top, the next particles' state and noise down to slot 0
 #pragma unroll
         for (int k = 0; k < 4 - PU; ++k) llv[k] = llv[k + PU];

@@ -75,20 +75,36 @@ struct OnlineAcc {
     for (int k = 0; k < DX; ++k) sx[k] = 0.0f;
   }
   __device__ __forceinline__ void rescale(float nm) {   // nm >= m
-    float sc = (m == -INFINITY) ? 0.0f : __expf(m - nm);
+    float sc = (m == -INFINITY) ? 0.0f : mufu_ex2((m - nm) * 1.44269504088896340736f);
     s *= sc; s2 *= sc * sc;
 #pragma unroll
     for (int k = 0; k < DX; ++k) sx[k] *= sc;
     m = nm;
   }
-  __device__ __forceinline__ void add(float ll, float wprev, const float* x) {
-    if (ll > m) rescale(ll);
-    // statistics only (sum, ESS, mean): the fast exponential's ~1e-7 relative error is far inside their 1e-5 bar;
-    // the weights themselves are computed with expf in norm_weight*
-    float e = (ll == -INFINITY) ? 0.0f : __expf(ll - m) * wprev;
-    s += e; s2 += e * e;
+  // P particles at once: ONE test against the running maximum (and at most one rescale) for the group -- ptxas turns the
+  // rescale into predicated code, so it is paid whether taken or not.  Statistics only (sum, ESS, mean): MUFU.EX2's ~1e-7
+  // relative error is far inside their 1e-5 bar; the weights themselves use expf (norm_weight*).  The difference
+  // ll - m is formed first (exact for nearby values) and only then scaled by log2(e): log-likelihoods of size 1e3
+  // (R = 25e-6) would otherwise lose the digits the exponential needs.
+  template <int P>
+  __device__ __forceinline__ void add_group(const float* ll, const float* wprev, const float (*x)[DX]) {
+    float gm = ll[0];
 #pragma unroll
-    for (int k = 0; k < DX; ++k) sx[k] += e * x[k];
+    for (int p = 1; p < P; ++p) gm = fmaxf(gm, ll[p]);
+    if (gm > m) rescale(gm);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float e = (ll[p] == -INFINITY) ? 0.0f : mufu_ex2((ll[p] - m) * 1.44269504088896340736f) * wprev[p];
+      s += e; s2 = fmaf(e, e, s2);
+#pragma unroll
+      for (int k = 0; k < DX; ++k) sx[k] = fmaf(e, x[p][k], sx[k]);
+    }
+  }
+  __device__ __forceinline__ void add(float ll, float wprev, const float* x) {
+    float xx[1][DX];
+#pragma unroll
+    for (int k = 0; k < DX; ++k) xx[0][k] = x[k];
+    add_group<1>(&ll, &wprev, xx);
   }
   __device__ __forceinline__ void merge(float om, float os, float os2, const float* osx) {
     float nm = fmaxf(m, om);

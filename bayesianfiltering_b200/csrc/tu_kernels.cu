@@ -45,7 +45,8 @@ struct Fill {
 int BFK_NAME(resident, BF_GROUP)(const ModelConst& mc, BfKernelSet* k) { Fill f{k}; return bf_dispatch_model(mc, f); }
 
 #elif BF_TU_KIND == 3  // ---------------------------------------------------------------- Gaussian-sum filter
-#include "gsf_kernels.cuh"
+#include "ugsf_kernels.cuh"
+#include "agsf_kernels.cuh"
 namespace {
 struct Fill {
   BfKernelSet* k;
@@ -56,6 +57,8 @@ struct Fill {
     k->gsf_warp[1] = (const void*)k_gsf_warp<M, 2>;
     k->gsf_warp[2] = (const void*)k_gsf_warp<M, 4>;
     k->gsf_warp[3] = (const void*)k_gsf_warp<M, 8>;
+    if constexpr (M::DX <= 4) k->agsf = (const void*)k_agsf<M>;
+    if constexpr (M::DX <= 4) k->ugsf = (const void*)k_ugsf<M>;      // sigma points of the augmented state live in registers
     return 0;
   }
 };

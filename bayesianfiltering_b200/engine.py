@@ -248,7 +248,8 @@ class ShardedParticleFilterEngine(ParticleFilterEngine):
 class GaussianSumFilterEngine:
     """Owns a bf_gsf_handle: M components x B independent trials of one registry model."""
 
-    def __init__(self, host_model, num_components, num_trials=1, device=None, flags=0):
+    def __init__(self, host_model, num_components, num_trials=1, device=None, flags=0, unscented=None):
+        """unscented = (alpha, beta, kappa): the unscented Gaussian-sum filter (inference.py:379-456) instead of the EKF one."""
         self.lib = _lib.load()
         self.hm = host_model
         self.M, self.B = int(num_components), int(num_trials)
@@ -257,6 +258,9 @@ class GaussianSumFilterEngine:
         cfg = _lib.GsfConfig(self.M, self.B, self.device, int(flags))
         self.h = C.c_void_p()
         _lib.check(self.lib.bf_gsf_create(C.byref(host_model.desc), C.byref(cfg), C.byref(self.h)))
+        if unscented is not None:
+            a, b, k = (float(v) for v in unscented)
+            _lib.check(self.lib.bf_gsf_set_unscented(self.h, a, b, k))
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
@@ -337,6 +341,85 @@ class GaussianSumFilterEngine:
         self._keep = (ins, outs)
         _lib.check(self.lib.bf_gsf_run(self.h, C.byref(io), torch.cuda.current_stream(dev).cuda_stream))
         return res
+
+
+AGSF_OUTPUTS = {
+    # name: (io field, per-(trial,step) shape as a function of (M, L, dx), dtype)
+    "weights": ("out_weights", lambda M, L, dx: (M,), np.float32),
+    "means": ("out_means", lambda M, L, dx: (M, dx), np.float32),
+    "covariances": ("out_covs", lambda M, L, dx: (M, dx, dx), np.float32),
+    "log_likelihood": ("out_loglik", lambda M, L, dx: (), np.float32),
+    "pre_weights": ("out_pre_weights", lambda M, L, dx: (L,), np.float32),
+    "updated_means": ("out_updated_means", lambda M, L, dx: (L, dx), np.float32),
+    "ancestors": ("out_ancestors", lambda M, L, dx: (M,), np.int32),
+}
+
+
+class AugmentedGaussianSumFilterEngine:
+    """Owns a bf_agsf_handle: M components, each branched N1 x N2 ways per step, x B independent trials."""
+
+    def __init__(self, host_model, num_components, num_trials=1, opt_args=(0.1, 0.1), seed=0, device=None):
+        self.lib = _lib.load()
+        self.hm = host_model
+        self.M, self.N1, self.N2 = (int(v) for v in num_components)
+        self.L = self.M * self.N1 * self.N2
+        self.B = int(num_trials)
+        self.dx, self.dy = host_model.dx, host_model.dy
+        self.device = _default_device() if device is None else int(device)
+        cfg = _lib.AgsfConfig(self.M, self.N1, self.N2, self.B, self.device, 0, float(opt_args[0]), float(opt_args[1]),
+                              int(seed) & 0xFFFFFFFFFFFFFFFF)
+        self.h = C.c_void_p()
+        _lib.check(self.lib.bf_agsf_create(C.byref(host_model.desc), C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.bf_agsf_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def run_host(self, emissions, inputs=None, init_means=None, init_covs=None, z_iid=None, s_iid=None, res_u=None,
+                 outputs=("weights", "means", "covariances")):
+        """z_iid [M,dx,N1] / s_iid [M*N1,dx,N2] / res_u [M]: one set of draws reused at every step (the reference), or with a
+        leading T axis one per step (all three then)."""
+        em = np.asarray(emissions, dtype=np.float32)
+        per_trial = em.ndim == 3
+        T = em.shape[-2]
+        M, N1, N2, dx, B = self.M, self.N1, self.N2, self.dx, self.B
+        per_step = any(a is not None and np.ndim(a) == nd + 1 for a, nd in ((z_iid, 3), (s_iid, 3), (res_u, 1)))
+        TR = (T,) if per_step else ()
+        ins = dict(emissions=_np32(em, (B, T, self.dy) if per_trial else (T, self.dy), "emissions"), inputs=_np32(inputs, (T,), "inputs"),
+                   init_means=_np32(init_means, (B, M, dx), "init_means"), init_covs=_np32(init_covs, (B, M, dx, dx), "init_covs"),
+                   z_iid=_np32(z_iid, TR + (M, dx, N1), "z_iid"), s_iid=_np32(s_iid, TR + (M * N1, dx, N2), "s_iid"),
+                   res_u=_np32(res_u, TR + (M,), "res_u"))
+        if ins["init_means"] is None:
+            raise ValueError("init_means is required")
+        io = _lib.AgsfIO()
+        io.T, io.emissions_per_trial, io.rand_per_step = int(T), int(per_trial), int(per_step)
+        for k, v in ins.items():
+            setattr(io, k, _ptr(v))
+        res = {}
+        for name in outputs:
+            if name not in AGSF_OUTPUTS:
+                raise ValueError(f"unknown augmented-filter output {name!r}")
+            field, shape, dt = AGSF_OUTPUTS[name]
+            res[name] = _host_empty((B, T) + shape(M, self.L, dx), dt)
+            setattr(io, field, _ptr(res[name]))
+        _lib.check(self.lib.bf_agsf_run_host(self.h, C.byref(io)))
+        return res
+
+
+def optimal_resampling_device(weights, N, uniforms):
+    """utils.optimal_resampling (utils.py:216-244) on the GPU: torch CUDA tensors weights [M], uniforms [M] -> (idx [N], w [N])."""
+    import torch
+    lib = _lib.load()
+    w = weights.contiguous().float()
+    u = uniforms.contiguous().float()
+    idx = torch.empty(int(N), dtype=torch.int32, device=w.device)
+    wo = torch.empty(int(N), dtype=torch.float32, device=w.device)
+    _lib.check(lib.bf_optimal_resampling(w.data_ptr(), w.numel(), int(N), u.data_ptr(), idx.data_ptr(), wo.data_ptr(),
+                                         torch.cuda.current_stream(w.device).cuda_stream))
+    return idx, wo
 
 
 def cumsum_canonical(w):

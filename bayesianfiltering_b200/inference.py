@@ -31,6 +31,13 @@ class PosteriorGaussianSumFiltered(NamedTuple):
     predicted_covariances: Optional[Any] = None   # [num_components, ntime, state_dim, state_dim]
 
 
+class ParamsUKF(NamedTuple):
+    """Parameters of the unscented transform (gaussfiltax/inference.py:41-49): spread alpha, prior-knowledge beta, kappa."""
+    alpha: float = 1e-3
+    beta: float = 2
+    kappa: float = 0
+
+
 def _is_torch(a):
     return type(a).__module__.startswith("torch")
 
@@ -156,3 +163,108 @@ def gaussian_sum_filter(params: ParamsNLSSM, emissions, num_components: int = 1,
             torch.cuda.current_stream().synchronize()
         engine.close()
     return (post, extras) if return_extras else post
+
+
+def unscented_gaussian_sum_filter(params: ParamsNLSSM, uparams: ParamsUKF, emissions, num_components: int = 1, num_iter: int = 1,
+                                  inputs=None, *, init_means=None, init_covariances=None, init_weights=None, key=PRNGKey(0),
+                                  outputs=("weights", "means", "covariances", "predicted_means", "predicted_covariances"),
+                                  num_trials=None, device=None, return_extras: bool = False):
+    r"""Unscented Gaussian-sum filter (inference.py:379-456): every component is updated and predicted with the unscented
+    transform of the noise-augmented state (`_ukf_condition_on_nonadditive` :198-224, `_ukf_predict_nonadditive` :146-174)
+    instead of a linearisation.  Same arguments, defaults, returned fields and axis order as the reference; the keyword-only
+    extensions are those of `gaussian_sum_filter`.  Note the reference's default ParamsUKF (alpha = 1e-3) makes the sigma-point
+    weights +-5e5 and is unusable in float32 -- there as here; its drivers pass ParamsUKF(1, 0, 0)
+    (BOT_Experiment_script.py:108)."""
+    m, hm = zoo.host_model_from_params(params)
+    B = 1 if num_trials is None else int(num_trials)
+    batched = num_trials is not None
+    M = int(num_components)
+    if init_means is None:
+        rng = np.random.default_rng(key_to_seed(key))
+        L = np.linalg.cholesky(np.asarray(params.initial_covariance, dtype=np.float64))
+        z = rng.standard_normal((B, M, m.dx))
+        init_means = (np.asarray(params.initial_mean, dtype=np.float64) + z @ L.T).astype(np.float32)
+    engine = GaussianSumFilterEngine(hm, M, B, device, unscented=(uparams.alpha, uparams.beta, uparams.kappa))
+    run = engine.run if _is_torch(emissions) else engine.run_host
+    raw = run(emissions, inputs=inputs, init_means=init_means, init_covs=init_covariances, init_weights=init_weights,
+              outputs=tuple(outputs))
+    post = PosteriorGaussianSumFiltered(**{k: _swap(raw[k], batched) for k in PosteriorGaussianSumFiltered._fields if k in raw})
+    extras = {}
+    if "log_likelihood" in raw:
+        ll = raw["log_likelihood"]
+        extras["log_likelihood_increments"] = ll if batched else ll[0]
+        tot = ll.double().sum(dim=1) if _is_torch(ll) else ll.astype(np.float64).sum(axis=1)
+        extras["marginal_log_likelihood"] = tot if batched else tot[0]
+    if "mixture_mean" in raw:
+        extras["mixture_mean"] = raw["mixture_mean"] if batched else raw["mixture_mean"][0]
+    if _is_torch(emissions):
+        import torch
+        torch.cuda.current_stream().synchronize()
+    engine.close()
+    return (post, extras) if return_extras else post
+
+
+def _kalman_step(m, P, f, F_x, F_q, Q, q0, u, h, H_x, H_r, R, r0, y, *, device=None):
+    r"""One extended-Kalman predict + update of a single Gaussian (inference.py:107-120): returns
+    (ll, posterior_mean, posterior_cov).  `f` and `h` must be the registry functions of one model (zoo); the Jacobian
+    arguments F_x, F_q, H_x, H_r of the reference's signature are accepted and ignored -- the kernel has the model's analytic
+    Jacobians.  On the GPU this is `bf_gsf_step` with one component in predict-first order."""
+    from . import _lib
+    mf = getattr(f, "__bf_model__", None)
+    if mf is None or getattr(h, "__bf_model__", None) is not mf:
+        raise TypeError("f and h must be the dynamics / emission functions of one bayesianfiltering_b200.zoo model")
+    dx = mf.dx
+    hm = mf.host_model(q0=q0, Q=Q, r0=r0, R=R, m0=np.zeros(dx, np.float32), P0=np.eye(dx, dtype=np.float32))
+    eng = GaussianSumFilterEngine(hm, 1, 1, device, flags=_lib.GSF_PREDICT_FIRST)
+    out = eng.run_host(np.asarray(y, np.float32).reshape(1, -1), inputs=np.asarray([u], np.float32),
+                       init_means=np.asarray(m, np.float32).reshape(1, 1, dx), init_covs=np.asarray(P, np.float32).reshape(1, 1, dx, dx),
+                       outputs=("means", "covariances", "log_likelihood"))
+    eng.close()
+    return out["log_likelihood"][0, 0], out["means"][0, 0, 0], out["covariances"][0, 0, 0]
+
+
+def speedy_augmented_gaussian_sum_filter(params: ParamsNLSSM, emissions, num_components, rng_key=PRNGKey(0), num_iter: int = 1,
+                                         opt_args=(0.1, 0.1), inputs=None, *, init_means=None, init_covariances=None,
+                                         z_iid=None, s_iid=None, resample_uniforms=None, num_trials=None, device=None):
+    r"""Augmented Gaussian-sum filter (inference.py:621-812): `num_components = [M, N1, N2]`; per step every component is split
+    into N1 Gaussian particles of covariance `opt_args[0] P`, predicted, split into N2 of covariance `opt_args[1] P^-`,
+    updated, reweighted, and M survivors are drawn with `jr.choice(p=weights)` (the particle filter's resampler).
+
+    Returns `(PosteriorGaussianSumFiltered(weights [M,T], means [M,T,dx], covariances [M,T,dx,dx]), aux_outputs)` like the
+    reference; aux_outputs holds 'pre_weights' [T,M*N1*N2], 'updated_means' [T,M*N1*N2,dx] (its :775-776), plus
+    'ancestors' [T,M] and 'log_likelihood_increments' [T].  The reference reuses ONE set of normal / uniform draws at every
+    step (its keys are closure constants, :677, :718, :764); so does this: `z_iid` [M,dx,N1], `s_iid` [M*N1,dx,N2],
+    `resample_uniforms` [M] (drawn from `rng_key` when not supplied; give them a leading T axis for per-step draws)."""
+    from .engine import AugmentedGaussianSumFilterEngine
+    m, hm = zoo.host_model_from_params(params)
+    M, N1, N2 = (int(v) for v in num_components)
+    B = 1 if num_trials is None else int(num_trials)
+    batched = num_trials is not None
+    rng = np.random.default_rng(key_to_seed(rng_key))
+    if init_means is None:                                 # :795
+        L = np.linalg.cholesky(np.asarray(params.initial_covariance, dtype=np.float64))
+        init_means = (np.asarray(params.initial_mean, dtype=np.float64) + np.random.default_rng(0).standard_normal((B, M, m.dx)) @ L.T).astype(np.float32)
+    if z_iid is None:
+        z_iid = rng.standard_normal((M, m.dx, N1)).astype(np.float32)
+    if s_iid is None:
+        s_iid = rng.standard_normal((M * N1, m.dx, N2)).astype(np.float32)
+    if resample_uniforms is None:
+        resample_uniforms = np.random.default_rng(0).random(M, dtype=np.float32)      # jr.choice(jr.PRNGKey(0), ...), :764
+    eng = AugmentedGaussianSumFilterEngine(hm, (M, N1, N2), B, opt_args, key_to_seed(rng_key), device)
+    raw = eng.run_host(emissions, inputs=inputs, init_means=init_means, init_covs=init_covariances, z_iid=z_iid, s_iid=s_iid,
+                       res_u=resample_uniforms,
+                       outputs=("weights", "means", "covariances", "pre_weights", "updated_means", "ancestors", "log_likelihood"))
+    eng.close()
+    post = PosteriorGaussianSumFiltered(_swap(raw["weights"], batched), _swap(raw["means"], batched), _swap(raw["covariances"], batched))
+    pick = (lambda a: a) if batched else (lambda a: a[0])
+    aux = {"pre_weights": pick(raw["pre_weights"]), "updated_means": pick(raw["updated_means"]), "ancestors": pick(raw["ancestors"]),
+           "log_likelihood_increments": pick(raw["log_likelihood"])}
+    return post, aux
+
+
+def augmented_gaussian_sum_filter(params: ParamsNLSSM, emissions, num_components, rng_key=PRNGKey(0), num_iter: int = 1,
+                                  opt_args=(0.1, 0.1), inputs=None, **kw):
+    r"""inference.py:458-619: the same recursion written over `containers.GaussianComponent` trees (`_branches_from_tree1/2`,
+    containers.py:63-161).  Its branch means are `jr.multivariate_normal(key, mean, P - Delta)` = `mean + chol(P - Delta) z`,
+    i.e. for the same standard-normal draws exactly the speedy filter -- which is what runs."""
+    return speedy_augmented_gaussian_sum_filter(params, emissions, num_components, rng_key, num_iter, opt_args, inputs, **kw)

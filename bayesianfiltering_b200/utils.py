@@ -44,3 +44,17 @@ def _resample(weights, particles, key, *, uniforms=None, resampler="multinomial"
     idx = resample_ancestors(w, u, resampler).cpu().numpy()
     resampled = np.take(np.asarray(particles), idx, axis=0)
     return np.ones(n, dtype=np.float32) / n, resampled, keys[1]
+
+
+def optimal_resampling(weights, N, key, *, uniforms=None):
+    """utils.py:216-244 (Fearnhead & Clifford 2003): keep the largest weights exactly, resample the small ones with a common
+    threshold weight; returns (indices [N], weights [N]).  Runs `bf_optimal_resampling` on the GPU.  `uniforms` [M] replaces the
+    draw its `jr.choice(key, M, (M,), p=res_weights)` makes."""
+    import torch
+    from .engine import optimal_resampling_device
+    w = torch.as_tensor(np.asarray(weights, dtype=np.float32)).cuda()
+    if uniforms is None:
+        uniforms = np.random.default_rng(key_to_seed(key)).random(w.numel(), dtype=np.float32)
+    u = torch.as_tensor(np.asarray(uniforms, dtype=np.float32)).cuda()
+    idx, wo = optimal_resampling_device(w, int(N), u)
+    return idx.cpu().numpy(), wo.cpu().numpy()

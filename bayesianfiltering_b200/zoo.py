@@ -123,6 +123,17 @@ def sin1d(dx=1, w=10.0, c=1.0):
     return RegisteredModel(_lib.MODEL_SIN1D, "sin1d", dx, dx, 1, 1, [w, c])
 
 
+def msv(phi, beta, sigma, h0):
+    """Multivariate stochastic volatility with a switch (adaptive_experiment.py:47-57): f = Phi x + q,
+    h = u beta exp(x/sigma) * r + (1-u)(H0 x + r) with diagonal Phi, H0 (vectors of length d <= 3).  The emission noise is
+    multiplicative when u = 1; `.emission_log_prob` is the reference's `lmsvlp` with covariance M R M^T."""
+    phi, beta, h0 = (np.atleast_1d(np.asarray(a, np.float32)) for a in (phi, beta, h0))
+    d = phi.size
+    if not (beta.size == d and h0.size == d and 1 <= d <= 3):
+        raise ValueError("msv needs phi, beta, h0 of one length d <= 3")
+    return RegisteredModel(_lib.MODEL_MSV, "msv", d, d, d, d, np.concatenate([phi, beta, [np.float32(sigma)], h0]))
+
+
 def resolve(params):
     """The RegisteredModel behind a ParamsNLSSM / ParamsBPF, or raise: no untagged callables, no fallback."""
     f = getattr(params, "dynamics_function", None)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BF_ABI_VERSION 3
+#define BF_ABI_VERSION 4
 
 typedef enum bf_status {
   BF_OK = 0, BF_EINVAL = -1, BF_ECUDA = -2, BF_ENOMODEL = -3, BF_ENOMEM = -4, BF_ECOMM = -5
@@ -39,7 +39,9 @@ typedef enum bf_model_id {
   BF_MODEL_L63 = 3,   /* dx=dq=3 dy=1         theta = sigma rho beta dt c             */
   BF_MODEL_L96 = 4,   /* dx=dq=d dy=d/2       theta = F dt c1 c2                      */
   BF_MODEL_LG = 5,    /* dx=dq<=8 dy=dr<=8    theta = A[dx*dx] H[dy*dx] (row-major)   */
-  BF_MODEL_SIN1D = 6  /* dx=dq<=3 dy=1        theta = w c                             */
+  BF_MODEL_SIN1D = 6, /* dx=dq<=3 dy=1        theta = w c                             */
+  BF_MODEL_MSV = 7    /* dx=dq=dy=dr=d<=3     theta = Phi[d] beta[d] sigma H0[d] (diagonals): multiplicative emission
+                         noise, state-dependent emission covariance (adaptive_experiment.py:47-57) */
 } bf_model_id;
 
 typedef enum bf_resampler { BF_RESAMPLE_MULTINOMIAL = 0, BF_RESAMPLE_SYSTEMATIC = 1 } bf_resampler;
@@ -181,9 +183,68 @@ typedef struct bf_gsf_io {
 
 int bf_gsf_create(const bf_model_desc* model, const bf_gsf_config* cfg, bf_gsf_handle* out);
 int bf_gsf_run(bf_gsf_handle h, const bf_gsf_io* io, void* cuda_stream);
+int bf_gsf_step(bf_gsf_handle h, const bf_gsf_io* io, void* cuda_stream); /* bf_gsf_run with T forced to 1: one `_step` of the
+                                  scan (inference.py:333-365); with BF_GSF_PREDICT_FIRST and one component it is `_kalman_step` (:107-120) */
 int bf_gsf_run_host(bf_gsf_handle h, const bf_gsf_io* host_io);
+/* Switch the handle to the UNSCENTED Gaussian-sum filter (gaussfiltax/inference.py:379-456 `unscented_gaussian_sum_filter`,
+ * `_ukf_condition_on_nonadditive` :198-224, `_ukf_predict_nonadditive` :146-174, `utils._get_sigma_points` utils.py:247-254):
+ * every later bf_gsf_run / _step / _run_host propagates 2 (dx + dr) and 2 (dx + dq) sigma points of the noise-augmented
+ * state per component instead of linearising; alpha, beta, kappa are the fields of the reference's ParamsUKF (:41-49).
+ * Models with dx <= 4; constant noise covariances (Q_t / R_t must be NULL). */
+int bf_gsf_set_unscented(bf_gsf_handle h, float alpha, float beta, float kappa);
 int bf_gsf_kernel_launches(bf_gsf_handle h, int64_t* out);
 int bf_gsf_destroy(bf_gsf_handle h);
+
+/* ---------------------------------------------------------------- augmented Gaussian-sum filter
+ * gaussfiltax/inference.py:621-812 `speedy_augmented_gaussian_sum_filter` (and, for the same supplied draws, :458-619
+ * `augmented_gaussian_sum_filter` with gaussfiltax/containers.py:63-161 `_branches_from_tree1/2`): every component is split
+ * into N1 Gaussian particles of covariance a0 P, each is predicted (EKF, :51-70), split again into N2 of covariance a1 P^-,
+ * each of the M N1 N2 leaves is updated (EKF, :72-105), reweighted by its evidence, and M survivors are drawn with
+ * jax.random.choice(p = weights) -- the particle filter's resampler, bit-exact ancestors. */
+typedef struct bf_agsf_s* bf_agsf_handle;
+
+typedef struct bf_agsf_config {
+  int32_t num_components;   /* M   num_components[0] */
+  int32_t num_branch1;      /* N1  num_components[1] */
+  int32_t num_branch2;      /* N2  num_components[2] */
+  int32_t num_trials;       /* B independent filters */
+  int32_t device;
+  int32_t reserved;
+  float alpha1, alpha2;     /* opt_args: Delta = alpha1 P, Lambda = alpha2 P^-, both in [0,1)  (:666, :718) */
+  uint64_t seed;            /* Philox key for draws that are not supplied */
+} bf_agsf_config;
+
+typedef struct bf_agsf_io {
+  int32_t T;
+  int32_t emissions_per_trial;  /* 0: [T,dy] shared ; 1: [B,T,dy] */
+  int32_t rand_per_step;        /* 0: one set of draws reused at every step (the reference: its keys are closure constants,
+                                   :677, :718, :764) ; 1: z_iid / s_iid / res_u carry a leading T axis */
+  int32_t reserved;
+  const float* emissions;
+  const float* inputs;          /* [T] or NULL */
+  const float* init_means;      /* [B,M,dx]  (reference: MVN(m0,P0).sample(M, PRNGKey(0)), :795) */
+  const float* init_covs;       /* [B,M,dx,dx] or NULL (P0 replicated, :796) */
+  const float* z_iid;           /* [(T,)M,dx,N1]     standard normals of branch 1 (:679), or NULL (Philox) */
+  const float* s_iid;           /* [(T,)M*N1,dx,N2]  standard normals of branch 2 (:722), or NULL */
+  const float* res_u;           /* [(T,)M]           uniforms of jr.choice (:764), or NULL */
+  float* out_weights;           /* [B,T,M]        = 1/M (:768) */
+  float* out_means;             /* [B,T,M,dx]     */
+  float* out_covs;              /* [B,T,M,dx,dx]  */
+  float* out_loglik;            /* [B,T]          max + log(sum) of the leaf evidences */
+  float* out_pre_weights;       /* [B,T,M*N1*N2]  aux_outputs["pre_weights"]   (:776) */
+  float* out_updated_means;     /* [B,T,M*N1*N2,dx] aux_outputs["updated_means"] (:775) */
+  int32_t* out_ancestors;       /* [B,T,M]        leaf index of each survivor */
+} bf_agsf_io;
+
+int bf_agsf_create(const bf_model_desc* model, const bf_agsf_config* cfg, bf_agsf_handle* out);
+int bf_agsf_run(bf_agsf_handle h, const bf_agsf_io* io, void* cuda_stream);
+int bf_agsf_run_host(bf_agsf_handle h, const bf_agsf_io* host_io);
+int bf_agsf_destroy(bf_agsf_handle h);
+
+/* gaussfiltax/utils.py:216-244 `optimal_resampling` (Fearnhead & Clifford 2003): from M weights (DEVICE, 2 <= N <= M <= 4096)
+ * return N (index, weight) pairs -- the largest weights kept exactly, the rest resampled with a common threshold weight.
+ * u [M]: the uniforms of its jr.choice(key, M, (M,), p=res_weights). */
+int bf_optimal_resampling(const float* w, int32_t M, int32_t N, const float* u, int32_t* idx_out, float* w_out, void* cuda_stream);
 
 /* ---------------------------------------------------------------- stand-alone resampler pieces */
 /* cdf[i] = inclusive prefix sum of w in lax.associative_scan order; bit-exact vs oracle/scan.py. */

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in bfilt.h but not exported by libbfilt.so"
         assert name in bound, f"{name} declared in bfilt.h but not bound in _lib.SYMBOLS"
-    assert lib.bf_abi_version() == 3
+    assert lib.bf_abi_version() == 4
 
 
 def test_no_torch_types_in_the_abi():

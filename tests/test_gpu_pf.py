@@ -122,29 +122,39 @@ def test_pf_stepwise_parity_many_tiles(name, T, N, thr, res):
 @pytest.mark.parametrize("path", ["resident", "streamed"])
 @pytest.mark.parametrize("gold", ["pf_ungm", "pf_bot2", "pf_ungm_sys", "pf_lg3"])
 def test_pf_golden_fixtures(gold, path):
-    """Whole trajectories against the committed oracle outputs (tests/golden/make_golden.py)."""
+    """The committed oracle trajectories (tests/golden/make_golden.py).  Linear-Gaussian: the whole trajectory at the
+    north_star tolerance (no error growth).  Nonlinear models (UNGM's slope reaches 25, BOT under R = 25e-6) amplify a
+    one-ulp difference into different resampling decisions within a few steps, so there every step is run from the
+    fixture's own carry (teacher-forced) and held to 1e-5 -- the same check the reference-generated fixtures get
+    (tests/test_gpu_ref.py)."""
     from tests.golden.make_golden import PF_CASES
     cname, T, N, thr, res = PF_CASES[gold]
     g = np.load(os.path.join(GOLD, gold + ".npz"))
     c = case(cname)
+    if not cname.startswith("lg"):
+        from tests.test_gpu_ref import pf_teacher_forced
+        gg = {k: g[k] for k in g.files}
+        gg.update(r0=c.r0, R=c.R)
+
+        class G(dict):
+            files = property(lambda self: list(self.keys()))
+        assert pf_teacher_forced(c.host_model(), c.omodel, G(gg), path, thr, res) > 0
+        return
     u = g["inputs"] if "inputs" in g.files else None
     eng = _engine(c, N, 1, thr, res, path)
     out = eng.run_host(g["emissions"], inputs=u, init_particles=g["x0"], noise=g["noise"], resample_u=g["res_u"],
                        outputs=ALL_OUT)
     eng.close()
     assert np.array_equal(out["resampled"][0], g["resampled"])
-    # linear-Gaussian: no error growth -> the north_star tolerance on the whole trajectory
-    tol = 1e-5 if cname.startswith("lg") else 2e-3
+    tol = 1e-5
     close(out["log_likelihood"][0], g["loglik_inc"], rtol=tol, atol_scale=tol, what="loglik")
     close(out["ess"][0], g["ess"], rtol=10 * tol, atol_scale=10 * tol, what="ess")
     close(out["means"][0], g["means"], rtol=10 * tol, atol_scale=10 * tol, what="means")
     # reference axis order: weights [N,T], particles [N,T,dx]  (inference.py:1378)
     W = np.swapaxes(out["weights"][0], 0, 1)
     X = np.swapaxes(out["particles"][0], 0, 1)
-    bad = ~np.isclose(X, g["particles"], rtol=tol, atol=tol * np.abs(g["particles"]).max())
-    assert bad.mean() < (0.0 if cname.startswith("lg") else 0.01) + 1e-12, f"{bad.mean():.4f} of particle entries differ"
-    badw = ~np.isclose(W, g["weights"], rtol=10 * tol, atol=10 * tol * np.abs(g["weights"]).max())
-    assert badw.mean() < (0.0 if cname.startswith("lg") else 0.01) + 1e-12
+    close(X, g["particles"], rtol=tol, atol_scale=tol, what="particles")
+    close(W, g["weights"], rtol=10 * tol, atol_scale=10 * tol, what="weights")
 
 
 def test_reference_entry_point_shapes_and_axis_order():
@@ -402,3 +412,56 @@ def test_large_streamed_properties_2pow22():
     for t in (0, T - 1):
         anc = oscan.resample_ancestors(out["norm_weights"][0, t], ru[t], "systematic")
         assert np.array_equal(out["ancestors"][0, t], anc)
+
+
+@pytest.mark.parametrize("res", ["systematic", "multinomial"])
+def test_headline_size_step_against_oracle_2pow24(res):
+    """The bench configuration's own size, N = 2^24 (147 CTAs x 56 tiles per CTA, the staged tile-sum scan, tau windows at
+    full size), general instantiation with every per-particle output: two steps on the bearings-only model, each
+    re-derived by the vectorised oracle from the kernel's previous state -- ancestors bit-exact, propagated particles
+    and normalised weights at 1e-5, log-likelihood increment, ESS and weighted mean."""
+    c = case("bot2")
+    T, N = 2, 1 << 24
+    _, ys = c.simulate(T, 21)
+    u = c.inputs(T)
+    x0, noise, ru = c.pf_randomness(T, N, 22, res)
+    eng = _engine(c, N, 1, 1.0, res, "streamed")
+    out = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru,
+                       outputs=("propagated", "norm_weights", "ancestors", "log_likelihood", "ess", "means", "resampled", "final_particles"))
+    eng.close()
+    x, w = x0, np.full(N, np.float32(1.0) / np.float32(N), np.float32)
+    f8 = lambda v: np.asarray(v, dtype=np.float64)
+    for t in range(T):
+        o = opf.pf_step(c.omodel, x, w, ys[t], u[t], noise[t], ru[t], c.r0, c.R, 1.0, res)
+        o8 = opf.pf_step(c.omodel, f8(x), f8(w), f8(ys[t]), u[t], f8(noise[t]), ru[t], c.r0, c.R, 1.0, res)
+        close(out["propagated"][0, t], o["propagated"], what=f"propagated t={t}")
+        close_cond(out["norm_weights"][0, t], o["norm_weights"], o8["norm_weights"], what=f"norm_weights t={t}")
+        ll_scale = max(1.0, abs(float(np.max(o["lls"]))), abs(float(o["loglik_inc"])))
+        assert abs(float(out["log_likelihood"][0, t]) - float(o["loglik_inc"])) <= 1e-5 * ll_scale + 8 * abs(float(o["loglik_inc"]) - float(o8["loglik_inc"]))
+        nw8 = f8(out["norm_weights"][0, t])
+        close(out["ess"][0, t], 1.0 / np.sum(nw8 * nw8), rtol=1e-4, atol_scale=1e-4, what=f"ess t={t}")
+        close(out["means"][0, t], np.sum(nw8[:, None] * f8(out["propagated"][0, t]), axis=0), rtol=1e-4, atol_scale=1e-4, what=f"mean t={t}")
+        assert out["resampled"][0, t] == 1
+        anc = oscan.resample_ancestors(out["norm_weights"][0, t], ru[t], res)
+        assert np.array_equal(out["ancestors"][0, t], anc), f"ancestors differ at t={t}"
+        x = out["propagated"][0, t][anc]
+        del o, o8
+    assert np.array_equal(out["final_particles"][0], x)
+
+
+def test_lean_equals_general_at_headline_size_2pow24(monkeypatch):
+    """lean == general, bit for bit, at the size the bench runs (the lean kernel emits summaries only)."""
+    c = case("bot2")
+    T, N = 5, 1 << 24
+    _, ys = c.simulate(T, 23)
+    u = c.inputs(T)
+    outs = ("means", "log_likelihood", "ess", "resampled")
+    res = {}
+    for lean in ("1", "0"):
+        monkeypatch.setenv("BF_PF_LEAN", lean)
+        eng = _engine(c, N, 1, 1.0, "systematic", "streamed", seed=5)
+        res[lean] = eng.run_host(ys, inputs=u, outputs=outs)
+        eng.close()
+    for k in outs:
+        assert np.array_equal(res["1"][k], res["0"][k]), k
+    assert np.all(np.isfinite(res["1"]["log_likelihood"])) and np.all(res["1"]["resampled"] == 1)
