@@ -27,7 +27,7 @@ class ModelDesc(C.Structure):
 class PfConfig(C.Structure):
     _fields_ = [("num_particles", C.c_int64), ("num_trials", C.c_int32), ("ess_threshold", C.c_float),
                 ("resampler", C.c_int32), ("path", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32),
-                ("reserved", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32)]
+                ("trial_offset", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32)]
 
 
 class PfIO(C.Structure):
@@ -98,6 +98,7 @@ SYMBOLS = [
                                 C.c_void_p, C.c_void_p]),
     ("bf_ssm_sample", C.c_int, [C.POINTER(ModelDesc), C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("bf_measure_fp32_peak", C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     ("bf_trim_memory", C.c_int, [C.c_int32]),
     ("bf_last_error", C.c_char_p, []),
     ("bf_abi_version", C.c_int, []),

@@ -507,6 +507,7 @@ struct PfRun {
     PfResidentArgs a;
     a.N = h->N; a.T = io->T; a.t_offset = io->t_offset; a.resume = io->resume; a.resampler = h->cfg.resampler;
     a.emissions_per_trial = io->emissions_per_trial; a.ess_threshold = h->cfg.ess_threshold; a.seed = h->cfg.seed;
+    a.trial_offset = h->cfg.trial_offset;
     a.emissions = io->emissions; a.inputs = io->inputs; a.init_particles = io->init_particles; a.init_weights = io->init_weights;
     a.noise = io->noise; a.res_u = io->resample_u;
     a.carry_x = h->carry_x.as<float>(); a.carry_w = h->carry_w.as<float>(); a.carry_uniform = h->carry_uniform.as<int>();
@@ -569,7 +570,11 @@ struct PfRun {
     }
     const int world = h->world, rank = h->rank;
     const size_t part_bytes = (((size_t)2 * world * grid * sizeof(PfPartial)) + 63) & ~(size_t)63;   // + ticket counter + folded stats
-    CUDA_OK(h->partials.ensure(part_bytes + 256));
+    {   // sized for the largest grid any instantiation can have (one CTA per SM slot), so that a later call with another
+        // kernel variant never re-allocates it under work still in flight on a caller's non-blocking stream
+      const size_t part_max = (((size_t)2 * world * std::max(grid, 2 * h->nsm) * sizeof(PfPartial)) + 63) & ~(size_t)63;
+      CUDA_OK(h->partials.ensure(std::max(part_bytes, part_max) + 256));
+    }
     const int grid_s = (int)std::min<int64_t>(((int64_t)N + 255) / 256, (int64_t)h->nsm * 8);
     const int Ng = N * world;
     int log2n = -1, log2ng = -1;
@@ -613,7 +618,7 @@ struct PfRun {
       float* cw = h->carry_w.as<float>() + (size_t)b * N;
       PfFusedArgs a;
       memset(&a, 0, sizeof a);
-      a.N = N; a.T = T; a.t_offset = io->t_offset; a.trial = b; a.B = B;
+      a.N = N; a.T = T; a.t_offset = io->t_offset; a.trial = h->cfg.trial_offset + b; a.B = B;
       a.resume = io->resume; a.w_uniform0 = io->init_weights ? 0 : 1; a.resampler = h->cfg.resampler;
       a.ntiles = ntiles; a.tiles_per_cta = tpc; a.log2n = log2n;
       a.ess_threshold = h->cfg.ess_threshold; a.seed = h->cfg.seed;
@@ -622,7 +627,7 @@ struct PfRun {
       if (io->resume) a.x_init = cx;
       else if (io->init_particles) a.x_init = io->init_particles + (size_t)b * N * DX;
       else {
-        if ((rck = launch_init_particles(DX, grid_s, s, h->mc, cx, N, h->cfg.seed, b, rank * N))) return rck;
+        if ((rck = launch_init_particles(DX, grid_s, s, h->mc, cx, N, h->cfg.seed, h->cfg.trial_offset + b, rank * N))) return rck;
         h->launches++;
         a.x_init = cx;
       }
@@ -1297,6 +1302,80 @@ extern "C" int bf_resample(const float* w, const float* u, int32_t* anc, int64_t
   return BF_OK;
 }
 
+// ========================================================================================== L96 sampler, FP32 peak
+// NonlinearSSM.sample (gaussfiltax/models.py:240-289) for the large-state Lorenz-96 model (diagonal Q, R, full P0 through
+// its Cholesky factor); one thread per trial, Philox draws (the small models go through k_ssm_sample<M>).
+__global__ void k_l96_sample(const LargeConst* __restrict__ lcp, const float* __restrict__ LP0, int B, int T, unsigned long long seed,
+                             float* __restrict__ states, float* __restrict__ emissions) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const LargeConst& lc = *lcp;
+  const int dx = lc.dx, dy = lc.dy;
+  float x[GL_MAXDX], xn[GL_MAXDX], z[GL_MAXDX];
+  for (int i = 0; i < dx; i += 4) { float n4[4]; philox_normals<4>(seed, 21u, 0u, (uint32_t)b, (uint64_t)(i >> 2), n4); for (int k = 0; k < 4 && i + k < dx; ++k) z[i + k] = n4[k]; }
+  for (int i = 0; i < dx; ++i) { float s = lc.m0[i]; for (int c = 0; c <= i; ++c) s += LP0[i * dx + c] * z[c]; x[i] = s; }
+  for (int t = 0; t < T; ++t) {
+    const size_t bt = (size_t)b * T + t;
+    if (t > 0) {
+      for (int i = 0; i < dx; i += 4) { float n4[4]; philox_normals<4>(seed, 22u, (uint32_t)t, (uint32_t)b, (uint64_t)(i >> 2), n4); for (int k = 0; k < 4 && i + k < dx; ++k) z[i + k] = n4[k]; }
+      for (int i = 0; i < dx; ++i) {
+        const float xm1 = x[(i + dx - 1) % dx], xm2 = x[(i + dx - 2) % dx], xp1 = x[(i + 1) % dx];
+        xn[i] = x[i] + lc.dt * ((xp1 - xm2) * xm1 - x[i] + lc.F) + lc.q0[i] + sqrtf(lc.qd[i]) * z[i];
+      }
+      for (int i = 0; i < dx; ++i) x[i] = xn[i];
+    }
+    for (int i = 0; i < dy; i += 4) { float n4[4]; philox_normals<4>(seed, 23u, (uint32_t)t, (uint32_t)b, (uint64_t)(i >> 2), n4); for (int k = 0; k < 4 && i + k < dy; ++k) z[i + k] = n4[k]; }
+    for (int i = 0; i < dx; ++i) states[bt * dx + i] = x[i];
+    for (int j = 0; j < dy; ++j) { const float xs = x[2 * j]; emissions[bt * dy + j] = lc.c1 * xs + lc.c2 * xs * xs + lc.r0[j] + sqrtf(lc.rd[j]) * z[j]; }
+  }
+}
+
+// FP32 (non-tensor) peak: 8 independent FFMA chains per thread, no memory traffic.  The denominator of the Gaussian-sum
+// filters' FP32-pipe fractions (SURVEY 8(d) asks for a MEASURED figure next to the HBM one).
+__global__ void __launch_bounds__(1024) k_fp32_peak(float* out, int iters, float a, float b) {
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = (float)(threadIdx.x + k);
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], a, b);
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += v[k];
+  if (s == 12345.678f) out[0] = s;
+}
+
+extern "C" int bf_measure_fp32_peak(int32_t device, double* tflops) {
+  if (!tflops) return fail(BF_EINVAL, "NULL argument");
+  CUDA_OK(cudaSetDevice(device));
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+  float* d;
+  CUDA_OK(cudaMalloc(&d, 4));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+  const int iters = 1 << 14, blocks = nsm * 2;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CUDA_OK(cudaEventRecord(e0, 0));
+    k_fp32_peak<<<blocks, 1024>>>(d, iters, 0.999f, 0.001f);
+    CUDA_OK(cudaEventRecord(e1, 0));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 64.0 * (double)iters * 1024.0 * (double)blocks;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops = best;
+  return BF_OK;
+}
+
 // ========================================================================================== model eval / sampler
 extern "C" int bf_model_eval(const bf_model_desc* model, int32_t what, int64_t n, const float* x, const float* aux, float u,
                              float* out, void* stream) {
@@ -1318,6 +1397,35 @@ extern "C" int bf_model_eval(const bf_model_desc* model, int32_t what, int64_t n
 extern "C" int bf_ssm_sample(const bf_model_desc* model, int32_t B, int32_t T, const float* inputs, uint64_t seed,
                              const float* z0, const float* q_noise, const float* r_noise, float* states, float* emissions,
                              void* stream) {
+  if (model && model->model_id == BF_MODEL_L96) {       // large-state model: Philox draws only
+    if (B < 1 || T < 1 || !states || !emissions) return fail(BF_EINVAL, "bad B/T or NULL output");
+    if (z0 || q_noise || r_noise || inputs) return fail(BF_EINVAL, "the Lorenz-96 generator draws its own noise and takes no inputs");
+    const int dx = model->dx, dy = model->dy;
+    if (dx < 4 || dx > GL_MAXDX || (dx & 1) || dy != dx / 2 || model->n_theta != 4) return fail(BF_EINVAL, "L96 needs even 4 <= dx <= %d, dy = dx/2", GL_MAXDX);
+    LargeConst* lch = new (std::nothrow) LargeConst();
+    if (!lch) return fail(BF_ENOMEM, "out of host memory");
+    memset(lch, 0, sizeof *lch);
+    lch->dx = dx; lch->dy = dy; lch->F = model->theta[0]; lch->dt = model->theta[1]; lch->c1 = model->theta[2]; lch->c2 = model->theta[3];
+    for (int i = 0; i < dx; ++i) { lch->q0[i] = model->q0[i]; lch->qd[i] = model->Q[i * dx + i]; lch->m0[i] = model->m0[i]; }
+    for (int i = 0; i < dy; ++i) { lch->r0[i] = model->r0[i]; lch->rd[i] = model->R[i * dy + i]; }
+    std::vector<float> L((size_t)dx * dx, 0.0f);
+    for (int i = 0; i < dx; ++i) for (int j = 0; j <= i; ++j) {
+      double sacc = model->P0[i * dx + j];
+      for (int k = 0; k < j; ++k) sacc -= (double)L[i * dx + k] * L[j * dx + k];
+      L[i * dx + j] = (i == j) ? (float)sqrt(std::max(sacc, 0.0)) : (float)(sacc / L[j * dx + j]);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char* dbuf;
+    CUDA_OK(cudaMallocAsync((void**)&dbuf, sizeof(LargeConst) + L.size() * 4, s));
+    CUDA_OK(cudaMemcpyAsync(dbuf, lch, sizeof(LargeConst), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(dbuf + sizeof(LargeConst), L.data(), L.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));        // the host staging buffers go out of scope
+    delete lch;
+    k_l96_sample<<<(B + 63) / 64, 64, 0, s>>>((const LargeConst*)dbuf, (const float*)(dbuf + sizeof(LargeConst)), B, T, seed, states, emissions);
+    LAUNCH_OK();
+    CUDA_OK(cudaFreeAsync(dbuf, s));
+    return BF_OK;
+  }
   ModelConst mc;
   int rc = build_model_const(model, &mc);
   if (rc) return rc;

@@ -44,7 +44,8 @@ struct GsfLargeArgs {
 };
 
 static inline size_t gsf_large_smem_bytes(int dx, int dy, int M) {
-  const size_t per_warp = (size_t)dx * dx + 2 * (size_t)dy * dx + 2 * (size_t)dy * dy + 4 * (size_t)dx + 4 * (size_t)dy + 8;
+  // rounded to 4 floats: every warp's workspace (its P is read with 128-bit accesses) stays 16-byte aligned for any even dx
+  const size_t per_warp = ((size_t)dx * dx + 2 * (size_t)dy * dx + 2 * (size_t)dy * dy + 4 * (size_t)dx + 4 * (size_t)dy + 8 + 3) & ~(size_t)3;
   return (GL_WARPS * per_warp + (size_t)M + 64) * sizeof(float);
 }
 
@@ -57,7 +58,7 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
   const LargeConst& lc = *a.lc;
   const int dx = DXT ? DXT : lc.dx, dy = DXT ? DXT / 2 : lc.dy, M = a.M, T = a.T, b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t per_warp = (size_t)dx * dx + 2 * (size_t)dy * dx + 2 * (size_t)dy * dy + 4 * (size_t)dx + 4 * (size_t)dy + 8;
+  const size_t per_warp = ((size_t)dx * dx + 2 * (size_t)dy * dx + 2 * (size_t)dy * dy + 4 * (size_t)dx + 4 * (size_t)dy + 8 + 3) & ~(size_t)3;
   float* ws = smem + warp * per_warp;
   float* P = ws;                         // [dx,dx]
   float* X = P + dx * dx;                // [dy,dx]  H P, then X = solve(S', H P)  (K = X^T)
@@ -137,53 +138,109 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
         dv[j] = y[j] - (lc.c1 * xs + lc.c2 * xs * xs + lc.r0[j]);
       }
       __syncwarp();
-      for (int idx = lane; idx < dy * dx; idx += 32) {           // H P
-        const int j = idx / dx, c = idx - j * dx;
-        X[idx] = hv[j] * P[(2 * j) * dx + c];
-      }
-      __syncwarp();
-      for (int idx = lane; idx < dy * dy; idx += 32) {           // S = H_r R H_r^T + H P H^T ; S' = S + 1e-6
-        const int j = idx / dy, k = idx - j * dy;
-        const float s = ((j == k) ? rdp[j * rds] : 0.0f) + X[j * dx + 2 * k] * hv[k];
-        S[idx] = s; Sj[idx] = s + jitter;
-      }
-      __syncwarp();
-      // LU with partial pivoting of S', applied to the dx right-hand sides in X   (jnp.linalg.solve, utils.py:259)
-      for (int k = 0; k < dy; ++k) {
-        float best = -1.0f; int bi = k;
-        for (int r = k + lane; r < dy; r += 32) { const float v = fabsf(Sj[r * dy + k]); if (v > best) { best = v; bi = r; } }
+      if constexpr (DXT == 40) {
+        // ---- K = solve(S + 1e-6, H P)^T in REGISTERS.  A lane owns columns `lane` and `lane + 32` of the 20 x 60 matrix
+        // [S' | H P] (columns 0-19: S', 20-59: the 40 right-hand sides), 20 rows each.  S' = S + 1e-6 11^T is symmetric
+        // positive definite, so Gaussian elimination needs no pivoting (growth factor 1; jnp.linalg.solve's partial
+        // pivoting changes the rounding, not the conditioning).  Multipliers and pivots travel by warp shuffle; every index
+        // is a compile-time constant after unrolling.  This replaces a shared-memory LU (4 instructions per FMA) that was
+        // half of the kernel's instructions.
+        float c0[20], c1[20];
+        const bool sc = lane < 20;                       // slot 0 holds an S' column (else the right-hand side lane - 20)
+        const int col0 = sc ? 2 * lane : lane - 20;      // column of P behind slot 0
+        const int col1 = (lane < 28) ? lane + 12 : 0;    // slot 1: right-hand side lane + 12 (lanes 28-31: idle copy)
+        const float hl = sc ? hv[lane] : 1.0f;
+        const float rl = sc ? rdp[lane * rds] : 0.0f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ob = __shfl_xor_sync(BF_FULL, best, o); const int oi = __shfl_xor_sync(BF_FULL, bi, o);
-          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        for (int j = 0; j < 20; ++j) {
+          const float hj = hv[j];
+          float v0 = hj * P[(2 * j) * 40 + col0];          // (H P)[j][col0]
+          c1[j] = hj * P[(2 * j) * 40 + col1];
+          if (sc) {
+            v0 = ((j == lane) ? rl : 0.0f) + v0 * hl;      // S = H_r R H_r^T + H P H^T   (:99)
+            S[j * 20 + lane] = v0;
+            v0 += jitter;                                  // psd_solve: + 1e-6 on EVERY element
+          }
+          c0[j] = v0;
         }
-        if (bi != k) {
-          for (int c = lane; c < dy; c += 32) { const float t0 = Sj[k * dy + c]; Sj[k * dy + c] = Sj[bi * dy + c]; Sj[bi * dy + c] = t0; }
-          for (int c = lane; c < dx; c += 32) { const float t0 = X[k * dx + c]; X[k * dx + c] = X[bi * dx + c]; X[bi * dx + c] = t0; }
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+          const float rp = __frcp_rn(__shfl_sync(BF_FULL, c0[k], k));
+#pragma unroll
+          for (int r = k + 1; r < 20; ++r) {
+            const float l = __shfl_sync(BF_FULL, c0[r], k) * rp;
+            c0[r] = fmaf(-l, c0[k], c0[r]);
+            c1[r] = fmaf(-l, c1[k], c1[r]);
+          }
+        }
+#pragma unroll
+        for (int k = 19; k >= 0; --k) {                    // back substitution on the right-hand-side slots only
+          const float rp = __frcp_rn(__shfl_sync(BF_FULL, c0[k], k));
+          float a0 = c0[k], a1 = c1[k];
+#pragma unroll
+          for (int j = k + 1; j < 20; ++j) {
+            const float uu = __shfl_sync(BF_FULL, c0[k], j);      // U[k][j]
+            a0 = fmaf(-uu, c0[j], a0);
+            a1 = fmaf(-uu, c1[j], a1);
+          }
+          if (!sc) c0[k] = a0 * rp;
+          c1[k] = a1 * rp;
+        }
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {                     // X = solve(S', H P)  (K = X^T) back to shared memory for the tiled products
+          if (!sc) X[k * 40 + lane - 20] = c0[k];
+          if (lane < 28) X[k * 40 + lane + 12] = c1[k];
         }
         __syncwarp();
-        const float piv = Sj[k * dy + k];
-        for (int r = k + 1 + lane; r < dy; r += 32) lr[r] = Sj[r * dy + k] / piv;
-        __syncwarp();
-        // rank-1 update of the trailing block of S' and of all of X: a lane owns COLUMNS of the concatenation
-        // [S'(:, k+1:) | X] and walks down the rows -- no index division in the loop (it was 38 % of the kernel's
-        // instructions when the block was flattened over (row, column)), the pivot-row element stays in a register
-        const int ncs = dy - k - 1;
-        for (int cc = lane; cc < ncs + dx; cc += 32) {
-          float* col = (cc < ncs) ? (Sj + k + 1 + cc) : (X + (cc - ncs));
-          const int stride = (cc < ncs) ? dy : dx;
-          const float top = col[k * stride];
-          for (int r = k + 1; r < dy; ++r) col[r * stride] -= lr[r] * top;
+      } else {
+      for (int idx = lane; idx < dy * dx; idx += 32) {           // H P
+          const int j = idx / dx, c = idx - j * dx;
+          X[idx] = hv[j] * P[(2 * j) * dx + c];
         }
         __syncwarp();
-      }
-      for (int k = dy - 1; k >= 0; --k) {                        // back substitution, one column of X per lane
-        for (int c = lane; c < dx; c += 32) {
-          float s = X[k * dx + c];
-          for (int j = k + 1; j < dy; ++j) s -= Sj[k * dy + j] * X[j * dx + c];
-          X[k * dx + c] = s / Sj[k * dy + k];
+        for (int idx = lane; idx < dy * dy; idx += 32) {           // S = H_r R H_r^T + H P H^T ; S' = S + 1e-6
+          const int j = idx / dy, k = idx - j * dy;
+          const float s = ((j == k) ? rdp[j * rds] : 0.0f) + X[j * dx + 2 * k] * hv[k];
+          S[idx] = s; Sj[idx] = s + jitter;
         }
         __syncwarp();
+        // LU with partial pivoting of S', applied to the dx right-hand sides in X   (jnp.linalg.solve, utils.py:259)
+        for (int k = 0; k < dy; ++k) {
+          float best = -1.0f; int bi = k;
+          for (int r = k + lane; r < dy; r += 32) { const float v = fabsf(Sj[r * dy + k]); if (v > best) { best = v; bi = r; } }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(BF_FULL, best, o); const int oi = __shfl_xor_sync(BF_FULL, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+          }
+          if (bi != k) {
+            for (int c = lane; c < dy; c += 32) { const float t0 = Sj[k * dy + c]; Sj[k * dy + c] = Sj[bi * dy + c]; Sj[bi * dy + c] = t0; }
+            for (int c = lane; c < dx; c += 32) { const float t0 = X[k * dx + c]; X[k * dx + c] = X[bi * dx + c]; X[bi * dx + c] = t0; }
+          }
+          __syncwarp();
+          const float piv = Sj[k * dy + k];
+          for (int r = k + 1 + lane; r < dy; r += 32) lr[r] = Sj[r * dy + k] / piv;
+          __syncwarp();
+          // rank-1 update of the trailing block of S' and of all of X: a lane owns COLUMNS of the concatenation
+          // [S'(:, k+1:) | X] and walks down the rows -- no index division in the loop (it was 38 % of the kernel's
+          // instructions when the block was flattened over (row, column)), the pivot-row element stays in a register
+          const int ncs = dy - k - 1;
+          for (int cc = lane; cc < ncs + dx; cc += 32) {
+            float* col = (cc < ncs) ? (Sj + k + 1 + cc) : (X + (cc - ncs));
+            const int stride = (cc < ncs) ? dy : dx;
+            const float top = col[k * stride];
+            for (int r = k + 1; r < dy; ++r) col[r * stride] -= lr[r] * top;
+          }
+          __syncwarp();
+        }
+        for (int k = dy - 1; k >= 0; --k) {                        // back substitution, one column of X per lane
+          for (int c = lane; c < dx; c += 32) {
+            float s = X[k * dx + c];
+            for (int j = k + 1; j < dy; ++j) s -= Sj[k * dy + j] * X[j * dx + c];
+            X[k * dx + c] = s / Sj[k * dy + k];
+          }
+          __syncwarp();
+        }
       }
       if constexpr (DXT == 40) {
         // register tiles: lane = (row group of 5) x (column group): 25 / 50 accumulators, 10 / 15 loads per 25 / 50 FMAs

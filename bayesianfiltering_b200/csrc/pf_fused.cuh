@@ -1073,6 +1073,17 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     lap(1);
     if (!(a.phases & PF_PH_C)) break;
 
+    if (!(a.phases & PF_PH_B)) {
+      // C-only launch (nccl transport): phase B ran in ANOTHER launch, whose shared memory is gone -- rebuild the chunk tree
+      // sums and first weights from the normalised weights it left in E (same additions, same bits)
+      for (int q = warp; q < nchunk_cta; q += CW) {
+        const float4 w4 = *reinterpret_cast<const float4*>(a.E + cta_base + 128 * q + lane * 4);
+        const float v[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float cs = chunk_tree_sum(v);
+        if (lane == 0) { s_wsum[q] = cs; s_v0[q] = v[0]; }
+      }
+      __syncthreads();
+    }
     // ------------------------------------------------------------------ phase C1 (CTA 0; every rank of a sharded filter)
     if (blockIdx.x == 0) {
       if (a.stage_ts) {                                // all the loads in flight at once: one L2 latency instead of ten

@@ -11,6 +11,7 @@
 
 struct PfResidentArgs {
   int N, T, t_offset, resume, resampler, emissions_per_trial;
+  int trial_offset;                  // global index of trial 0 (Philox counters)
   float ess_threshold;
   unsigned long long seed;
   const float* emissions; const float* inputs;
@@ -87,7 +88,7 @@ k_pf_resident(const __grid_constant__ ModelConst mc, const __grid_constant__ PfR
         for (int k = 0; k < DX; ++k) Xa[i * DX + k] = x0[(size_t)i * DX + k];
       } else {
         float z[DX];
-        philox_normals<DX>(a.seed, BF_STREAM_INIT, 0u, (uint32_t)b, (uint64_t)i, z);
+        philox_normals<DX>(a.seed, BF_STREAM_INIT, 0u, (uint32_t)(a.trial_offset + b), (uint64_t)i, z);
 #pragma unroll
         for (int r = 0; r < DX; ++r) {
           float s = mc.m0[r];
@@ -121,7 +122,7 @@ k_pf_resident(const __grid_constant__ ModelConst mc, const __grid_constant__ PfR
         for (int k = 0; k < DQ; ++k) q[k] = np_[k];
       } else {
         float z[DQ];
-        philox_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)b, (uint64_t)i, z);
+        philox_normals<DQ>(a.seed, BF_STREAM_NOISE, (uint32_t)(t + a.t_offset), (uint32_t)(a.trial_offset + b), (uint64_t)i, z);
 #pragma unroll
         for (int r = 0; r < DQ; ++r) {
           float s = mc.q0[r];
@@ -186,12 +187,12 @@ k_pf_resident(const __grid_constant__ ModelConst mc, const __grid_constant__ PfR
       float u0 = 0.0f;
       if (a.resampler == 1)
         u0 = a.res_u ? a.res_u[(size_t)t * gridDim.x + b]
-                     : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(t + a.t_offset), (uint32_t)b, 0ull);
+                     : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(t + a.t_offset), (uint32_t)(a.trial_offset + b), 0ull);
       for (int i = tid; i < N; i += NT) {
         float uu = u0;
         if (a.resampler == 0)
           uu = a.res_u ? a.res_u[((size_t)t * gridDim.x + b) * N + i]
-                       : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(t + a.t_offset), (uint32_t)b, (uint64_t)i);
+                       : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(t + a.t_offset), (uint32_t)(a.trial_offset + b), (uint64_t)i);
         const float r = resample_position(a.resampler, total, uu, i, N);
         ANC[i] = bisect_left_exclusive(Eb, N, levels, r);
       }

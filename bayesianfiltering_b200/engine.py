@@ -84,7 +84,7 @@ class ParticleFilterEngine:
     """Owns a bf_pf_handle: N particles x B independent trials of one registry model."""
 
     def __init__(self, host_model, num_particles, num_trials=1, ess_threshold=0.5, resampler="multinomial",
-                 path="auto", seed=0, device=None, shard_rank=0, shard_world=1):
+                 path="auto", seed=0, device=None, shard_rank=0, shard_world=1, trial_offset=0):
         self.lib = _lib.load()
         self.hm = host_model
         self.N, self.B = int(num_particles), int(num_trials)
@@ -92,7 +92,7 @@ class ParticleFilterEngine:
         self.resampler = resampler
         self.device = _default_device() if device is None else int(device)
         cfg = _lib.PfConfig(self.N, self.B, float(ess_threshold), _RESAMPLERS[resampler], _PATHS[path],
-                            int(seed) & 0xFFFFFFFFFFFFFFFF, self.device, 0, int(shard_rank), int(shard_world))
+                            int(seed) & 0xFFFFFFFFFFFFFFFF, self.device, int(trial_offset), int(shard_rank), int(shard_world))
         self.h = C.c_void_p()
         _lib.check(self.lib.bf_pf_create(C.byref(host_model.desc), C.byref(cfg), C.byref(self.h)))
 

@@ -61,7 +61,7 @@ def bootstrap_particle_filter(params: ParamsBPF, emissions, num_particles, key=P
                               ess_threshold: float = 0.5, *, resampler: str = "multinomial", noise=None,
                               resample_uniforms=None, init_particles=None, init_weights=None,
                               outputs=("weights", "particles"), num_trials=None, path: str = "auto", device=None,
-                              engine: Optional[ParticleFilterEngine] = None, shard_particles: bool = False):
+                              engine: Optional[ParticleFilterEngine] = None, shard_particles: bool = False, trial_offset: int = 0):
     r"""Bootstrap particle filter for the nonlinear state space model (inference.py:1302-1380).
 
     Args (reference): params, emissions [T,dy], num_particles, key, inputs [T] or None, ess_threshold.
@@ -75,6 +75,8 @@ def bootstrap_particle_filter(params: ParamsBPF, emissions, num_particles, key=P
         num_trials         B independent filters; every array above then takes a leading/embedded B axis
                            (emissions [B,T,dy] or shared [T,dy], noise [T,B,N,dq], uniforms [T,B,N] / [T,B]).
         path               'auto' | 'resident' (one CTA per trial, shared memory) | 'streamed' (HBM pipeline).
+        trial_offset       global index of trial 0 of this call (Monte-Carlo runs split over ranks: the in-kernel Philox
+                           counters use trial_offset + b, so the draws of a trial do not depend on the split).
         shard_particles    True under torchrun: ONE filter whose num_particles are split over the ranks' GPUs
                            (engine.ShardedParticleFilterEngine); per-particle arguments and results are then the
                            local shard, per-step scalars come from rank 0.
@@ -90,7 +92,7 @@ def bootstrap_particle_filter(params: ParamsBPF, emissions, num_particles, key=P
             engine = ShardedParticleFilterEngine(hm, int(num_particles), float(ess_threshold), resampler, key_to_seed(key), device)
         else:
             engine = ParticleFilterEngine(hm, int(num_particles), B, float(ess_threshold), resampler, path,
-                                          key_to_seed(key), device)
+                                          key_to_seed(key), device, trial_offset=trial_offset)
         own = True
     else:
         own = False

@@ -68,9 +68,11 @@ def particle_filter_trials(params, emissions, num_particles, true_states=None, k
     emissions = np.asarray(emissions, np.float32)
 
     def block(start, stop):
-        out = gf.bootstrap_particle_filter(params, emissions[start:stop], num_particles, key_to_seed(key) + start, inputs,
+        # ONE seed for every rank; the block's global trial index goes into the Philox counters (trial_offset), so trial b
+        # draws the same numbers whatever the number of ranks
+        out = gf.bootstrap_particle_filter(params, emissions[start:stop], num_particles, key_to_seed(key), inputs,
                                            ess_threshold, resampler=resampler, outputs=("means", "log_likelihood"),
-                                           num_trials=stop - start, device=device)
+                                           num_trials=stop - start, device=device, trial_offset=start)
         res = {"means": out["means"], "marginal_log_likelihood": out["marginal_log_likelihood"]}
         if true_states is not None:
             res["rmse"] = rmse(out["means"], np.asarray(true_states)[start:stop])
@@ -87,7 +89,12 @@ def gaussian_sum_filter_trials(params, emissions, num_components, true_states=No
     emissions = np.asarray(emissions, np.float32)
 
     def block(start, stop):
-        _, ex = gf.gaussian_sum_filter(params, emissions[start:stop], num_components, 1, inputs, key=key_to_seed(key) + start,
+        # initial component means per GLOBAL trial (generator keyed by (key, trial)): independent of the number of ranks
+        m0 = np.asarray(params.initial_mean, np.float64)
+        L = np.linalg.cholesky(np.asarray(params.initial_covariance, np.float64))
+        means0 = np.stack([m0 + np.random.default_rng([key_to_seed(key) & 0xFFFFFFFF, b]).standard_normal((int(num_components), m0.size)) @ L.T
+                           for b in range(start, stop)]).astype(np.float32)
+        _, ex = gf.gaussian_sum_filter(params, emissions[start:stop], num_components, 1, inputs, init_means=means0,
                                        outputs=("log_likelihood", "mixture_mean"), num_trials=stop - start, device=device,
                                        return_extras=True)
         res = {"means": ex["mixture_mean"], "marginal_log_likelihood": ex["marginal_log_likelihood"]}

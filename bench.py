@@ -5,17 +5,22 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (config.workload): BASELINE.json configs[2] -- bootstrap particle filter on the 4-D manoeuvring
+Headline workload (config.workload): BASELINE.json configs[2] -- bootstrap particle filter on the 4-D manoeuvring
 bearings-only tracking model (BOT_Experiment_script.py:19-53), N = 2^24 particles per GPU, T = 1000 time steps,
 ess_threshold = 1.0 (resample every step, :151), systematic resampling, in-kernel Philox noise, outputs =
 per-step weighted mean + log-likelihood increment (the [N,T,dx] trajectory is 335 GB and is not stored).
 One bench "step" = one whole filter run (all T time steps) = N*T particle-steps per GPU.  With --gpus N every
 rank runs its own independent filter (trial sharding, no data-path collective): scaling = weak.
-The Gaussian-sum filter number (configs[1]: UNGM, M=100 x 1024 trials, T=500) is reported beside it under
-"gsf" in the same JSON line.
 
-Keys beyond the base contract: roofline, cpu_baseline, e2e, gpu_launches, clocks, gsf.
-The oracle (oracle/) is executed here only for cpu_baseline and --impl reference.
+Beside it, in the same JSON line:
+  "sharded"  (N > 1 only) configs[2] AS WRITTEN: ONE filter of 2^24 particles sharded over the N GPUs, T = 1000
+  "gsf"      configs[1]: Gaussian-sum EKF filter, UNGM, M = 100 x 1024 trials x T = 500 per GPU
+  "gsf_l96"  configs[3]: Gaussian-sum filter on Lorenz-96 d = 40, M = 256 x 512 trials per GPU (4096 over 8), T = 100
+  "fp32_peak_tflops"  measured FFMA throughput (bf_measure_fp32_peak), the denominator of the fp32_frac entries
+Keys beyond the base contract: roofline, cpu_baseline, e2e, gpu_launches, clocks.
+
+Synthetic data comes from the package's own generator (NonlinearSSM.sample -> bf_ssm_sample); the oracle (oracle/) is
+executed only for cpu_baseline and --impl reference.
 """
 import argparse
 import json
@@ -32,16 +37,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PF_LOG2N = int(os.environ.get("BF_BENCH_LOG2N", "24"))
-# "trials": every rank runs its own N = 2^24 filter (weak scaling, no collective) -- the default;
-# "particles": ONE filter of N = 2^24 particles sharded over the ranks (strong scaling; NCCL + peer gathers every step)
-PF_MODE = os.environ.get("BF_BENCH_MODE", "trials")
 PF_T = int(os.environ.get("BF_BENCH_T", "1000"))
+SHARD_STEPS = int(os.environ.get("BF_BENCH_SHARD_STEPS", "2"))
 GSF_M, GSF_B, GSF_T = 100, 1024, 500
+L96_M, L96_B, L96_T = 256, int(os.environ.get("BF_BENCH_L96_B", "512")), 100
 BYTES_PER_PARTICLE_STEP = 84     # 4*(4*dx + 5) for dx=4, in-kernel RNG, resampling step
-# DRAM bytes the fused kernel actually moves per particle-step: ncu --set full, dram__bytes_read+write of one launch /
-# (N*T) (profiles/r1_m_pf_fused_T40_ncu.txt).  Below the algorithmic figure because the resampled copy of the
-# particles is never materialised (the gather is fused into the next step's propagate).
+# DRAM bytes the fused kernel actually moves per particle-step, from the ncu --set full capture named in MOVED_SOURCE
+# (dram__bytes_read + dram__bytes_write of one launch / (N*T)).  Below the algorithmic figure because the resampled copy
+# of the particles is never materialised (the gather is fused into the next step's propagate).  NOT measured in this run.
 MOVED_BYTES_PER_PARTICLE_STEP = 52.0
+MOVED_SOURCE = "profiles/r1_m_pf_fused_T40_ncu.txt"
+GSF_BYTES = 20                   # 4*(2 dx + 2 dx^2 + 1), dx = 1: the five posterior fields
+GSF_FLOPS = 60                   # ~60 flop per component-step incl. exp / log
+L96_BYTES = 8 * (40 + 1600 + 1) + 4 * (1 + 40.0 / 256)     # carry read + write, weights + mixture mean out: ~13.1 KB
+L96_FLOPS_EXECUTED = 1.65e5      # banded F (4 nnz/row) and H (1 nnz/row): solve 37k, K S 32k, (K S) K^T 64k, F P F^T 26k, rest 6k
+L96_FLOPS_DENSE = 4.9e5          # SURVEY 8(d) figure for dense Jacobians
 METRIC, UNIT = "particle-steps/s", "particle-steps/s"
 
 
@@ -100,17 +110,30 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def _bot_case():
-    from tests.parity_cases import case
-    return case("bot2")
-
-
 # ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def _cpu_worker(args):
-    """One process = one independent filter of the oracle (NumPy restatement of inference.py:1302-1380)."""
+    """One process = one independent filter of the oracle (NumPy restatement of inference.py:1302-1380), ONE BLAS thread:
+    the workers already occupy every core, and a multi-threaded BLAS under them oversubscribes the box (it made this arm
+    5-10x slower in round 1)."""
     seed, N, T = args
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
     from oracle import pf as opf
-    c = _bot_case()
+    from tests.parity_cases import case
+    c = case("bot2")
     _, ys = c.simulate(T, 1000 + seed)
     u = c.inputs(T)
     x0, noise, ru = c.pf_randomness(T, N, 2000 + seed, "systematic")
@@ -123,6 +146,8 @@ def cpu_throughput(seconds_target=12.0):
     """Oracle port on all host cores: one independent filter per core (the same trial sharding the GPU arm uses),
     N = 2^17 particles, T sized for ~seconds_target of work.  Returns (particle-steps/s, cores, sample string)."""
     import multiprocessing as mp
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"                      # inherited by the workers; threadpoolctl covers an already-loaded BLAS
     cores = os.cpu_count() or 1
     N = 1 << 17
     ctx = mp.get_context("fork")
@@ -134,38 +159,50 @@ def cpu_throughput(seconds_target=12.0):
         t0 = time.perf_counter()
         pool.map(_cpu_worker, [(i, N, T) for i in range(cores)])
         wall = time.perf_counter() - t0
-    return cores * N * T / wall, cores, f"{cores} independent BOT filters x N=2^17 x T={T} (NumPy oracle, one per core, {wall:.1f} s)"
+    sample = (f"{cores} independent BOT filters x N=2^17 x T={T} (NumPy oracle, one process per core, 1 BLAS thread each, {wall:.1f} s; "
+              f"per-particle-step figure extrapolated to the N=2^24, T={PF_T} workload)")
+    return cores * N * T / wall, cores, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times = []
-    sample = ""
+    probe = {}
+    for mod in ("jax", "tensorflow_probability"):
+        try:
+            __import__(mod)
+            probe[mod] = "importable"
+        except Exception as e:      # noqa: BLE001
+            probe[mod] = f"{type(e).__name__}"
+    vals = []
+    sample, cores = "", 1
     for i in range(args.warmup + args.steps):
         v, cores, sample = cpu_throughput(seconds_target=6.0 if args.steps > 1 else 12.0)
         if i >= args.warmup:
-            times.append(v)
-    v = float(np.mean(times))
-    N = 1 << 17
+            vals.append(v)
+    v = float(np.mean(vals))
+    cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "blas_threads_per_worker": 1,
+           "cpu_model": _cpu_model(), "reference_runtime_probe": probe,
+           "note": "the reference itself needs jax + tensorflow_probability, absent on this box (probe above): the arm times the "
+                   "NumPy oracle, which tests/test_ref_pin.py holds to the reference's own outputs"}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * (1 << 17) * cores / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * (1 << PF_LOG2N) * PF_T / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"BPF bearings-only dx=4 dy=2, resample every step, systematic; CPU sample: {sample}"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from bayesianfiltering_b200 import inference as gf
+    from bayesianfiltering_b200 import inference as gf, workloads, _lib
     from bayesianfiltering_b200.engine import ParticleFilterEngine, GaussianSumFilterEngine, ShardedParticleFilterEngine
     from bayesianfiltering_b200.random import PRNGKey
-    from tests.parity_cases import case
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -189,19 +226,32 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed(fn, steps, warmup):
+        """`steps` calls of fn between a barrier + synchronize on both sides, CUDA events on torch's stream (the one the
+        kernels are launched on), max over ranks -> ms per call."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
     peak, peak_src = _peaks()
-    c = _bot_case()
+    fp32 = C.c_double()
+    _lib.check(_lib.load().bf_measure_fp32_peak(local, C.byref(fp32)))
+    fp32_peak = fp32.value
+
+    # ---- headline: configs[2], one independent N = 2^24 filter per GPU
+    wl = workloads.bot()
     N, T = 1 << PF_LOG2N, PF_T
-    _, ys = c.simulate(T, 1000 + (0 if PF_MODE == 'particles' else rank))       # one filter: the same data on every rank
-    u = c.inputs(T)
+    u = wl.inputs(T)
+    _, ys = wl.sample(T, 1000 + rank)
     ys_d, u_d = torch.from_numpy(ys).to(dev), torch.from_numpy(u).to(dev)
-    sharded = PF_MODE == "particles" and world > 1
-    if sharded:
-        eng = ShardedParticleFilterEngine(c.host_model(), N, 1.0, "systematic", seed=1234, device=local)
-        Nloc = N // world
-    else:
-        eng = ParticleFilterEngine(c.host_model(), N, 1, 1.0, "systematic", "streamed", 1234 + rank, local)
-        Nloc = N
+    eng = ParticleFilterEngine(wl.host_model(), N, 1, 1.0, "systematic", "streamed", 1234 + rank, local)
     outs = ("means", "log_likelihood")
     bufs = {"means": torch.empty((1, T, 4), device=dev), "log_likelihood": torch.empty((1, T), device=dev)}
 
@@ -216,107 +266,164 @@ def run_ours(args):
         clocks.start()
     l0 = eng.launches()
     eng.phase_times(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = timed(step, args.steps, 0)
     clk = clocks.stop() if rank == 0 else None
     launches = eng.launches() - l0
     phases = {k: v * 1e3 / (args.steps * T) for k, v in eng.phase_times().items()}     # us per time step
-    if os.environ.get("BF_BENCH_ALLRANKS"):
-        print(f"rank {rank}: phases us/step {({k: round(v, 1) for k, v in phases.items()})}", file=sys.stderr, flush=True)
     ll = bufs["log_likelihood"].double().sum().item()
-    if sharded and rank != 0:
-        ll = 0.0                                   # per-step scalars of a sharded filter are written by rank 0
     if not np.isfinite(ll):
         raise SystemExit(f"benchmark produced a non-finite log-likelihood ({ll})")
-    ms_per_step = ms / args.steps
-    value = (N if sharded else world * N) * T / (ms_per_step * 1e-3)
-    # roofline: algorithmic bytes of one rank's share of a run / its device time
-    achieved = Nloc * T * BYTES_PER_PARTICLE_STEP / (ms_per_step * 1e-3) / 1e9
+    value = world * N * T / (ms_per_step * 1e-3)
+    achieved = N * T * BYTES_PER_PARTICLE_STEP / (ms_per_step * 1e-3) / 1e9
+    ll_one = bufs["log_likelihood"].cpu().numpy().copy() if rank == 0 else None
     eng.close()
 
-    # ---- end to end through the reference-facing entry point: host emissions in, host estimates out
-    params = c.params_bpf()
-    ne2e = max(1, min(args.steps, 3))
-    gf.bootstrap_particle_filter(params, ys, N, PRNGKey(7), u, 1.0, resampler="systematic", outputs=outs, path="streamed",
-                                 device=local, shard_particles=sharded)
+    # ---- end to end through the reference-facing entry point: host emissions in, host estimates out (median of 3, warm)
+    params = wl.params_bpf()
+
+    def e2e_call():
+        return gf.bootstrap_particle_filter(params, ys, N, PRNGKey(7), u, 1.0, resampler="systematic", outputs=outs, path="streamed", device=local)
+
+    post = e2e_call()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(ne2e):
-        post = gf.bootstrap_particle_filter(params, ys, N, PRNGKey(7), u, 1.0, resampler="systematic", outputs=outs,
-                                            path="streamed", device=local, shard_particles=sharded)
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / ne2e
-    e2e = {"value": (N if sharded else world * N) * T / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(ys.nbytes + u.nbytes),
+    e2e_times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        post = e2e_call()
+        torch.cuda.synchronize()
+        e2e_times.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = max_over_ranks(float(np.median(e2e_times)))
+    e2e = {"value": world * N * T / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(ys.nbytes + u.nbytes),
            "d2h_bytes_per_step": int(post["means"].nbytes + post["log_likelihood_increments"].nbytes),
            "call": "inference.bootstrap_particle_filter(params, emissions[host], N, key, inputs, 1.0, "
-                   "resampler='systematic', outputs=('means','log_likelihood'))", "ms_per_step": e2e_ms}
+                   "resampler='systematic', outputs=('means','log_likelihood'))", "ms_per_step": e2e_ms, "calls_timed": 3}
+
+    # ---- configs[2] as written: ONE filter of 2^24 particles sharded over the ranks (N > 1 only)
+    sharded = None
+    if world > 1:
+        _, ys1 = wl.sample(T, 1000)                       # the same data and seed on every rank
+        ys1_d = torch.from_numpy(ys1).to(dev)
+        seng = ShardedParticleFilterEngine(wl.host_model(), N, 1.0, "systematic", seed=1234, device=local)
+        sb = {"means": torch.empty((1, T, 4), device=dev), "log_likelihood": torch.empty((1, T), device=dev)}
+        sstep = lambda: seng.run(ys1_d, inputs=u_d, outputs=outs, out_buffers=sb)
+        seng.phase_times(reset=True)
+        sms = timed(sstep, SHARD_STEPS, 1)
+        sph = {k: v * 1e3 / ((SHARD_STEPS + 1) * T) for k, v in seng.phase_times().items()}
+        sll = sb["log_likelihood"].cpu().numpy().copy()
+        seng.close()
+        par = None
+        if rank == 0:                                     # the same filter on one GPU: same seed, same data
+            one = ParticleFilterEngine(wl.host_model(), N, 1, 1.0, "systematic", "streamed", 1234, local)
+            ob = {"means": torch.empty((1, T, 4), device=dev), "log_likelihood": torch.empty((1, T), device=dev)}
+            one.run(ys1_d, inputs=u_d, outputs=outs, out_buffers=ob)
+            torch.cuda.synchronize()
+            oll = ob["log_likelihood"].cpu().numpy()
+            one.close()
+            d = np.abs(sll - oll)
+            par = {"bit_equal_loglik_steps": int(np.sum(sll == oll)), "steps": int(T),
+                   "first_step_bit_equal": bool(sll[0, 0] == oll[0, 0]),
+                   "max_abs_diff_loglik_increment": float(d.max()), "marginal_loglik_sharded": float(sll.astype(np.float64).sum()),
+                   "marginal_loglik_one_gpu": float(oll.astype(np.float64).sum())}
+        barrier()
+        sharded = {"metric": METRIC, "value": N * T / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms, "scaling": "strong",
+                   "speedup_vs_1gpu": ms_per_step / sms, "efficiency_vs_1gpu": ms_per_step / sms / world,
+                   "config": {"workload": f"ONE bootstrap PF, N=2^{PF_LOG2N} particles in total sharded x{world}, T={T}, BOT, systematic, resample every step",
+                              "parallelism": "particles sharded; per step: weight statistics + tile sums exchanged by peer-memory stores and "
+                                             "flag barriers inside the persistent kernel; ancestors on other ranks gathered over NVLink"},
+                   "phase_us_per_time_step_rank0": sph, "parity_vs_1gpu": par, "steps": SHARD_STEPS, "warmup": 1}
 
     # ---- Gaussian-sum filter, configs[1]: UNGM, M=100 x 1024 trials x T=500 (per rank)
-    g = case("ungm")
-    gy = np.stack([g.simulate(GSF_T, 50000 + rank * GSF_B + b)[1] for b in range(16)])
-    gy = np.tile(gy, (GSF_B // 16, 1, 1)) + np.random.default_rng(rank).normal(0, 0.1, (GSF_B, GSF_T, 1)).astype(np.float32)
+    g = workloads.ungm()
+    _, gy = g.sample(GSF_T, 50000 + rank, num_trials=GSF_B)
     gu = g.inputs(GSF_T)
-    gm0 = np.stack([g.gsf_means0(GSF_M, 60000 + b) for b in range(GSF_B)])
+    gm0 = g.init_means(GSF_M, GSF_B, 60000 + rank)
     geng = GaussianSumFilterEngine(g.host_model(), GSF_M, GSF_B, local)
     gy_d, gu_d, gm0_d = (torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev) for a in (gy, gu, gm0))
     fields = ("weights", "means", "covariances", "predicted_means", "predicted_covariances")
     gb = {k: torch.empty((GSF_B, GSF_T, GSF_M) + ((1,) if "mean" in k else (1, 1) if "cov" in k else ()), device=dev)
           for k in fields}
-    for _ in range(args.warmup):
-        geng.run(gy_d, inputs=gu_d, init_means=gm0_d, outputs=fields, out_buffers=gb)
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(args.steps):
-        geng.run(gy_d, inputs=gu_d, init_means=gm0_d, outputs=fields, out_buffers=gb)
-    g1.record()
-    barrier()
-    gms = max_over_ranks(g0.elapsed_time(g1)) / args.steps
+    gl0 = geng.launches()
+    gms = timed(lambda: geng.run(gy_d, inputs=gu_d, init_means=gm0_d, outputs=fields, out_buffers=gb), args.steps, args.warmup)
+    launches += (geng.launches() - gl0) * args.steps // (args.steps + args.warmup)
     gval = world * GSF_M * GSF_B * GSF_T / (gms * 1e-3)
-    t0 = time.perf_counter()
-    geng.run_host(gy, inputs=gu, init_means=gm0, outputs=fields)
-    ge2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    res = geng.run_host(gy, inputs=gu, init_means=gm0, outputs=fields)        # warm: pinned result pages, staging buffers
+    ge = []
+    for _ in range(3):
+        del res
+        t0 = time.perf_counter()
+        res = geng.run_host(gy, inputs=gu, init_means=gm0, outputs=fields)
+        ge.append((time.perf_counter() - t0) * 1e3)
+    ge2e_ms = max_over_ranks(float(np.median(ge)))
+    d2h = int(sum(v.nbytes for v in res.values()))
+    del res
     geng.close()
+    cs = GSF_M * GSF_B * GSF_T
     gsf = {"metric": "component-steps/s", "value": gval, "unit": "component-steps/s", "ms_per_step": gms,
            "config": {"workload": f"GSF(EKF) UNGM M={GSF_M} x {GSF_B} trials x T={GSF_T} per GPU, all five posterior fields written"},
-           "roofline": {"bound": "hbm", "achieved": GSF_M * GSF_B * GSF_T * 20 / (gms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": GSF_M * GSF_B * GSF_T * 20 / (gms * 1e-3) / 1e9 / peak, "traffic": None,
-                        "note": "20 B/component-step of outputs; state is register-resident"},
-           "e2e": {"value": world * GSF_M * GSF_B * GSF_T / (ge2e_ms * 1e-3), "unit": "component-steps/s",
-                   "h2d_bytes_per_step": int(gy.nbytes + gu.nbytes + gm0.nbytes),
-                   "d2h_bytes_per_step": int(GSF_M * GSF_B * GSF_T * 20)}}
+           "roofline": {"bound": "hbm", "achieved": cs * GSF_BYTES / (gms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": cs * GSF_BYTES / (gms * 1e-3) / 1e9 / peak, "traffic": 971.4e6,
+                        "traffic_source": "profiles/r2_a_gsf_c2_cta_ncu.txt (ncu --set full of one launch)",
+                        "fp32_frac": cs * GSF_FLOPS / (gms * 1e-3) / 1e12 / fp32_peak, "flops_per_component_step": GSF_FLOPS,
+                        "note": "20 B/component-step of outputs; the state is register-resident; the kernel is instruction-issue bound "
+                                "(322 SASS instructions per component-step, issue slots 69 % busy, profiles/r2_a_gsf_c2_cta_ncu.txt)"},
+           "e2e": {"value": world * cs / (ge2e_ms * 1e-3), "unit": "component-steps/s", "ms_per_step": ge2e_ms, "calls_timed": 3,
+                   "h2d_bytes_per_step": int(gy.nbytes + gu.nbytes + gm0.nbytes), "d2h_bytes_per_step": d2h,
+                   "pcie_bound_ms": d2h / 50e9 * 1e3,
+                   "call": "GaussianSumFilterEngine.run_host (what inference.gaussian_sum_filter(..., num_trials=1024) calls): host arrays in, "
+                           "1 GB of posterior fields back into pinned host memory"}}
+
+    # ---- Gaussian-sum filter, configs[3]: Lorenz-96 d=40, M=256 x 512 trials per GPU, T=100 (trial-sharded)
+    l = workloads.l96(40)
+    _, ly = l.sample(L96_T, 700 + rank, num_trials=L96_B)
+    lm0 = l.init_means(L96_M, L96_B, 800 + rank)
+    leng = GaussianSumFilterEngine(l.host_model(), L96_M, L96_B, local)
+    ly_d, lm0_d = torch.from_numpy(ly).to(dev), torch.from_numpy(lm0).to(dev)
+    louts = ("weights", "mixture_mean", "log_likelihood")
+    lb = {"weights": torch.empty((L96_B, L96_T, L96_M), device=dev), "mixture_mean": torch.empty((L96_B, L96_T, 40), device=dev),
+          "log_likelihood": torch.empty((L96_B, L96_T), device=dev)}
+    lms = timed(lambda: leng.run(ly_d, init_means=lm0_d, outputs=louts, out_buffers=lb), max(1, min(args.steps, 2)), 1)
+    launches += max(1, min(args.steps, 2))
+    lll = float(lb["log_likelihood"].double().sum().item())
+    leng.close()
+    if not np.isfinite(lll):
+        raise SystemExit("Lorenz-96 Gaussian-sum filter produced a non-finite log-likelihood")
+    lcs = L96_M * L96_B * L96_T
+    gsf_l96 = {"metric": "component-steps/s", "value": world * lcs / (lms * 1e-3), "unit": "component-steps/s", "ms_per_step": lms,
+               "per_gpu": lcs / (lms * 1e-3),
+               "config": {"workload": f"GSF(EKF) Lorenz-96 dx=40 dy=20, M={L96_M} x {L96_B} trials per GPU ({L96_B * world} in all), T={L96_T}, "
+                                      "outputs = weights + mixture mean + log-lik", "parallelism": f"trial-sharded x{world}, no collective"},
+               "roofline": {"bound": "hbm", "achieved": lcs * L96_BYTES / (lms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": lcs * L96_BYTES / (lms * 1e-3) / 1e9 / peak, "bytes_per_component_step": L96_BYTES, "traffic": None,
+                            "fp32_frac": lcs * L96_FLOPS_EXECUTED / (lms * 1e-3) / 1e12 / fp32_peak,
+                            "flops_per_component_step_executed": L96_FLOPS_EXECUTED, "flops_per_component_step_dense_survey": L96_FLOPS_DENSE,
+                            "note": "state streamed through HBM once per fused update+predict; the Jacobians are banded and applied as such"}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, sample = cpu_throughput()
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "blas_threads_per_worker": 1,
+               "cpu_model": _cpu_model()}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"BPF bearings-only (BOT) dx=4 dq=2 dy=2, N=2^{PF_LOG2N} particles {'in total' if sharded else 'per GPU'}, T={T}, "
+                "config": {"workload": f"BPF bearings-only (BOT) dx=4 dq=2 dy=2, N=2^{PF_LOG2N} particles per GPU, T={T}, "
                                        "ess_threshold=1.0 (resample every step), systematic resampling, Philox noise in-kernel, "
                                        "outputs=weighted mean + log-lik per step",
-                           "parallelism": (f"ONE filter, particles sharded x{world} (NCCL: weight statistics + scan offsets per step; "
-                                           f"ancestors on other ranks gathered over NVLink peer memory)") if sharded else
-                                          f"trial-sharded x{world} (one independent filter per GPU, no collective)",
+                           "parallelism": f"trial-sharded x{world} (one independent filter per GPU, no collective)",
                            "l2_policy": "inputs larger than L2 (268 MB particle state per buffer)",
                            "step": "one whole filter run = N*T particle-steps"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": MOVED_BYTES_PER_PARTICLE_STEP * Nloc * T, "traffic_source": "ncu capture of a T=40 launch, scaled to this T",
-                             "moved_bytes_per_particle_step": MOVED_BYTES_PER_PARTICLE_STEP,
+                             "traffic": MOVED_BYTES_PER_PARTICLE_STEP * N * T,
+                             "traffic_source": f"NOT measured in this run: {MOVED_BYTES_PER_PARTICLE_STEP} B per particle-step from the ncu capture {MOVED_SOURCE}, scaled to N*T",
+                             "moved_frac_of_peak": MOVED_BYTES_PER_PARTICLE_STEP * N * T / (ms_per_step * 1e-3) / 1e9 / peak,
                              "peak_source": peak_src, "bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
-                             "bound_note": "this model is instruction-issue-bound (~475 SASS instructions per particle-step, issue slots 65% busy, DRAM 32% of peak: profiles/r1_m_pf_fused_T40_ncu.txt)",
+                             "bound_note": "this model is instruction-issue-bound, not HBM-bound (Philox, Box-Muller, sin/cos, atan2, exp per particle): see profiles/",
                              "kernel": "k_pf_fused (persistent cooperative kernel, all T steps in one launch)",
                              "phase_us_per_time_step": phases},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "gsf": gsf}
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+                "fp32_peak_tflops": fp32_peak, "sharded": sharded, "gsf": gsf, "gsf_l96": gsf_l96}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

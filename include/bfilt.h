@@ -74,7 +74,8 @@ typedef struct bf_pf_config {
                                 STREAMED = one persistent cooperative kernel, state in HBM      */
   uint64_t seed;             /* Philox key for every random input that is not supplied          */
   int32_t device;            /* CUDA device ordinal                                             */
-  int32_t reserved;
+  int32_t trial_offset;      /* global index of this handle's trial 0: Philox counters use trial_offset + b, so a block of trials
+                                run on another rank draws the same numbers as in a single-handle run (0 = standalone) */
   /* One filter sharded over the GPUs of a box (one process per GPU): this rank owns num_particles consecutive
    * particles of a filter of shard_world * num_particles.  0/0 or x/1 = not sharded.  See bf_pf_shard_* below. */
   int32_t shard_rank, shard_world;
@@ -261,10 +262,14 @@ int bf_model_eval(const bf_model_desc* model, int32_t what, int64_t n, const flo
                   float* out, void* cuda_stream);
 /* NonlinearSSM.sample (gaussfiltax/models.py:240-289) for B independent trials (DEVICE pointers):
  * states [B,T,dx], emissions [B,T,dy].  z0 [B,dx], q_noise [B,T,dq] (row t=0 unused), r_noise [B,T,dr]
- * are already-coloured draws, or NULL to draw them with Philox(seed). */
+ * are already-coloured draws, or NULL to draw them with Philox(seed).  BF_MODEL_L96 (large state): Philox draws only. */
 int bf_ssm_sample(const bf_model_desc* model, int32_t B, int32_t T, const float* inputs, uint64_t seed,
                   const float* z0, const float* q_noise, const float* r_noise, float* states, float* emissions,
                   void* cuda_stream);
+
+/* FP32 (non-tensor) FMA throughput of the device, measured with a register-only FFMA kernel (TFLOP/s): the denominator of
+ * the FP32-pipe fractions bench.py reports for the Gaussian-sum filters.  Synchronises the device. */
+int bf_measure_fp32_peak(int32_t device, double* tflops);
 
 /* Handles draw their device memory from the device's stream-ordered pool and leave it cached there when they are
  * destroyed (creating a handle per call stays cheap).  This returns the cached memory to the driver. */

@@ -465,3 +465,22 @@ def test_lean_equals_general_at_headline_size_2pow24(monkeypatch):
     for k in outs:
         assert np.array_equal(res["1"][k], res["0"][k]), k
     assert np.all(np.isfinite(res["1"]["log_likelihood"])) and np.all(res["1"]["resampled"] == 1)
+
+
+@pytest.mark.parametrize("path,N", [("resident", 512), ("streamed", 4096)])
+def test_trial_offset_makes_split_monte_carlo_runs_identical(path, N):
+    """Independent trials split over handles (ranks): with `trial_offset` the in-kernel Philox counters use the GLOBAL
+    trial index, so trial b gives the same bits whether it ran in one handle of 4 trials or as trial 0 of a second handle."""
+    from bayesianfiltering_b200.engine import ParticleFilterEngine
+    c = case("ungm")
+    T = 8
+    ys = np.stack([c.simulate(T, 30 + b)[1] for b in range(4)])
+    u = c.inputs(T)
+    outs = ("means", "log_likelihood", "final_particles")
+    mk = lambda B, off: ParticleFilterEngine(c.host_model(), N, B, 0.5, "systematic", path, 77, 0, trial_offset=off)
+    e = mk(4, 0); full = e.run_host(ys, inputs=u, outputs=outs); e.close()
+    e = mk(2, 0); a = e.run_host(ys[:2], inputs=u, outputs=outs); e.close()
+    e = mk(2, 2); b = e.run_host(ys[2:], inputs=u, outputs=outs); e.close()
+    for k in outs:
+        assert np.array_equal(np.concatenate([a[k], b[k]], axis=0), full[k]), k
+    assert not np.array_equal(full["means"][0], full["means"][2])
