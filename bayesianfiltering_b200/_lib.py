@@ -12,6 +12,7 @@ MODEL_UNGM, MODEL_BOT, MODEL_L63, MODEL_L96, MODEL_LG, MODEL_SIN1D, MODEL_MSV = 
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 PATH_AUTO, PATH_RESIDENT, PATH_STREAMED = 0, 1, 2
 GSF_PREDICT_FIRST, GSF_NO_JITTER, GSF_COV_PLUS_P = 1, 2, 4
+LEGACY_UKF, LEGACY_MCF = 1, 2
 SHARD_BLOB_BYTES, NCCL_ID_BYTES = 512, 128
 
 _fp = C.POINTER(C.c_float)
@@ -50,7 +51,7 @@ class GsfIO(C.Structure):
                 ("init_weights", C.c_void_p),
                 ("out_weights", C.c_void_p), ("out_means", C.c_void_p), ("out_covs", C.c_void_p),
                 ("out_pred_means", C.c_void_p), ("out_pred_covs", C.c_void_p), ("out_loglik", C.c_void_p),
-                ("out_mix_mean", C.c_void_p), ("Q_t", C.c_void_p), ("R_t", C.c_void_p)]
+                ("out_mix_mean", C.c_void_p), ("Q_t", C.c_void_p), ("R_t", C.c_void_p), ("mc_draws", C.c_void_p)]
 
 
 class AgsfConfig(C.Structure):
@@ -85,6 +86,7 @@ SYMBOLS = [
     ("bf_gsf_step", C.c_int, [C.c_void_p, C.POINTER(GsfIO), C.c_void_p]),
     ("bf_gsf_run_host", C.c_int, [C.c_void_p, C.POINTER(GsfIO)]),
     ("bf_gsf_set_unscented", C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
+    ("bf_gsf_set_legacy_moments", C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_uint64]),
     ("bf_gsf_kernel_launches", C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("bf_gsf_destroy", C.c_int, [C.c_void_p]),
     ("bf_agsf_create", C.c_int, [C.POINTER(ModelDesc), C.POINTER(AgsfConfig), C.POINTER(C.c_void_p)]),

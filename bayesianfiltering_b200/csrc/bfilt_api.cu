@@ -260,6 +260,7 @@ struct bf_pf_s {
   DevBuf carry_x, carry_w, carry_uniform, carry_stats;
   // streamed scratch
   DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats, phase_ns, V;
+  unsigned run_id = 0;                // runs launched on this handle (tags of the unit partials)
   int ntiles;
   // Independent trials of the streamed path run CONCURRENTLY (one cooperative kernel each, on its own stream, with its
   // own scratch): at the reference's sizes (Nsim = 100 trials of N = 10^4) one trial fills a few SMs only.
@@ -569,12 +570,16 @@ struct PfRun {
       if (grid > per_sm * h->nsm) return fail(BF_ECUDA, "cooperative grid of %d CTAs does not fit (%d per SM)", grid, per_sm);
     }
     const int world = h->world, rank = h->rank;
-    const size_t part_bytes = (((size_t)2 * world * grid * sizeof(PfPartial)) + 63) & ~(size_t)63;   // + ticket counter + folded stats
-    {   // sized for the largest grid any instantiation can have (one CTA per SM slot), so that a later call with another
-        // kernel variant never re-allocates it under work still in flight on a caller's non-blocking stream
-      const size_t part_max = (((size_t)2 * world * std::max(grid, 2 * h->nsm) * sizeof(PfPartial)) + 63) & ~(size_t)63;
-      CUDA_OK(h->partials.ensure(std::max(part_bytes, part_max) + 256));
-    }
+    // canonical statistics tree (pf_fused.cuh, PfFusedArgs::upart): units of 512 particles, blocks of <= 256 units
+    const int nunits = (N + 511) / 512;
+    int bsz = 256;
+    if (world > 1) while (bsz > nunits) bsz >>= 1;      // a shard is an aligned power-of-two subtree: blocks never straddle ranks
+    const int nblocks = (nunits + bsz - 1) / bsz, nb_total = world * nblocks;
+    const size_t root_bytes = (((size_t)2 * nb_total * sizeof(PfPartial)) + 63) & ~(size_t)63;
+    const size_t unit_bytes = (size_t)nunits * sizeof(UnitRec);
+    const size_t ctr_bytes = (((size_t)nblocks + 1) * sizeof(unsigned int) + 63) & ~(size_t)63;      // block tickets + the CTA ticket
+    const size_t part_bytes = root_bytes + unit_bytes + ctr_bytes;                                  // + folded stats
+    CUDA_OK(h->partials.ensure(part_bytes + 256));
     const int grid_s = (int)std::min<int64_t>(((int64_t)N + 255) / 256, (int64_t)h->nsm * 8);
     const int Ng = N * world;
     int log2n = -1, log2ng = -1;
@@ -647,13 +652,22 @@ struct PfRun {
         a.tau_tile = a.Etile + ntiles_g + 4;
       }
       a.stage_ts = stage_ts ? 1 : 0;
-      a.partials = (sl ? sl->partials : h->partials).as<PfPartial>();
-      a.fold_ctr = reinterpret_cast<unsigned int*>((sl ? sl->partials : h->partials).as<char>() + part_bytes);
-      a.fold_stats = reinterpret_cast<StepStats*>((sl ? sl->partials : h->partials).as<char>() + part_bytes + 64);
+      {
+        char* pb = (sl ? sl->partials : h->partials).as<char>();
+        a.broot = reinterpret_cast<PfPartial*>(pb);
+        a.upart = reinterpret_cast<UnitRec*>(pb + root_bytes);
+        a.run_tag = (unsigned)(++h->run_id) & 0xFFFu;
+        a.bctr = reinterpret_cast<unsigned int*>(pb + root_bytes + unit_bytes);
+        a.fold_ctr = a.bctr + nblocks;
+        a.fold_stats = reinterpret_cast<StepStats*>(pb + part_bytes);
+        a.nunits = nunits; a.bsz = bsz; a.nblocks = nblocks; a.nb_total = nb_total; a.blk_off = rank * nblocks;
+        CUDA_OK(cudaMemsetAsync(a.upart, 0, unit_bytes + ctr_bytes, s));     // stale tags of an earlier owner of this memory; tickets
+      }
       if (world > 1) {                   // the exchanged arrays live in the IPC-mapped exchange buffer
         char* xb = h->xchg.as<char>();
-        if ((size_t)2 * world * grid * sizeof(PfPartial) > h->off_ts - h->off_part) return fail(BF_EINVAL, "cooperative grid of %d CTAs exceeds the exchange buffer", grid);
-        a.partials = reinterpret_cast<PfPartial*>(xb + h->off_part);
+        if (root_bytes > h->off_ts - h->off_part) return fail(BF_EINVAL, "%d block roots exceed the exchange buffer", nb_total);
+        a.broot = reinterpret_cast<PfPartial*>(xb + h->off_part);       // the peers store their roots here
+        a.off_root = (int)h->off_part;
         a.tilesum = reinterpret_cast<float*>(xb + h->off_ts);
         a.V = reinterpret_cast<float*>(xb + h->off_V); a.total = h->V.as<float>();
         a.off_part = (int)h->off_part; a.off_ts = (int)h->off_ts; a.off_V = (int)h->off_V;
@@ -684,7 +698,6 @@ struct PfRun {
       a.world = world; a.rank = rank; a.goff = rank * N; a.Ng = Ng; a.log2ng = log2ng; a.log2ns = log2n;
       a.tile_off = rank * (world > 1 ? ntiles : 0); a.ntiles_g = ntiles_g; a.phases = PF_PH_ALL;
       if (world == 1) {
-        CUDA_OK(cudaMemsetAsync(a.fold_ctr, 0, sizeof(unsigned int), s));
         void* params[] = {(void*)&h->mc, (void*)&a};
         CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NW * 32), params, smem, s));
         h->launches++;
@@ -705,7 +718,7 @@ struct PfRun {
         NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, s));
         continue;
       }
-      const size_t pf_floats = (size_t)grid * sizeof(PfPartial) / 4;
+      const size_t pf_floats = (size_t)nblocks * sizeof(PfPartial) / 4;       // this rank's block roots of one step
       int64_t nlaunch = 0;
       auto launch = [&](cudaStream_t st, int phases, int t, int Tl) -> int {
         PfFusedArgs p = a;
@@ -734,7 +747,7 @@ struct PfRun {
         LAUNCH_OK(); ++nlaunch;
         for (int t = 0; t < T; ++t) {
           if ((rc = launch(st, PF_PH_A, t, 1))) return rc;
-          float* pbase = reinterpret_cast<float*>(a.partials) + (size_t)(t & 1) * world * pf_floats;
+          float* pbase = reinterpret_cast<float*>(a.broot) + (size_t)(t & 1) * world * pf_floats;
           NCCL_OK(nc->AllGather(pbase + (size_t)rank * pf_floats, pbase, pf_floats, ncclFloat, h->comm, st));
           if ((rc = launch(st, PF_PH_B, t, 1))) return rc;
           NCCL_OK(nc->AllGather(a.tilesum + (size_t)rank * ntiles, a.tilesum, ntiles, ncclFloat, h->comm, st));
@@ -890,7 +903,9 @@ struct bf_gsf_s {
   DevBuf lconst, post_m;
   int64_t launches;
   bool have_carry;
-  bool unscented = false;   // bf_gsf_set_unscented: sigma points instead of Jacobians (k_ugsf)
+  bool unscented = false;   // bf_gsf_set_unscented / bf_gsf_set_legacy_moments: sigma points or draws instead of Jacobians (k_ugsf)
+  int uk_mode = 0, uk_np = 0;
+  unsigned long long uk_seed = 0;
   float uk_alpha = 1e-3f, uk_beta = 2.0f, uk_kappa = 0.0f;
   DevBuf uk_sqrt;           // [sqrtm(Q) | sqrtm(R)], BF_MAXD^2 floats each
   DevBuf carry_w, carry_m, carry_P;
@@ -982,7 +997,7 @@ struct GsfRun {
     a.out_weights = io->out_weights; a.out_means = io->out_means; a.out_covs = io->out_covs;
     a.out_pred_means = io->out_pred_means; a.out_pred_covs = io->out_pred_covs; a.out_loglik = io->out_loglik;
     a.out_mix_mean = io->out_mix_mean;
-    a.Q_t = io->Q_t; a.R_t = io->R_t;
+    a.Q_t = io->Q_t; a.R_t = io->R_t; a.mc_draws = io->mc_draws;
     // one warp per trial when the mixture fits CPL components per lane within the register budget
     // (state words per lane: CPL * (1 + dx + dx^2)); else one CTA per trial, one thread per component
     const int DXm = h->mc.dx, WORDS = 1 + DXm + DXm * DXm;
@@ -1007,6 +1022,7 @@ struct GsfRun {
       UkfArgs uk;
       uk.alpha = h->uk_alpha; uk.beta = h->uk_beta; uk.kappa = h->uk_kappa;
       uk.sqrtQ = h->uk_sqrt.as<float>(); uk.sqrtR = h->uk_sqrt.as<float>() + BF_MAXD * BF_MAXD;
+      uk.mode = h->uk_mode; uk.np = h->uk_np; uk.draws = io->mc_draws; uk.seed = h->uk_seed;
       const int threads = std::max(32, ((a.M + 31) / 32) * 32);
       void* params[] = {(void*)&h->mc, (void*)&a, (void*)&uk};
       CUDA_OK(cudaLaunchKernel(ks.ugsf, dim3(B), dim3(threads), params, 0, s));
@@ -1047,7 +1063,8 @@ extern "C" int bf_gsf_run(bf_gsf_handle h, const bf_gsf_io* io, void* stream) {
     a.out_pred_covs = io->out_pred_covs; a.out_loglik = io->out_loglik; a.out_mix_mean = io->out_mix_mean;
     a.Q_t = io->Q_t; a.R_t = io->R_t;                   // (their off-diagonal elements are ignored on this path)
     const size_t smem = gsf_large_smem_bytes(h->dx, h->dy, a.M);
-    const void* kl = bfk_gsf_large(h->dx == 40 ? 40 : 0);
+    const char* genv = getenv("BF_GSF_LARGE_GENERIC");        // experiments: the generic (any dx) instantiation also for dx = 40
+    const void* kl = bfk_gsf_large((h->dx == 40 && !(genv && genv[0] == '1')) ? 40 : 0);
     CUDA_OK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* params[] = {(void*)&a};
     CUDA_OK(cudaLaunchKernel(kl, dim3(h->cfg.num_trials), dim3(GL_WARPS * 32), params, smem, (cudaStream_t)stream));
@@ -1096,7 +1113,19 @@ extern "C" int bf_gsf_set_unscented(bf_gsf_handle h, float alpha, float beta, fl
   sym_sqrt_host(h->mc.R, h->mc.dr, host + BF_MAXD * BF_MAXD);
   if (h->uk_sqrt.ensure(sizeof host)) return fail(BF_ENOMEM, "cudaMalloc failed");
   CUDA_OK(cudaMemcpy(h->uk_sqrt.p, host, sizeof host, cudaMemcpyHostToDevice));
-  h->unscented = true; h->uk_alpha = alpha; h->uk_beta = beta; h->uk_kappa = kappa;
+  h->unscented = true; h->uk_mode = 0; h->uk_alpha = alpha; h->uk_beta = beta; h->uk_kappa = kappa;
+  return BF_OK;
+}
+
+extern "C" int bf_gsf_set_legacy_moments(bf_gsf_handle h, int32_t kind, float alpha, float beta, float kappa, int32_t num_particles, uint64_t seed) {
+  if (!h) return fail(BF_EINVAL, "NULL argument");
+  if (h->large) return fail(BF_ENOMODEL, "the legacy moment approximations run on the register-resident models only");
+  if (kind != BF_LEGACY_UKF && kind != BF_LEGACY_MCF) return fail(BF_EINVAL, "kind must be BF_LEGACY_UKF or BF_LEGACY_MCF");
+  if (h->mc.dq != h->mc.dx) return fail(BF_EINVAL, "the legacy classes have additive noise: dq must equal dx");
+  if (kind == BF_LEGACY_MCF && num_particles < 1) return fail(BF_EINVAL, "num_particles must be >= 1");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  if (h->uk_sqrt.ensure(2 * BF_MAXD * BF_MAXD * 4)) return fail(BF_ENOMEM, "cudaMalloc failed");
+  h->unscented = true; h->uk_mode = kind; h->uk_alpha = alpha; h->uk_beta = beta; h->uk_kappa = kappa; h->uk_np = num_particles; h->uk_seed = seed;
   return BF_OK;
 }
 
@@ -1131,6 +1160,7 @@ extern "C" int bf_gsf_run_host(bf_gsf_handle h, const bf_gsf_io* hio) {
   }
   IN(Q_t, T * h->mc.dq * h->mc.dq)
   IN(R_t, T * h->mc.dr * h->mc.dr)
+  IN(mc_draws, B * T * M * 2 * (size_t)std::max(h->uk_np, 1) * dx)
   OUT(out_weights, B * T * M) OUT(out_means, B * T * M * dx) OUT(out_covs, B * T * M * dx * dx)
   OUT(out_pred_means, B * T * M * dx) OUT(out_pred_covs, B * T * M * dx * dx) OUT(out_loglik, B * T) OUT(out_mix_mean, B * T * dx)
 #undef IN

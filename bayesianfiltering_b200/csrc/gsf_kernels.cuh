@@ -27,6 +27,7 @@ struct GsfArgs {
   float* out_weights; float* out_means; float* out_covs; float* out_pred_means; float* out_pred_covs;
   float* out_loglik; float* out_mix_mean;
   const float* Q_t; const float* R_t;                   // [T,DQ,DQ] / [T,DY,DY] time-varying covariances or NULL (k_gsf only)
+  const float* mc_draws;                                // legacy MCF: [B,T,M,2,np,DX] offsets x - m, or NULL (k_ugsf mode 2)
 };
 
 // C[RxC] = A[RxK] @ B[KxC]

@@ -52,7 +52,7 @@ static inline size_t gsf_large_smem_bytes(int dx, int dy, int M) {
 // DXT: compile-time state dimension (0 = read it from LargeConst): index arithmetic folds, and for DXT = 40 the two
 // rank-dy products are register-tiled.
 template <int DXT>
-__global__ void __launch_bounds__(GL_WARPS * 32)
+__global__ void __launch_bounds__(GL_WARPS * 32, 2)
 k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
   extern __shared__ __align__(16) float smem[];
   const LargeConst& lc = *a.lc;
@@ -125,6 +125,10 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
       const float* msrc = fresh ? a.init_means + bm * dx : a.carry_m + bm * dx;
       const float* Psrc = fresh ? (a.init_covs ? a.init_covs + bm * dx * dx : lc.P0) : a.carry_P + bm * dx * dx;
       for (int i = lane; i < dx; i += 32) mv[i] = msrc[i];
+      if (!fresh && m + GL_WARPS < M) {                        // this warp's NEXT component: start its 6.4 KB on the way to L2 now
+        const char* nxt = reinterpret_cast<const char*>(a.carry_P + (bm + GL_WARPS) * dx * dx);
+        for (int off = lane * 128; off < dx * dx * 4; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
+      }
 #pragma unroll 4
       for (int i = lane; i < dx * dx / 4; i += 32)           // dx is even: dx^2 is a multiple of 4, rows are 16-byte aligned
         reinterpret_cast<float4*>(P)[i] = reinterpret_cast<const float4*>(Psrc)[i];
@@ -242,6 +246,7 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
           __syncwarp();
         }
       }
+      float pt[DXT == 40 ? 5 : 1][DXT == 40 ? 10 : 1];     // DXT = 40: this lane's 5 x 10 tile of the posterior covariance
       if constexpr (DXT == 40) {
         // register tiles: lane = (row group of 5) x (column group): 25 / 50 accumulators, 10 / 15 loads per 25 / 50 FMAs
         const int rg = lane >> 2, cg = lane & 3;
@@ -288,7 +293,13 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
 #pragma unroll
           for (int i = 0; i < 5; ++i)
 #pragma unroll
-            for (int j = 0; j < 10; ++j) P[(5 * rg + i) * 40 + 10 * cg + j] -= acc[i][j];      // P - (K S) K^T  (inference.py:101)
+            for (int j = 0; j < 10; ++j) pt[i][j] = P[(5 * rg + i) * 40 + 10 * cg + j] - acc[i][j];      // P - (K S) K^T  (inference.py:101)
+          if (a.out_covs) {                                  // only a requested output needs the posterior back in shared memory
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+              for (int j = 0; j < 10; ++j) P[(5 * rg + i) * 40 + 10 * cg + j] = pt[i][j];
+          }
         }
       } else {
         for (int idx = lane; idx < dx * dy; idx += 32) {           // K S,  K = X^T
@@ -312,29 +323,50 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
         mv[i] += s;
       }
       __syncwarp();
-      // log N(y; h(m), S): Cholesky of the un-jittered S (TFP), column by column, in Sj
-      float logdet = 0.0f;
-      for (int j = 0; j < dy; ++j) {                             // dy <= 32: lane l owns row j + l of column j
-        const int i = j + lane;
-        float v = 0.0f;
-        if (i < dy) {
-          v = S[i * dy + j];
-          for (int k = 0; k < j; ++k) v -= Sj[i * dy + k] * Sj[j * dy + k];
+      // log N(y; h(m), S) with the un-jittered S (TFP: Cholesky + forward substitution)
+      float logdet = 0.0f, ss = 0.0f;
+      if constexpr (DXT == 40) {
+        // S = L D L^T by the same register-resident elimination (lane k < 20 owns column k of S, lane 20 the innovation):
+        // z' = L^-1 d,  ||chol(S)^-1 d||^2 = sum z'_k^2 / D_k,  sum log diag chol(S) = 0.5 sum log D_k
+        float c0[20];
+#pragma unroll
+        for (int j = 0; j < 20; ++j) c0[j] = (lane < 20) ? S[j * 20 + lane] : ((lane == 20) ? dv[j] : 0.0f);
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+          const float piv = __shfl_sync(BF_FULL, c0[k], k);
+          const float zk = __shfl_sync(BF_FULL, c0[k], 20);
+          const float rp = __frcp_rn(piv);
+          logdet += 0.5f * logf(piv);
+          ss = fmaf(zk * zk, rp, ss);
+#pragma unroll
+          for (int r = k + 1; r < 20; ++r) {
+            const float l = __shfl_sync(BF_FULL, c0[r], k) * rp;
+            c0[r] = fmaf(-l, c0[k], c0[r]);
+          }
         }
-        const float ljj = sqrtf(__shfl_sync(BF_FULL, v, 0));     // lane 0 holds the diagonal element
-        logdet += logf(ljj);
-        if (i < dy) Sj[i * dy + j] = (i == j) ? ljj : v / ljj;
-        __syncwarp();
-      }
-      float ss = 0.0f;
-      for (int i = 0; i < dy; ++i) {                             // forward substitution (uniform across the warp)
-        float s = dv[i];
-        for (int k = 0; k < i; ++k) s -= Sj[i * dy + k] * zv[k];
-        const float z = s / Sj[i * dy + i];
-        __syncwarp();
-        if (lane == 0) zv[i] = z;
-        __syncwarp();
-        ss += z * z;
+      } else {
+      // log N(y; h(m), S): Cholesky of the un-jittered S (TFP), column by column, in Sj
+        for (int j = 0; j < dy; ++j) {                             // dy <= 32: lane l owns row j + l of column j
+          const int i = j + lane;
+          float v = 0.0f;
+          if (i < dy) {
+            v = S[i * dy + j];
+            for (int k = 0; k < j; ++k) v -= Sj[i * dy + k] * Sj[j * dy + k];
+          }
+          const float ljj = sqrtf(__shfl_sync(BF_FULL, v, 0));     // lane 0 holds the diagonal element
+          logdet += logf(ljj);
+          if (i < dy) Sj[i * dy + j] = (i == j) ? ljj : v / ljj;
+          __syncwarp();
+        }
+        for (int i = 0; i < dy; ++i) {                             // forward substitution (uniform across the warp)
+          float s = dv[i];
+          for (int k = 0; k < i; ++k) s -= Sj[i * dy + k] * zv[k];
+          const float z = s / Sj[i * dy + i];
+          __syncwarp();
+          if (lane == 0) zv[i] = z;
+          __syncwarp();
+          ss += z * z;
+        }
       }
       if (lane == 0) s_ll[m] = -0.5f * ss - logdet - 0.5f * (float)dy * 1.8378770664093453f;
       // posterior outputs, and the posterior mean for the mixture mean after the reweighting
@@ -346,16 +378,84 @@ k_gsf_large(const __grid_constant__ GsfLargeArgs a) {
       if (a.out_covs) for (int i = lane; i < dx * dx; i += 32) a.out_covs[btm * dx * dx + i] = P[i];
       __syncwarp();
       // ---- `_predict`, then the carry goes back to HBM
-      predict(u);
-      for (int i = lane; i < dx; i += 32) {
-        a.carry_m[bm * dx + i] = mv[i];
-        if (a.out_pred_means) a.out_pred_means[btm * dx + i] = mv[i];
-      }
+      if constexpr (DXT == 40) {
+        // F P F^T on the 5 x 10 register tiles: F has 4 non-zeros per row (columns i-2, i-1, i, i+1, cyclic), so F P mixes a
+        // tile with two rows of the lane above and one of the lane below, (F P) F^T with two columns of the lane to the left
+        // and one to the right -- warp shuffles; the covariance never returns to shared memory and goes to HBM from registers
+        const int rg = lane >> 2, cg = lane & 3;
+        for (int i = lane; i < 40; i += 32) {
+          const float xm1 = mv[wrap(i - 1)], xm2 = mv[wrap(i - 2)], xp1 = mv[wrap(i + 1)];
+          fa[i] = dt * xm1;
+          fb[i] = dt * (xp1 - xm2);
+          mn[i] = mv[i] + dt * ((xp1 - xm2) * xm1 - mv[i] + lc.F) + lc.q0[i];
+        }
+        __syncwarp();
+        const int up = (((rg + 7) & 7) << 2) | cg, dn = (((rg + 1) & 7) << 2) | cg;
+        const int lf = (rg << 2) | ((cg + 3) & 3), rt = (rg << 2) | ((cg + 1) & 3);
+        float fp[5][10];
+        {
+          float e0[10], e1[10], e7[10];                    // rows i-2, i-1 of the first tile row; row i+1 of the last
+#pragma unroll
+          for (int j = 0; j < 10; ++j) {
+            e0[j] = __shfl_sync(BF_FULL, pt[3][j], up); e1[j] = __shfl_sync(BF_FULL, pt[4][j], up);
+            e7[j] = __shfl_sync(BF_FULL, pt[0][j], dn);
+          }
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            const float far = fa[5 * rg + r], fbr = fb[5 * rg + r];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+              const float m2 = (r == 0) ? e0[j] : (r == 1) ? e1[j] : pt[r >= 2 ? r - 2 : 0][j];
+              const float m1 = (r == 0) ? e1[j] : pt[r >= 1 ? r - 1 : 0][j];
+              const float p1 = (r == 4) ? e7[j] : pt[r < 4 ? r + 1 : 4][j];
+              fp[r][j] = -far * m2 + fbr * m1 + onemdt * pt[r][j] + far * p1;
+            }
+          }
+        }
+        float fac[10], fbc[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) { fac[j] = fa[10 * cg + j]; fbc[j] = fb[10 * cg + j]; }
+        float* cP = a.carry_P + bm * 1600;
+        float* oP = a.out_pred_covs ? a.out_pred_covs + btm * 1600 : nullptr;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const float l0 = __shfl_sync(BF_FULL, fp[r][8], lf), l1 = __shfl_sync(BF_FULL, fp[r][9], lf);
+          const float r0 = __shfl_sync(BF_FULL, fp[r][0], rt);
+          float o[10];
+#pragma unroll
+          for (int j = 0; j < 10; ++j) {
+            const float m2 = (j == 0) ? l0 : (j == 1) ? l1 : fp[r][j >= 2 ? j - 2 : 0];
+            const float m1 = (j == 0) ? l1 : fp[r][j >= 1 ? j - 1 : 0];
+            const float p1 = (j == 9) ? r0 : fp[r][j < 9 ? j + 1 : 9];
+            const float v = -fac[j] * m2 + fbc[j] * m1 + onemdt * fp[r][j] + fac[j] * p1;
+            const int gi = 5 * rg + r, gc = 10 * cg + j;
+            o[j] = v + (cov_plus_p ? pt[r][j] : ((gi == gc) ? qdp[gi * qds] : 0.0f));
+          }
+          float2* dst = reinterpret_cast<float2*>(cP + (5 * rg + r) * 40 + 10 * cg);       // 40-byte aligned rows of 10 floats
+#pragma unroll
+          for (int j = 0; j < 5; ++j) dst[j] = make_float2(o[2 * j], o[2 * j + 1]);
+          if (oP) {
+            float2* d2 = reinterpret_cast<float2*>(oP + (5 * rg + r) * 40 + 10 * cg);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) d2[j] = make_float2(o[2 * j], o[2 * j + 1]);
+          }
+        }
+        for (int i = lane; i < 40; i += 32) {
+          a.carry_m[bm * 40 + i] = mn[i];
+          if (a.out_pred_means) a.out_pred_means[btm * 40 + i] = mn[i];
+        }
+      } else {
+        predict(u);
+        for (int i = lane; i < dx; i += 32) {
+          a.carry_m[bm * dx + i] = mv[i];
+          if (a.out_pred_means) a.out_pred_means[btm * dx + i] = mv[i];
+        }
 #pragma unroll 4
-      for (int i = lane; i < dx * dx / 4; i += 32)
-        reinterpret_cast<float4*>(a.carry_P + bm * dx * dx)[i] = reinterpret_cast<const float4*>(P)[i];
-      if (a.out_pred_covs) for (int i = lane; i < dx * dx; i += 32) {
-        a.out_pred_covs[btm * dx * dx + i] = P[i];
+        for (int i = lane; i < dx * dx / 4; i += 32)
+          reinterpret_cast<float4*>(a.carry_P + bm * dx * dx)[i] = reinterpret_cast<const float4*>(P)[i];
+        if (a.out_pred_covs) for (int i = lane; i < dx * dx; i += 32) {
+          a.out_pred_covs[btm * dx * dx + i] = P[i];
+        }
       }
       __syncwarp();
     }

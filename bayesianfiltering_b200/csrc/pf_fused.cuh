@@ -64,7 +64,17 @@ struct PfFusedArgs {
   int use_tau;                               // N = 2^k >= 8: E holds the effective thresholds tau
   float* tilesum;                            // [ntiles]
   float* Etile;                              // [ntiles+1]
-  PfPartial* partials;                       // [2*gridDim.x]
+  // Step statistics (max, sum e, sum e^2, sum e x) are reduced over a CANONICAL binary tree of the particle index, so that
+  // their bits do not depend on the grid, the warp assignment or the number of GPUs: a UNIT = 512 consecutive particles
+  // (4 chunks, one warp, 16 particles per lane) -> a BLOCK = `bsz` consecutive units (power of two <= 256), folded by the
+  // warp that completes it (ticket) -> the block roots of the whole filter, folded by the last CTA out of the phase (or, in a
+  // sharded filter, by every CTA of every rank after the roots have been exchanged).
+  UnitRec* upart;                            // [nunits] unit partials of this rank, tagged (published without a fence)
+  unsigned int run_tag;                      // distinguishes this run's tags from a previous run's in the same buffer
+  PfPartial* broot;                          // [2][nb_total] block roots of the whole filter, by step parity
+  unsigned int* bctr;                        // [nblocks] tickets (never reset within a run: counted modulo the block's size)
+  int nunits, bsz, nblocks, nb_total, blk_off;   // units of this rank; units per block; blocks of this rank / of the filter; this rank's first block
+  int off_root;                              // byte offset of broot inside an exchange buffer (sharded, p2p)
   StepStats* carry_stats;                    // [1] in (resume) / out
   const float* noise;                        // + (t*B + trial)*N*DQ, or NULL (Philox)
   const float* res_u;                        // multinomial + (t*B + trial)*N ; systematic + t*B + trial ; or NULL
@@ -428,6 +438,39 @@ __device__ __forceinline__ void load_state_cg(const float* base, size_t i, float
   }
 }
 
+// Cold pieces of the canonical statistics tree, kept out of line so that their registers (eight accumulators; a stack of
+// twelve) do not weigh on the hot loop's allocation.
+// One warp folds the `gsize` (<= 256) unit partials of a block as the balanced binary tree over the unit index: 8 consecutive
+// units per lane (tree of 8), then a butterfly of merges, adjacent lanes first.  Lane 0 stores the root.
+template <int DX>
+__device__ __noinline__ void fold_block(const UnitRec* up, int gsize, unsigned tag, PfPartial* out) {
+  const int lane = threadIdx.x & 31;
+  OnlineAcc<DX> v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j].init();
+    if (lane * 8 + j < gsize) v[j].load_tagged(up + lane * 8 + j, tag);
+  }
+  v[0].merge_acc(v[1]); v[2].merge_acc(v[3]); v[4].merge_acc(v[5]); v[6].merge_acc(v[7]);
+  v[0].merge_acc(v[2]); v[4].merge_acc(v[6]);
+  v[0].merge_acc(v[4]);
+  v[0].warp_tree_reduce();
+  if (lane == 0) v[0].store(out);
+}
+// balanced tree over the aligned range [first, first + R) of block roots (R a power of two > 2; N >= 2^28 only), by binary carries
+template <int DX>
+__device__ __noinline__ void fold_root_range(const PfPartial* roots, int first, int R, int nroots, PfPartial* out) {
+  OnlineAcc<DX> st[12], cur;
+  for (int i = 0; i < R; ++i) {
+    cur.init();
+    if (first + i < nroots) cur.load(roots + first + i);
+    int lv = 0;
+    for (int bits = i; bits & 1; bits >>= 1, ++lv) { OnlineAcc<DX> l = st[lv]; l.merge_acc(cur); cur = l; }
+    st[lv] = cur;
+  }
+  cur.store(out);
+}
+
 // SH: the sharded-filter code paths (peer tables, staging of remote ancestor ranges, cross-GPU barriers) are compiled
 // only into the SH = true instantiation; the one-GPU kernel does not carry their registers.
 template <class M, int CW, int CTAS_PER_SM, bool SH, bool LEAN>
@@ -458,7 +501,6 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   int* s_lo = reinterpret_cast<int*>(s_meta_f + 2 * tpc);       // [TW*tpc + 2] tau window start of each chunk
   float* s_win = s_dyn + (((3 * TW + 2) * tpc + 2 + 3) & ~3);   // 16-byte aligned (vector accesses to the histogram)
   float* s_xst = s_win + CW * WINCAP;                           // [CW][XCAP*DX], sharded filters only (host sizes it)
-  __shared__ PfPartial s_part[CW];
   __shared__ __align__(16) StepStats s_stats;
   __shared__ int s_last;                              // this CTA took the last ticket of the step (it folds the statistics)
   __shared__ int s_ctr[4];                            // chunk queues of phases A / B / C2
@@ -740,48 +782,61 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   auto trace = [&](int, int) {};
 #endif
 
-  // Fold the CTA partials of step t into the step's statistics (s_stats).  The order is fixed -- thread b takes
-  // partial b, b + NT, ...; then lanes, then warps -- so whoever folds gets the same bits.  All threads call it.
+  // Fold the block roots of step t into the step's statistics (s_stats): the balanced binary tree over the block index,
+  // level by level in shared memory (the tau-window area, idle here).  Whoever folds gets the same bits.  All threads call it.
   auto fold_statistics = [&](OnlineAcc<DX>& acc, int t, int pt, bool outputs_by_cta0) {
+    const PfPartial* roots = a.broot + (size_t)(pt & 1) * a.nb_total;
+    int P2 = 2;
+    while (P2 < a.nb_total) P2 <<= 1;
+    const int R = max(2, P2 / NT);                     // roots per thread at the bottom level (a power of two)
     acc.init();
-    for (int b = tid; b < a.world * G; b += NT) {     // same order in every CTA of every rank: bit-identical stats
-      const PfPartial* p = &a.partials[(size_t)(pt & 1) * a.world * G + b];
-      float sx[DX];
+    if (R == 2) {
+      if (2 * tid < a.nb_total) acc.load(roots + 2 * tid);
+      if (2 * tid + 1 < a.nb_total) { OnlineAcc<DX> o; o.load(roots + 2 * tid + 1); acc.merge_acc(o); }
+    } else {
+      PfPartial tmp;
+      fold_root_range<DX>(roots, tid * R, R, a.nb_total, &tmp);
+      acc.m = tmp.m; acc.s = tmp.s; acc.s2 = tmp.s2;
 #pragma unroll
-      for (int k = 0; k < DX; ++k) sx[k] = __ldcg(&p->sx[k]);
-      acc.merge(__ldcg(&p->m), __ldcg(&p->s), __ldcg(&p->s2), sx);
+      for (int k = 0; k < DX; ++k) acc.sx[k] = tmp.sx[k];
     }
-    acc.warp_reduce();
-    if (lane == 0) {
-      s_part[warp].m = acc.m; s_part[warp].s = acc.s; s_part[warp].s2 = acc.s2;
+    float* tr = s_win;                                 // [3 + DX][NT]
+    const int nent = (P2 + R - 1) / R;                 // entries at the bottom level of the shared-memory tree (<= NT)
+    tr[tid] = acc.m; tr[NT + tid] = acc.s; tr[2 * NT + tid] = acc.s2;
 #pragma unroll
-      for (int k = 0; k < DX; ++k) s_part[warp].sx[k] = acc.sx[k];
-    }
+    for (int k = 0; k < DX; ++k) tr[(3 + k) * NT + tid] = acc.sx[k];
     __syncthreads();
-    if (warp == 0) {
-      acc.init();
-      if (lane < CW) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
-      acc.warp_reduce();
-      if (lane == 0) {
-        StepStats st;
-        st.mx = acc.m; st.Z = acc.s;
-        st.loglik = acc.m + logf(acc.s);                       // log p(y_t | y_1:t-1)
-        st.ess = acc.s * acc.s / acc.s2;                       // 1 / sum (e/Z)^2   (inference.py:1356)
-        st.flag = (st.ess < a.ess_threshold * (float)Ng) ? 1 : 0;
-        st.w_uniform = st.flag;
-        st.pad0 = st.pad1 = 0;
+    for (int st2 = 1; st2 < nent; st2 <<= 1) {
+      if ((tid & (2 * st2 - 1)) == 0 && tid + st2 < nent) {
+        float osx[DX];
 #pragma unroll
-        for (int k = 0; k < BF_MAXD; ++k) st.mean[k] = (k < DX) ? acc.sx[k] / acc.s : 0.0f;
-        s_stats = st;
-        if (blockIdx.x == 0 && !all_phases) a.carry_stats[(pt + 1) & 1] = st;
-        if ((blockIdx.x == 0 || !outputs_by_cta0) && a.rank == 0) {
-          if (a.out_loglik) a.out_loglik[t] = st.loglik;
-          if (a.out_ess) a.out_ess[t] = st.ess;
-          if (a.out_resampled) a.out_resampled[t] = st.flag;
-          if (a.out_mean) {
+        for (int k = 0; k < DX; ++k) osx[k] = tr[(3 + k) * NT + tid + st2];
+        acc.merge(tr[tid + st2], tr[NT + tid + st2], tr[2 * NT + tid + st2], osx);
+        tr[tid] = acc.m; tr[NT + tid] = acc.s; tr[2 * NT + tid] = acc.s2;
 #pragma unroll
-            for (int k = 0; k < DX; ++k) a.out_mean[(size_t)t * DX + k] = st.mean[k];
-          }
+        for (int k = 0; k < DX; ++k) tr[(3 + k) * NT + tid] = acc.sx[k];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      StepStats st;
+      st.mx = acc.m; st.Z = acc.s;
+      st.loglik = acc.m + logf(acc.s);                       // log p(y_t | y_1:t-1)
+      st.ess = acc.s * acc.s / acc.s2;                       // 1 / sum (e/Z)^2   (inference.py:1356)
+      st.flag = (st.ess < a.ess_threshold * (float)Ng) ? 1 : 0;
+      st.w_uniform = st.flag;
+      st.pad0 = st.pad1 = 0;
+#pragma unroll
+      for (int k = 0; k < BF_MAXD; ++k) st.mean[k] = (k < DX) ? acc.sx[k] / acc.s : 0.0f;
+      s_stats = st;
+      if (blockIdx.x == 0 && !all_phases) a.carry_stats[(pt + 1) & 1] = st;
+      if ((blockIdx.x == 0 || !outputs_by_cta0) && a.rank == 0) {
+        if (a.out_loglik) a.out_loglik[t] = st.loglik;
+        if (a.out_ess) a.out_ess[t] = st.ess;
+        if (a.out_resampled) a.out_resampled[t] = st.flag;
+        if (a.out_mean) {
+#pragma unroll
+          for (int k = 0; k < DX; ++k) a.out_mean[(size_t)t * DX + k] = st.mean[k];
         }
       }
     }
@@ -808,8 +863,15 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     // ------------------------------------------------------------------ phase A
     if (a.phases & PF_PH_A) {
     if (gather) begin_gather(t - 1);
+    // Warps take UNITS of 4 consecutive chunks (512 particles): a lane's 16 particles are accumulated in index order and the
+    // unit is reduced at once, so the unit partial is a function of the data alone (see PfFusedArgs::upart).
+    for (int un = next_chunk(0); un < nchunk_cta / 4; un = next_chunk(0)) {
+    const int lu = cta_base / 512 + un;                // unit index within this rank
+    if (lu >= a.nunits) break;                         // tile padding past N
     acc.init();
-    for (int q = next_chunk(0); q < nchunk_valid; q = next_chunk(0)) {
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const int q = 4 * un + c4;
+      if (q >= nchunk_valid) break;
       const int base = cta_base + 128 * q + lane * 4;
       const int nv = max(0, min(4, N - base));
       int anc[4] = {a.goff + base, a.goff + base + 1, a.goff + base + 2, a.goff + base + 3};     // global indices
@@ -913,50 +975,49 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
       *reinterpret_cast<float4*>(a.LL + base) = make_float4(llv[0], llv[1], llv[2], llv[3]);
     }
-    acc.warp_reduce();
+    // unit partial -> global; the warp that completes a block folds it (balanced tree over the block's units)
+    acc.unit_reduce();
+    const int lb = lu / a.bsz;
+    unsigned tk = 0;
+    const unsigned utag = (a.run_tag << 20) ^ (unsigned)(t + a.t_offset + 1);
     if (lane == 0) {
-      s_part[warp].m = acc.m; s_part[warp].s = acc.s; s_part[warp].s2 = acc.s2;
-#pragma unroll
-      for (int k = 0; k < DX; ++k) s_part[warp].sx[k] = acc.sx[k];
+      acc.store_tagged(a.upart + lu, utag);            // no fence: the folding warp validates the tags
+      tk = atomicAdd(a.bctr + lb, 1u);
     }
+    tk = __shfl_sync(BF_FULL, tk, 0);
+    const int gsize = min(a.bsz, a.nunits - lb * a.bsz);
+    if ((tk + 1u) % (unsigned)gsize == 0u) {
+      const size_t ridx = (size_t)(pt & 1) * a.nb_total + a.blk_off + lb;
+      fold_block<DX>(a.upart + (size_t)lb * a.bsz, gsize, utag, a.broot + ridx);
+      if (lane == 0) {
+        if (p2p) {                                     // the same root into every peer's exchange buffer
+          const PfPartial rootv = a.broot[ridx];
+          for (int r = 0; r < a.world; ++r) {
+            if (r == a.rank) continue;
+            reinterpret_cast<PfPartial*>(a.xchg_peers[r] + a.off_root)[ridx] = rootv;
+          }
+          __threadfence_system();
+        }
+        __threadfence();
+      }
+    }
+    }  // units
     if (tid == 0) { s_ctr[1] = 0; s_ctr[2] = 0; }      // queues of phases B and C2 (nobody is in them now)
 #ifndef BF_DYNAMIC_CHUNKS
     turn[1] = 0; turn[2] = 0;
 #endif
     __syncthreads();
-    if (warp == 0) {
-      acc.init();
-      if (lane < CW) acc.merge(s_part[lane].m, s_part[lane].s, s_part[lane].s2, s_part[lane].sx);
-      acc.warp_reduce();
-      if (lane == 0) {
-        const size_t pidx = ((size_t)(pt & 1) * a.world + a.rank) * G + blockIdx.x;
-        PfPartial* p = &a.partials[pidx];
-        p->m = acc.m; p->s = acc.s; p->s2 = acc.s2;
-#pragma unroll
-        for (int k = 0; k < DX; ++k) p->sx[k] = acc.sx[k];
-        if (p2p) {                                   // the same record into every peer's exchange buffer
-          for (int r = 0; r < a.world; ++r) {
-            if (r == a.rank) continue;
-            PfPartial* rp = reinterpret_cast<PfPartial*>(a.xchg_peers[r] + a.off_part) + pidx;
-            rp->m = acc.m; rp->s = acc.s; rp->s2 = acc.s2;
-#pragma unroll
-            for (int k = 0; k < DX; ++k) rp->sx[k] = acc.sx[k];
-          }
-          __threadfence_system();
-        }
-        if (!SH && all_phases) {                     // one-GPU run: take a ticket; the last CTA out folds for everybody
-          __threadfence();
-          const unsigned tk = atomicAdd(a.fold_ctr, 1u);
-          s_last = ((tk + 1u) % (unsigned)G == 0u) ? 1 : 0;
-        }
-      }
-    }
     if (!SH && all_phases) {
-      // Every CTA folding all G partials itself reads the same 13 KB at the same moment: measured 11 us of phase B
-      // (L2 hot spot).  The last CTA to finish phase A does it once, before the grid leaves the barrier, and the others
-      // fetch the 64-byte result.
+      // One-GPU run: the LAST CTA out of the phase (ticket) folds the block roots once, before the grid leaves the barrier,
+      // and the others fetch the 64-byte result (every CTA folding them itself was an 11 us L2 hot spot per step).
+      if (tid == 0) {
+        __threadfence();
+        const unsigned tkc = atomicAdd(a.fold_ctr, 1u);
+        s_last = ((tkc + 1u) % (unsigned)G == 0u) ? 1 : 0;
+      }
       __syncthreads();
       if (s_last) {
+        __threadfence();
         fold_statistics(acc, t, pt, false);
         if (tid == 0) {
           *a.fold_stats = s_stats;

@@ -32,6 +32,11 @@ struct StepStats {
 };
 
 struct PfPartial { float m, s, s2; float sx[BF_MAXD]; };
+// A unit partial as published to other warps WITHOUT a memory fence: four 16-byte records, each carrying the tag of the step
+// that wrote it.  A 16-byte aligned vector store is not torn, so a reader that finds the expected tag in a record has that
+// record's data; it spins on the (rare) record that has not landed yet.  (A __threadfence per unit -- it has to drain the
+// warp's outstanding particle stores -- cost 8 % of the propagate phase when measured.)
+struct __align__(16) UnitRec { float4 r[4]; };
 
 // ---------------------------------------------------------------- vectorised particle access
 template <int DX>
@@ -111,10 +116,76 @@ struct OnlineAcc {
     float a = (m == -INFINITY) ? 0.0f : expf(m - nm);
     float b = (om == -INFINITY) ? 0.0f : expf(om - nm);
     if (om != om || m != m) nm = NAN;             // NaN log-lik poisons the step like jnp.max does
-    s = s * a + os * b; s2 = s2 * a * a + os2 * b * b;
+    // (explicit mul / add, no fma: both partners of a butterfly must get the same bits from swapped arguments)
+    s = __fadd_rn(__fmul_rn(s, a), __fmul_rn(os, b)); s2 = __fadd_rn(__fmul_rn(s2, __fmul_rn(a, a)), __fmul_rn(os2, __fmul_rn(b, b)));
 #pragma unroll
-    for (int k = 0; k < DX; ++k) sx[k] = sx[k] * a + osx[k] * b;
+    for (int k = 0; k < DX; ++k) sx[k] = __fadd_rn(__fmul_rn(sx[k], a), __fmul_rn(osx[k], b));
     m = nm;
+  }
+  // ---- canonical reduction tree of the step statistics (pf_fused.cuh): the same binary tree over the particle index
+  // whatever the grid, the warp assignment or the number of GPUs a filter is sharded over.
+  __device__ __forceinline__ void merge_acc(const OnlineAcc& o) { merge(o.m, o.s, o.s2, o.sx); }
+  __device__ __forceinline__ void load(const PfPartial* p) {
+    m = __ldcg(&p->m); s = __ldcg(&p->s); s2 = __ldcg(&p->s2);
+#pragma unroll
+    for (int k = 0; k < DX; ++k) sx[k] = __ldcg(&p->sx[k]);
+  }
+  __device__ __forceinline__ void store_tagged(UnitRec* p, unsigned tag) const {
+    const float tg = __uint_as_float(tag);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (k < DX) ? sx[k < DX ? k : 0] : 0.0f;
+    __stcg(&p->r[0], make_float4(m, s, s2, tg));
+    __stcg(&p->r[1], make_float4(v[0], v[1], v[2], tg));
+    if (DX > 3) __stcg(&p->r[2], make_float4(v[3], v[4], v[5], tg));
+    if (DX > 6) __stcg(&p->r[3], make_float4(v[6], v[7], 0.0f, tg));
+  }
+  __device__ __forceinline__ void load_tagged(const UnitRec* p, unsigned tag) {
+    float v[8];
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      if (part == 2 && DX <= 3) break;
+      if (part == 3 && DX <= 6) break;
+      float4 q = __ldcg(&p->r[part]);
+      while (__float_as_uint(q.w) != tag) { __nanosleep(20); q = __ldcg(&p->r[part]); }
+      if (part == 0) { m = q.x; s = q.y; s2 = q.z; }
+      else { v[3 * part - 3] = q.x; v[3 * part - 2] = q.y; if (3 * part - 1 < 8) v[3 * part - 1] = q.z; }
+    }
+#pragma unroll
+    for (int k = 0; k < DX; ++k) sx[k] = v[k];
+  }
+  __device__ __forceinline__ void store(PfPartial* p) const {
+    p->m = m; p->s = s; p->s2 = s2;
+#pragma unroll
+    for (int k = 0; k < DX; ++k) p->sx[k] = sx[k];
+  }
+  // the 32 lane accumulators of one unit (512 consecutive particles, 16 per lane) -> the unit's partial, in every lane:
+  // one common maximum, one rescale per lane, then plain butterfly sums (adjacent lanes first)
+  __device__ __forceinline__ void unit_reduce() {
+    const bool anynan = __any_sync(BF_FULL, m != m);
+    const float mu = warp_max(m);
+    const float f = (m == -INFINITY) ? 0.0f : mufu_ex2((m - mu) * 1.44269504088896340736f);
+    s *= f; s2 *= f * f;
+#pragma unroll
+    for (int k = 0; k < DX; ++k) sx[k] *= f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      s = __fadd_rn(s, __shfl_xor_sync(BF_FULL, s, o)); s2 = __fadd_rn(s2, __shfl_xor_sync(BF_FULL, s2, o));
+#pragma unroll
+      for (int k = 0; k < DX; ++k) sx[k] = __fadd_rn(sx[k], __shfl_xor_sync(BF_FULL, sx[k], o));
+    }
+    m = anynan ? NAN : mu;
+  }
+  // butterfly of full merges, adjacent lanes first: the balanced binary tree over the lane index
+  __device__ __forceinline__ void warp_tree_reduce() {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float om = __shfl_xor_sync(BF_FULL, m, o), os = __shfl_xor_sync(BF_FULL, s, o), os2 = __shfl_xor_sync(BF_FULL, s2, o);
+      float osx[DX];
+#pragma unroll
+      for (int k = 0; k < DX; ++k) osx[k] = __shfl_xor_sync(BF_FULL, sx[k], o);
+      merge(om, os, os2, osx);
+    }
   }
   __device__ __forceinline__ void warp_reduce() {
 #pragma unroll

@@ -18,65 +18,77 @@
 // Update: K = solve(S + 1e-6, C)^T (psd_solve, LU), P+ = P - K S K^T, m+ = m + K (y - mu), ll = MVN(mu, S).log_prob(y).
 #pragma once
 #include "gsf_kernels.cuh"
+#include "agsf_kernels.cuh"      // chol_lower
 
+// mode 0: the reference's unscented_gaussian_sum_filter (noise-augmented sigma points, sqrtm).
+// mode 1: legacy gaussfilt.UKF.moment_approx (gaussfilt.py:146-170): ADDITIVE noise, 2 dx + 1 sigma points from the Cholesky
+//         factor of P (utils.split_to_sigma_points, utils.py:52-65), noise covariance added to the transformed covariance.
+// mode 2: legacy gaussfilt.MCF.moment_approx (gaussfilt.py:186-198): moments from `np` Monte-Carlo draws of N(m, P).
 struct UkfArgs {
   float alpha, beta, kappa;
-  const float* sqrtQ;       // [DQ,DQ] principal square root of Q (device)
+  const float* sqrtQ;       // [DQ,DQ] principal square root of Q (device)          (mode 0)
   const float* sqrtR;       // [DR,DR]
+  int mode;
+  int np;                   // mode 2: draws per moment approximation
+  const float* draws;       // mode 2: [B,T,M,2,np,DX] coloured offsets x - m (prediction draws, update draws), or NULL (Philox)
+  unsigned long long seed;
 };
 
-// principal square root of a symmetric PSD N x N matrix: cyclic Jacobi, every index compile-time (registers)
+// principal square root of a symmetric PSD N x N matrix: cyclic Jacobi, every index compile-time (registers).  The sweeps run
+// in float64: the covariances of the tracking models span five orders of magnitude (position 1e-1, velocity 1e-6) and a
+// float32 eigen-decomposition loses the small eigen-directions to ~1e-3 relative (measured against the reference fixtures);
+// N <= 4 here, so the float64 pipe is not a cost that matters.
 template <int N>
 __device__ __forceinline__ void sym_sqrt(const float* P, float* L) {
   if constexpr (N == 1) { L[0] = sqrtf(fmaxf(P[0], 0.0f)); return; }
-  float A[N * N], V[N * N];
+  double A[N * N], V[N * N];
 #pragma unroll
   for (int i = 0; i < N; ++i)
 #pragma unroll
-    for (int j = 0; j < N; ++j) { A[i * N + j] = 0.5f * (P[i * N + j] + P[j * N + i]); V[i * N + j] = (i == j) ? 1.0f : 0.0f; }
-  constexpr int SWEEPS = (N == 2) ? 1 : (N <= 4 ? 6 : 9);
+    for (int j = 0; j < N; ++j) { A[i * N + j] = 0.5 * ((double)P[i * N + j] + (double)P[j * N + i]); V[i * N + j] = (i == j) ? 1.0 : 0.0; }
+  constexpr int SWEEPS = (N == 2) ? 2 : (N <= 4 ? 8 : 12);
 #pragma unroll 1
   for (int sw = 0; sw < SWEEPS; ++sw) {
 #pragma unroll
     for (int p = 0; p < N - 1; ++p)
 #pragma unroll
       for (int q = p + 1; q < N; ++q) {
-        const float apq = A[p * N + q];
-        const float app = A[p * N + p], aqq = A[q * N + q];
+        const double apq = A[p * N + q];
+        const double app = A[p * N + p], aqq = A[q * N + q];
         // rotation that annihilates A[p][q]; skipped when it is already negligible against the diagonal
-        const bool rot = fabsf(apq) > 1e-12f * (fabsf(app) + fabsf(aqq)) && apq != 0.0f;
-        const float th = (aqq - app) / (2.0f * (rot ? apq : 1.0f));
-        const float tt = copysignf(1.0f, th) / (fabsf(th) + sqrtf(fmaf(th, th, 1.0f)));
-        const float cs = rot ? rsqrtf(fmaf(tt, tt, 1.0f)) : 1.0f;
-        const float sn = rot ? tt * cs : 0.0f;
+        const bool rot = fabs(apq) > 1e-300 && fabs(apq) > 1e-22 * (fabs(app) + fabs(aqq));
+        const double th = (aqq - app) / (2.0 * (rot ? apq : 1.0));
+        const double tt = copysign(1.0, th) / (fabs(th) + sqrt(fma(th, th, 1.0)));
+        const double cs = rot ? rsqrt(fma(tt, tt, 1.0)) : 1.0;
+        const double sn = rot ? tt * cs : 0.0;
 #pragma unroll
         for (int k = 0; k < N; ++k) {          // A <- A J   (columns p, q)
-          const float akp = A[k * N + p], akq = A[k * N + q];
+          const double akp = A[k * N + p], akq = A[k * N + q];
           A[k * N + p] = cs * akp - sn * akq; A[k * N + q] = sn * akp + cs * akq;
         }
 #pragma unroll
         for (int k = 0; k < N; ++k) {          // A <- J^T A (rows p, q)
-          const float apk = A[p * N + k], aqk = A[q * N + k];
+          const double apk = A[p * N + k], aqk = A[q * N + k];
           A[p * N + k] = cs * apk - sn * aqk; A[q * N + k] = sn * apk + cs * aqk;
         }
 #pragma unroll
         for (int k = 0; k < N; ++k) {          // V <- V J
-          const float vkp = V[k * N + p], vkq = V[k * N + q];
+          const double vkp = V[k * N + p], vkq = V[k * N + q];
           V[k * N + p] = cs * vkp - sn * vkq; V[k * N + q] = sn * vkp + cs * vkq;
         }
       }
   }
-  float rt[N];
+  double rt[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) rt[i] = sqrtf(fmaxf(A[i * N + i], 0.0f));
+  for (int i = 0; i < N; ++i) rt[i] = sqrt(fmax(A[i * N + i], 0.0));
 #pragma unroll
   for (int i = 0; i < N; ++i)
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      float s = 0.0f;
+      double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < N; ++k) s = fmaf(V[i * N + k] * rt[k], V[j * N + k], s);
-      L[i * N + j] = s;
+      for (int k = 0; k < N; ++k) s = fma(V[i * N + k] * rt[k], V[j * N + k], s);
+      L[i * N + j] = (float)s;
     }
 }
 
@@ -91,7 +103,8 @@ __device__ __forceinline__ void unscented(const float* m, const float* Lx, const
   const float ws = 1.0f / (2.0f * (lam + (float)n));
   const float wc = lam / (lam + (float)n);
   const float wcc = wc + 1.0f - alpha * alpha + beta;
-  float g0[DO], pts[2 * n][DO], nz0[DN];
+  constexpr int DNA = DN > 0 ? DN : 1;
+  float g0[DO], pts[2 * n][DO], nz0[DNA];
 #pragma unroll
   for (int k = 0; k < DN; ++k) nz0[k] = n0[k];
   g(m, nz0, g0);
@@ -99,7 +112,7 @@ __device__ __forceinline__ void unscented(const float* m, const float* Lx, const
   for (int i = 0; i < n; ++i) {
 #pragma unroll
     for (int sgn = 0; sgn < 2; ++sgn) {
-      float x[DX], nz[DN];
+      float x[DX], nz[DNA];
       const float cc = sgn ? -c : c;
 #pragma unroll
       for (int k = 0; k < DX; ++k) x[k] = (i < DX) ? fmaf(cc, Lx[k * DX + (i < DX ? i : 0)], m[k]) : m[k];
@@ -141,15 +154,11 @@ __device__ __forceinline__ void unscented(const float* m, const float* Lx, const
   }
 }
 
-// `_ukf_condition_on_nonadditive` (inference.py:198-224): m, P in/out; returns ll
-template <class Mo>
-__device__ __forceinline__ float ukf_condition(float* m, float* P, const float* y, float u, const ModelConst& mc, const UkfArgs& uk,
-                                               float jitter) {
-  constexpr int DX = Mo::DX, DY = Mo::DY, DR = Mo::DR;
-  float L[DX * DX], mu[DY], S[DY * DY], Sj[DY * DY], X[DY * DX];
-  sym_sqrt<DX>(P, L);
-  unscented<DX, DR, DY, true>(m, L, mc.r0, uk.sqrtR, uk.alpha, uk.beta, uk.kappa,
-                              [&](const float* x, const float* r, float* o) { Mo::h(x, r, u, mc, o); }, mu, S, X);
+// Gain, posterior and evidence from the moments (mu, S, C) of a transform: X holds C [DY,DX] on entry.
+//   K = solve(S + jitter, C)^T, P+ = P - K S K^T, m+ = m + K (y - mu), ll = MVN(mu, S).log_prob(y)
+template <int DX, int DY>
+__device__ __forceinline__ float kalman_from_moments(float* m, float* P, const float* y, const float* mu, const float* S, float* X, float jitter) {
+  float Sj[DY * DY];
 #pragma unroll
   for (int i = 0; i < DY * DY; ++i) Sj[i] = S[i] + jitter;      // psd_solve: + 1e-6 on EVERY element
   lu_solve<DY, DX>(Sj, X);                                     // X = solve(S', C);  K = X^T   (:222)
@@ -185,14 +194,127 @@ __device__ __forceinline__ float ukf_condition(float* m, float* P, const float* 
   return mvn_logpdf_chol<DY>(S, d);
 }
 
-// `_ukf_predict_nonadditive` (inference.py:146-174)
+// Monte-Carlo moments of g over N(m, P) (gaussfilt.MCF.moment_approx, gaussfilt.py:186-198): particles m + d_i with the
+// offsets d_i supplied (`dr` [np,DX]) or drawn here (Cholesky of P times Philox normals); two passes, g evaluated twice
+// rather than np transformed particles kept per thread.  Returns mu, S = cov + sample covariance, C [DO,DX] (if WITH_C).
+template <int DX, int DO, bool WITH_C, class G>
+__device__ __forceinline__ void mc_moments(const float* m, const float* P, const float* cov, int np, const float* dr,
+                                           unsigned long long seed, uint32_t stream, uint32_t t, uint32_t b, uint32_t comp, G g,
+                                           float* mu, float* S, float* C) {
+  float L[DX * DX];
+  if (!dr) chol_lower<DX>(P, L);
+  auto particle = [&](int i, float* x) {
+    if (dr) {
+#pragma unroll
+      for (int k = 0; k < DX; ++k) x[k] = m[k] + dr[(size_t)i * DX + k];
+    } else {
+      float z[DX];
+      philox_normals<DX>(seed, stream, t, b, ((uint64_t)comp << 32) | (uint32_t)i, z);
+#pragma unroll
+      for (int k = 0; k < DX; ++k) {
+        float s2 = m[k];
+#pragma unroll
+        for (int q = 0; q <= k; ++q) s2 = fmaf(L[k * DX + q], z[q], s2);
+        x[k] = s2;
+      }
+    }
+  };
+  const float inp = 1.0f / (float)np;
+#pragma unroll
+  for (int a = 0; a < DO; ++a) mu[a] = 0.0f;
+  for (int i = 0; i < np; ++i) {
+    float x[DX], o[DO];
+    particle(i, x);
+    g(x, o);
+#pragma unroll
+    for (int a = 0; a < DO; ++a) mu[a] += o[a];
+  }
+#pragma unroll
+  for (int a = 0; a < DO; ++a) mu[a] *= inp;
+#pragma unroll
+  for (int i = 0; i < DO * DO; ++i) S[i] = 0.0f;
+  if constexpr (WITH_C) {
+#pragma unroll
+    for (int i = 0; i < DO * DX; ++i) C[i] = 0.0f;
+  }
+  for (int i = 0; i < np; ++i) {
+    float x[DX], o[DO];
+    particle(i, x);
+    g(x, o);
+#pragma unroll
+    for (int a = 0; a < DO; ++a)
+#pragma unroll
+      for (int c = 0; c < DO; ++c) S[a * DO + c] = fmaf(o[a] - mu[a], o[c] - mu[c], S[a * DO + c]);
+    if constexpr (WITH_C) {
+#pragma unroll
+      for (int a = 0; a < DO; ++a)
+#pragma unroll
+        for (int k = 0; k < DX; ++k) C[a * DX + k] = fmaf(o[a] - mu[a], x[k] - m[k], C[a * DX + k]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < DO * DO; ++i) S[i] = fmaf(S[i], inp, cov[i]);
+  if constexpr (WITH_C) {
+#pragma unroll
+    for (int i = 0; i < DO * DX; ++i) C[i] *= inp;
+  }
+}
+
+// where the Monte-Carlo draws of (trial b, step t, component c, phase ph) start, or NULL
+__device__ __forceinline__ const float* mc_draws(const UkfArgs& uk, int b, int T, int t, int M, int c, int ph, int dx) {
+  if (!uk.draws || t >= T) return nullptr;
+  return uk.draws + (((((size_t)b * T + t) * M + c) * 2 + ph) * uk.np) * dx;
+}
+
+// update of one component: `_ukf_condition_on_nonadditive` (inference.py:198-224) or the legacy moment approximations
 template <class Mo>
-__device__ __forceinline__ void ukf_predict(float* m, float* P, float u, const ModelConst& mc, const UkfArgs& uk) {
+__device__ __forceinline__ float ukf_condition(float* m, float* P, const float* y, float u, const ModelConst& mc, const UkfArgs& uk,
+                                               float jitter, const float* dr, int t, int b, int comp) {
+  constexpr int DX = Mo::DX, DY = Mo::DY, DR = Mo::DR;
+  float L[DX * DX], mu[DY], S[DY * DY], X[DY * DX];
+  if (uk.mode == 0) {
+    sym_sqrt<DX>(P, L);
+    unscented<DX, DR, DY, true>(m, L, mc.r0, uk.sqrtR, uk.alpha, uk.beta, uk.kappa,
+                                [&](const float* x, const float* r, float* o) { Mo::h(x, r, u, mc, o); }, mu, S, X);
+  } else if (uk.mode == 1) {         // gaussfilt.UKF, 'upd': g(x) = h(x, 0, 0), + R
+    chol_lower<DX>(P, L);
+    float none[1] = {0.0f};
+    unscented<DX, 0, DY, true>(m, L, none, none, uk.alpha, uk.beta, uk.kappa,
+                               [&](const float* x, const float*, float* o) { float r0[DR]; for (int k = 0; k < DR; ++k) r0[k] = 0.0f; Mo::h(x, r0, u, mc, o); },
+                               mu, S, X);
+#pragma unroll
+    for (int i = 0; i < DY * DY; ++i) S[i] += mc.R[i];
+  } else {                           // gaussfilt.MCF, 'upd'
+    mc_moments<DX, DY, true>(m, P, mc.R, uk.np, dr, uk.seed, 32u, (uint32_t)t, (uint32_t)b, (uint32_t)comp,
+                             [&](const float* x, float* o) { float r0[DR]; for (int k = 0; k < DR; ++k) r0[k] = 0.0f; Mo::h(x, r0, u, mc, o); },
+                             mu, S, X);
+  }
+  return kalman_from_moments<DX, DY>(m, P, y, mu, S, X, jitter);
+}
+
+// prediction of one component: `_ukf_predict_nonadditive` (inference.py:146-174) or the legacy moment approximations ('pred')
+template <class Mo>
+__device__ __forceinline__ void ukf_predict(float* m, float* P, float u, const ModelConst& mc, const UkfArgs& uk, const float* dr,
+                                            int t, int b, int comp) {
   constexpr int DX = Mo::DX, DQ = Mo::DQ;
   float L[DX * DX], mu[DX], S[DX * DX];
-  sym_sqrt<DX>(P, L);
-  unscented<DX, DQ, DX, false>(m, L, mc.q0, uk.sqrtQ, uk.alpha, uk.beta, uk.kappa,
-                               [&](const float* x, const float* q, float* o) { Mo::f(x, q, u, mc, o); }, mu, S, nullptr);
+  if (uk.mode == 0) {
+    sym_sqrt<DX>(P, L);
+    unscented<DX, DQ, DX, false>(m, L, mc.q0, uk.sqrtQ, uk.alpha, uk.beta, uk.kappa,
+                                 [&](const float* x, const float* q, float* o) { Mo::f(x, q, u, mc, o); }, mu, S, nullptr);
+  } else {
+    // additive-noise legacy classes: f(x) = f(x, 0, 0), + Q (needs F_q = I, i.e. DQ == DX: checked on the host)
+    auto fx = [&](const float* x, float* o) { float q0[DQ]; for (int k = 0; k < DQ; ++k) q0[k] = 0.0f; Mo::f(x, q0, u, mc, o); };
+    if (uk.mode == 1) {
+      chol_lower<DX>(P, L);
+      float none[1] = {0.0f};
+      unscented<DX, 0, DX, false>(m, L, none, none, uk.alpha, uk.beta, uk.kappa, [&](const float* x, const float*, float* o) { fx(x, o); }, mu, S, nullptr);
+#pragma unroll
+      for (int i = 0; i < DX * DX; ++i) S[i] += mc.Q[(DQ == DX) ? i : 0];
+    } else {
+      mc_moments<DX, DX, false>(m, P, mc.Q, uk.np, dr, uk.seed, 31u, (uint32_t)t, (uint32_t)b, (uint32_t)comp, fx, mu, S, nullptr);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < DX; ++i) m[i] = mu[i];
 #pragma unroll
@@ -222,6 +344,10 @@ __global__ void k_ugsf(const __grid_constant__ ModelConst mc, const __grid_const
     for (int i = 0; i < DX * DX; ++i) P[i] = a.init_covs ? a.init_covs[bm * DX * DX + i] : mc.P0[i];
   }
   const float jitter = (a.flags & BF_GSF_NO_JITTER) ? 0.0f : 1e-6f;
+  const int comp = active ? tid : 0;
+  // legacy order (gaussfilt.py:108-113): the carry entering the call holds FILTERED moments -> predict first
+  if ((a.flags & BF_GSF_PREDICT_FIRST) && !a.resume)
+    ukf_predict<Mo>(m, P, a.inputs ? a.inputs[0] : 0.0f, mc, uk, mc_draws(uk, b, T, 0, M, comp, 0, DX), 0, b, comp);
   for (int t = 0; t < T; ++t) {
     const float* yp = a.emissions + ((size_t)(a.emissions_per_trial ? b : 0) * T + t) * DY;
     float y[DY];
@@ -229,7 +355,7 @@ __global__ void k_ugsf(const __grid_constant__ ModelConst mc, const __grid_const
     for (int k = 0; k < DY; ++k) y[k] = yp[k];
     const float u = a.inputs ? a.inputs[t] : 0.0f;
     const size_t btm = ((size_t)b * T + t) * M + (active ? tid : 0);
-    float ll = ukf_condition<Mo>(m, P, y, u, mc, uk, jitter);
+    float ll = ukf_condition<Mo>(m, P, y, u, mc, uk, jitter, mc_draws(uk, b, T, t, M, comp, 1, DX), t, b, comp);
     if (!active) ll = -INFINITY;
     if (active) {
       if (a.out_means) store_vec<DX>(a.out_means + btm * DX, m);
@@ -267,7 +393,10 @@ __global__ void k_ugsf(const __grid_constant__ ModelConst mc, const __grid_const
       }
     }
     __syncthreads();
-    ukf_predict<Mo>(m, P, u, mc, uk);
+    {   // predict-first order: this is the prediction of step t + 1 (its draws, if supplied, are those of t + 1)
+      const bool pf = (a.flags & BF_GSF_PREDICT_FIRST) != 0;
+      ukf_predict<Mo>(m, P, u, mc, uk, mc_draws(uk, b, T, pf ? t + 1 : t, M, comp, 0, DX), pf ? t + 1 : t, b, comp);
+    }
     if (active) {
       if (a.out_pred_means) store_vec<DX>(a.out_pred_means + btm * DX, m);
       if (a.out_pred_covs) store_vec<DX * DX>(a.out_pred_covs + btm * DX * DX, P);

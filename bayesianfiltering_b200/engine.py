@@ -248,8 +248,10 @@ class ShardedParticleFilterEngine(ParticleFilterEngine):
 class GaussianSumFilterEngine:
     """Owns a bf_gsf_handle: M components x B independent trials of one registry model."""
 
-    def __init__(self, host_model, num_components, num_trials=1, device=None, flags=0, unscented=None):
-        """unscented = (alpha, beta, kappa): the unscented Gaussian-sum filter (inference.py:379-456) instead of the EKF one."""
+    def __init__(self, host_model, num_components, num_trials=1, device=None, flags=0, unscented=None, legacy=None):
+        """unscented = (alpha, beta, kappa): the unscented Gaussian-sum filter (inference.py:379-456) instead of the EKF one.
+        legacy = ("ukf", alpha, beta, kappa) or ("mcf", num_particles, seed): the moment approximations of the legacy
+        gaussfilt.UKF / gaussfilt.MCF classes (gaussfilt.py:146-198)."""
         self.lib = _lib.load()
         self.hm = host_model
         self.M, self.B = int(num_components), int(num_trials)
@@ -258,9 +260,18 @@ class GaussianSumFilterEngine:
         cfg = _lib.GsfConfig(self.M, self.B, self.device, int(flags))
         self.h = C.c_void_p()
         _lib.check(self.lib.bf_gsf_create(C.byref(host_model.desc), C.byref(cfg), C.byref(self.h)))
+        self.mc_np = 0
         if unscented is not None:
             a, b, k = (float(v) for v in unscented)
             _lib.check(self.lib.bf_gsf_set_unscented(self.h, a, b, k))
+        if legacy is not None:
+            if legacy[0] == "ukf":
+                _lib.check(self.lib.bf_gsf_set_legacy_moments(self.h, _lib.LEGACY_UKF, float(legacy[1]), float(legacy[2]), float(legacy[3]), 0, 0))
+            elif legacy[0] == "mcf":
+                self.mc_np = int(legacy[1])
+                _lib.check(self.lib.bf_gsf_set_legacy_moments(self.h, _lib.LEGACY_MCF, 0.0, 0.0, 0.0, self.mc_np, int(legacy[2]) & 0xFFFFFFFFFFFFFFFF))
+            else:
+                raise ValueError(f"unknown legacy moment approximation {legacy[0]!r}")
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
@@ -278,7 +289,8 @@ class GaussianSumFilterEngine:
         B, M, dx = self.B, self.M, self.dx
         dq, dr = self.hm.desc.dq, self.hm.desc.dr
         return dict(emissions=((B, T, self.dy) if per_trial else (T, self.dy)), inputs=(T,), init_means=(B, M, dx),
-                    init_covs=(B, M, dx, dx), init_weights=(B, M), Q_t=(T, dq, dq), R_t=(T, dr, dr))
+                    init_covs=(B, M, dx, dx), init_weights=(B, M), Q_t=(T, dq, dq), R_t=(T, dr, dr),
+                    mc_draws=(B, T, M, 2, max(self.mc_np, 1), dx))
 
     def _io(self, T, per_trial, resume, ins, outs):
         io = _lib.GsfIO()
@@ -291,15 +303,16 @@ class GaussianSumFilterEngine:
 
     def run_host(self, emissions, inputs=None, init_means=None, init_covs=None, init_weights=None,
                  outputs=("weights", "means", "covariances", "predicted_means", "predicted_covariances"), resume=False,
-                 Q_t=None, R_t=None):
-        """Q_t [T,dq,dq] / R_t [T,dr,dr]: time-varying noise covariances (`_get_params`, inference.py:21)."""
+                 Q_t=None, R_t=None, mc_draws=None):
+        """Q_t [T,dq,dq] / R_t [T,dr,dr]: time-varying noise covariances (`_get_params`, inference.py:21).
+        mc_draws [B,T,M,2,np,dx]: the legacy Monte-Carlo filter's draws as offsets x - m (else Philox in the kernel)."""
         em = np.asarray(emissions, dtype=np.float32)
         per_trial = em.ndim == 3
         T = em.shape[-2]
         shp = self._in_shapes(T, per_trial)
         ins = {k: _np32(v, shp[k], k) for k, v in dict(emissions=em, inputs=inputs, init_means=init_means,
                                                         init_covs=init_covs, init_weights=init_weights,
-                                                        Q_t=Q_t, R_t=R_t).items()}
+                                                        Q_t=Q_t, R_t=R_t, mc_draws=mc_draws).items()}
         res, outs = {}, {}
         for name in outputs:
             if name not in GSF_OUTPUTS:

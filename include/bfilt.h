@@ -180,6 +180,10 @@ typedef struct bf_gsf_io {
      time-indexed by the reference: `_get_params(x, 2, t)` needs ndim 3.) */
   const float* Q_t;             /* [T,dq,dq] or NULL */
   const float* R_t;             /* [T,dr,dr] or NULL */
+  /* legacy Monte-Carlo filter only (bf_gsf_set_legacy_moments, kind MCF): the draws of every moment approximation as
+     offsets x - m ~ N(0, P): per step and component first the `num_particles` prediction draws, then the update draws.
+     NULL = drawn in the kernel (Cholesky of P times Philox normals). */
+  const float* mc_draws;        /* [B,T,M,2,num_particles,dx] or NULL */
 } bf_gsf_io;
 
 int bf_gsf_create(const bf_model_desc* model, const bf_gsf_config* cfg, bf_gsf_handle* out);
@@ -193,6 +197,16 @@ int bf_gsf_run_host(bf_gsf_handle h, const bf_gsf_io* host_io);
  * state per component instead of linearising; alpha, beta, kappa are the fields of the reference's ParamsUKF (:41-49).
  * Models with dx <= 4; constant noise covariances (Q_t / R_t must be NULL). */
 int bf_gsf_set_unscented(bf_gsf_handle h, float alpha, float beta, float kappa);
+/* Switch the handle to one of the LEGACY moment approximations of gaussfiltax/gaussfilt.py behind GaussFilt.run (:88-130) and
+ * gaussfilt.GaussSumFilt.run (:325-361): additive noise (dq = dx), single-argument f(x) = f(x,0,0), g(x) = h(x,0,0).
+ *   BF_LEGACY_UKF  UKF.moment_approx (:146-170): 2 dx + 1 sigma points from chol(P) (utils.split_to_sigma_points, utils.py:52-65)
+ *   BF_LEGACY_MCF  MCF.moment_approx (:186-198): num_particles Monte-Carlo draws of N(m, P) per moment approximation
+ * (EKF.moment_approx is the default kernel with BF_GSF_PREDICT_FIRST | BF_GSF_NO_JITTER; MCLAF.moment_approx cannot run in the
+ * reference either: gaussfilt.py:286 calls utils.sdp_opt with 8 arguments, utils.py:110 takes 7.)
+ * Create the handle with BF_GSF_PREDICT_FIRST | BF_GSF_NO_JITTER for the classes' predict-then-update order and plain inverse. */
+#define BF_LEGACY_UKF 1
+#define BF_LEGACY_MCF 2
+int bf_gsf_set_legacy_moments(bf_gsf_handle h, int32_t kind, float alpha, float beta, float kappa, int32_t num_particles, uint64_t seed);
 int bf_gsf_kernel_launches(bf_gsf_handle h, int64_t* out);
 int bf_gsf_destroy(bf_gsf_handle h);
 

@@ -203,10 +203,18 @@ def test_resident_and_streamed_agree_and_chunked_resume_is_exact(path):
     e2.close()
     for name in outs:
         assert np.array_equal(np.concatenate([a[name], b[name]], axis=1), full[name]), name
+    # The other kernel is the same filter, not the same bits: the resident kernel sums the weights per thread and CTA, the
+    # streamed one over its canonical tree (so that a filter sharded over GPUs equals the one-GPU filter), and a last-bit
+    # difference in a weight can move an ancestor.  Same estimates to fp32 round-off, and the same ancestors until such a flip.
     other = _engine(c, N, 1, 0.6, "multinomial", "streamed" if path == "resident" else "resident")
     o = other.run_host(ys, init_particles=x0, noise=noise, resample_u=ru, outputs=outs)
     other.close()
-    assert np.array_equal(o["ancestors"], full["ancestors"])
+    first = int(np.argmax(np.any(o["ancestors"] != full["ancestors"], axis=2)[0])) if np.any(o["ancestors"] != full["ancestors"]) else T
+    assert first >= 2, f"the two kernels' ancestors already differ at step {first}"
+    assert np.mean(o["ancestors"][0, :first + 1] == full["ancestors"][0, :first + 1]) > 0.99
+    close(o["log_likelihood"][:, :first + 1], full["log_likelihood"][:, :first + 1], rtol=1e-4, atol_scale=1e-5,
+          what="log-likelihood of the two kernels up to the first ancestor flip")
+    close(o["log_likelihood"].sum(), full["log_likelihood"].sum(), rtol=5e-2, atol_scale=0.0, what="marginal log-likelihood of the two kernels")
     close(o["particles"], full["particles"])
     close(o["log_likelihood"], full["log_likelihood"])
 

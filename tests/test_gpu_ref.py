@@ -269,3 +269,51 @@ def test_optimal_resampling_vs_reference():
         close(w, d[f"weights{k}"], rtol=1e-5, atol_scale=1e-6, what=f"optimal_resampling weights {k}")
         k += 1
     assert k >= 3
+
+
+# ------------------------------------------------------------------------------------------ legacy NumPy classes
+def _legacy_ssm(name, d):
+    """the single-argument faces of the registry models the legacy fixtures were generated with"""
+    from bayesianfiltering_b200 import zoo
+    from bayesianfiltering_b200.gaussfilt import SSM
+    g = lambda k: d[f"{name}_{k}"]
+    z = zoo.lorenz63() if name == "l63" else zoo.ungm(c=0.0)
+    dx, dy = g("Q").shape[0], g("R").shape[0]
+    return SSM(dx, dy, np.zeros(dx), g("Q"), np.zeros(dy), g("R"), f=z.f, g=z.g)
+
+
+@pytest.mark.parametrize("name", ["l63", "ungm"])
+@pytest.mark.parametrize("kind", ["EKF", "UKF", "MCF"])
+def test_legacy_gaussfilt_classes_vs_reference(name, kind):
+    """gaussfilt.{EKF, UKF, MCF}(ssm).run (gaussfilt.py:88-252): the float64 NumPy reference against the float32 kernels, on
+    15 steps; the Monte-Carlo filter gets the reference's own draws"""
+    from bayesianfiltering_b200 import gaussfilt as gfm
+    d = ref("legacy_gaussfilt")
+    g = lambda k: d[f"{name}_{k}"]
+    ssm = _legacy_ssm(name, d)
+    if kind == "EKF":
+        ll, ms, Ps = gfm.EKF(ssm, order=1).run(g("ys"), g("m0"), g("P0"))
+    elif kind == "UKF":
+        ll, ms, Ps = gfm.UKF(ssm, alpha=1.0, beta=2.0, kappa=0.5).run(g("ys"), g("m0"), g("P0"))
+    else:
+        ll, ms, Ps = gfm.MCF(ssm, g("MCF_draws").shape[2]).run(g("ys"), g("m0"), g("P0"), draws=g("MCF_draws"))
+    tol = 5e-3 if (kind == "MCF" and name == "l63") else 5e-4     # fp32 against fp64 over 15 steps; the 48-draw sample covariance is ill-conditioned on L63
+    close(ms, g(f"{kind}_means"), rtol=tol, atol_scale=tol, what=f"{kind} means")
+    close(Ps, g(f"{kind}_covs"), rtol=10 * tol, atol_scale=tol, what=f"{kind} covs")
+    close(ll, g(f"{kind}_ll"), rtol=10 * tol, atol_scale=tol, what=f"{kind} ll")
+
+
+def test_legacy_bank_of_ukfs_vs_reference_and_mclaf_raises():
+    """gaussfilt.GaussSumFilt(UKF(ssm), M).run (gaussfilt.py:325-361) on the scalar model; MCLAF has no behaviour to match"""
+    from bayesianfiltering_b200 import gaussfilt as gfm
+    d = ref("legacy_bank")
+    g = lambda k: d[f"ungm_{k}"]
+    ssm = _legacy_ssm("ungm", d)
+    M = g("UKF_init_means").shape[0]
+    out = gfm.GaussSumFilt(gfm.UKF(ssm, alpha=1.0, beta=2.0, kappa=0.5), M).run(g("ys"), g("m0"), g("P0"), init_means=g("UKF_init_means"))
+    for a, k in zip(out, ("means", "covs", "weights", "point")):
+        close(a, g(f"UKF_{k}"), rtol=2e-3, atol_scale=5e-4, what=f"bank of UKFs {k}")
+    with pytest.raises(NotImplementedError):
+        gfm.MCLAF(ssm, 8).run(g("ys"), g("m0"), g("P0"))
+    with pytest.raises(ValueError):
+        gfm.UKF(ssm).run(g("ys"), g("m0"), g("P0"))            # default alpha = 1e-3: refused in float32
