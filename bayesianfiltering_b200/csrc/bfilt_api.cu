@@ -570,15 +570,15 @@ struct PfRun {
       if (grid > per_sm * h->nsm) return fail(BF_ECUDA, "cooperative grid of %d CTAs does not fit (%d per SM)", grid, per_sm);
     }
     const int world = h->world, rank = h->rank;
-    // canonical statistics tree (pf_fused.cuh, PfFusedArgs::upart): units of 512 particles, blocks of <= 256 units
+    // canonical statistics tree (pf_fused.cuh, PfFusedArgs::upart): units of 512 particles, blocks of bt tiles, rank roots
     const int nunits = (N + 511) / 512;
-    int bsz = 256;
-    if (world > 1) while (bsz > nunits) bsz >>= 1;      // a shard is an aligned power-of-two subtree: blocks never straddle ranks
-    const int nblocks = (nunits + bsz - 1) / bsz, nb_total = world * nblocks;
-    const size_t root_bytes = (((size_t)2 * nb_total * sizeof(PfPartial)) + 63) & ~(size_t)63;
-    const size_t unit_bytes = (size_t)nunits * sizeof(UnitRec);
-    const size_t ctr_bytes = (((size_t)nblocks + 1) * sizeof(unsigned int) + 63) & ~(size_t)63;      // block tickets + the CTA ticket
-    const size_t part_bytes = root_bytes + unit_bytes + ctr_bytes;                                  // + folded stats
+    int bt = 1;
+    while (bt < 8 && tpc % (2 * bt) == 0) bt *= 2;      // a CTA owns whole blocks
+    const int nroots = (ntiles + bt - 1) / bt;
+    const size_t unit_bytes = (((size_t)nunits * sizeof(PfPartial)) + 63) & ~(size_t)63;
+    const size_t root_bytes = (((size_t)nroots * sizeof(PfPartial)) + 63) & ~(size_t)63;
+    const size_t rank_bytes = (((size_t)2 * world * sizeof(PfPartial)) + 63) & ~(size_t)63;
+    const size_t part_bytes = unit_bytes + root_bytes + rank_bytes + 64;                           // + the CTA ticket; then the folded stats
     CUDA_OK(h->partials.ensure(part_bytes + 256));
     const int grid_s = (int)std::min<int64_t>(((int64_t)N + 255) / 256, (int64_t)h->nsm * 8);
     const int Ng = N * world;
@@ -654,19 +654,17 @@ struct PfRun {
       a.stage_ts = stage_ts ? 1 : 0;
       {
         char* pb = (sl ? sl->partials : h->partials).as<char>();
-        a.broot = reinterpret_cast<PfPartial*>(pb);
-        a.upart = reinterpret_cast<UnitRec*>(pb + root_bytes);
-        a.run_tag = (unsigned)(++h->run_id) & 0xFFFu;
-        a.bctr = reinterpret_cast<unsigned int*>(pb + root_bytes + unit_bytes);
-        a.fold_ctr = a.bctr + nblocks;
+        a.upart = reinterpret_cast<PfPartial*>(pb);
+        a.lroot = reinterpret_cast<PfPartial*>(pb + unit_bytes);
+        a.broot = reinterpret_cast<PfPartial*>(pb + unit_bytes + root_bytes);
+        a.fold_ctr = reinterpret_cast<unsigned int*>(pb + unit_bytes + root_bytes + rank_bytes);
         a.fold_stats = reinterpret_cast<StepStats*>(pb + part_bytes);
-        a.nunits = nunits; a.bsz = bsz; a.nblocks = nblocks; a.nb_total = nb_total; a.blk_off = rank * nblocks;
-        CUDA_OK(cudaMemsetAsync(a.upart, 0, unit_bytes + ctr_bytes, s));     // stale tags of an earlier owner of this memory; tickets
+        a.nunits = nunits; a.bt = bt; a.nroots = nroots;
+        CUDA_OK(cudaMemsetAsync(a.fold_ctr, 0, 64, s));
       }
       if (world > 1) {                   // the exchanged arrays live in the IPC-mapped exchange buffer
         char* xb = h->xchg.as<char>();
-        if (root_bytes > h->off_ts - h->off_part) return fail(BF_EINVAL, "%d block roots exceed the exchange buffer", nb_total);
-        a.broot = reinterpret_cast<PfPartial*>(xb + h->off_part);       // the peers store their roots here
+        a.broot = reinterpret_cast<PfPartial*>(xb + h->off_part);       // the peers store their rank roots here
         a.off_root = (int)h->off_part;
         a.tilesum = reinterpret_cast<float*>(xb + h->off_ts);
         a.V = reinterpret_cast<float*>(xb + h->off_V); a.total = h->V.as<float>();
@@ -718,7 +716,7 @@ struct PfRun {
         NCCL_OK(nc->AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, s));
         continue;
       }
-      const size_t pf_floats = (size_t)nblocks * sizeof(PfPartial) / 4;       // this rank's block roots of one step
+      const size_t pf_floats = sizeof(PfPartial) / 4;                        // this rank's root of one step
       int64_t nlaunch = 0;
       auto launch = [&](cudaStream_t st, int phases, int t, int Tl) -> int {
         PfFusedArgs p = a;

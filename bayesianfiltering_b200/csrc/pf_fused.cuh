@@ -65,15 +65,17 @@ struct PfFusedArgs {
   float* tilesum;                            // [ntiles]
   float* Etile;                              // [ntiles+1]
   // Step statistics (max, sum e, sum e^2, sum e x) are reduced over a CANONICAL binary tree of the particle index, so that
-  // their bits do not depend on the grid, the warp assignment or the number of GPUs: a UNIT = 512 consecutive particles
-  // (4 chunks, one warp, 16 particles per lane) -> a BLOCK = `bsz` consecutive units (power of two <= 256), folded by the
-  // warp that completes it (ticket) -> the block roots of the whole filter, folded by the last CTA out of the phase (or, in a
-  // sharded filter, by every CTA of every rank after the roots have been exchanged).
-  UnitRec* upart;                            // [nunits] unit partials of this rank, tagged (published without a fence)
-  unsigned int run_tag;                      // distinguishes this run's tags from a previous run's in the same buffer
-  PfPartial* broot;                          // [2][nb_total] block roots of the whole filter, by step parity
-  unsigned int* bctr;                        // [nblocks] tickets (never reset within a run: counted modulo the block's size)
-  int nunits, bsz, nblocks, nb_total, blk_off;   // units of this rank; units per block; blocks of this rank / of the filter; this rank's first block
+  // their bits do not depend on the grid, the warp assignment or the number of GPUs a filter is sharded over:
+  //   unit   512 consecutive particles (4 chunks, one warp, 16 particles per lane, accumulated in index order), reduced by
+  //          the warp as soon as it is done; the partial goes to global memory with plain stores
+  //   block  `bt` tiles = 4 bt units (bt = the largest power of two <= 8 dividing tiles_per_cta, so a CTA owns whole blocks):
+  //          folded by a warp of the owning CTA after the CTA's end-of-phase barrier (balanced tree over the unit index)
+  //   rank   the LAST CTA out of the phase (ticket) folds the rank's block roots (balanced tree) -> the step statistics on one
+  //          GPU; in a sharded filter the rank's root goes to every peer and every CTA folds the `world` roots.
+  PfPartial* upart;                          // [nunits] unit partials of this rank
+  PfPartial* lroot;                          // [nroots] block roots of this rank
+  PfPartial* broot;                          // [2][world] rank roots by step parity (sharded; in the exchange buffer)
+  int nunits, bt, nroots;
   int off_root;                              // byte offset of broot inside an exchange buffer (sharded, p2p)
   StepStats* carry_stats;                    // [1] in (resume) / out
   const float* noise;                        // + (t*B + trial)*N*DQ, or NULL (Philox)
@@ -438,25 +440,7 @@ __device__ __forceinline__ void load_state_cg(const float* base, size_t i, float
   }
 }
 
-// Cold pieces of the canonical statistics tree, kept out of line so that their registers (eight accumulators; a stack of
-// twelve) do not weigh on the hot loop's allocation.
-// One warp folds the `gsize` (<= 256) unit partials of a block as the balanced binary tree over the unit index: 8 consecutive
-// units per lane (tree of 8), then a butterfly of merges, adjacent lanes first.  Lane 0 stores the root.
-template <int DX>
-__device__ __noinline__ void fold_block(const UnitRec* up, int gsize, unsigned tag, PfPartial* out) {
-  const int lane = threadIdx.x & 31;
-  OnlineAcc<DX> v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    v[j].init();
-    if (lane * 8 + j < gsize) v[j].load_tagged(up + lane * 8 + j, tag);
-  }
-  v[0].merge_acc(v[1]); v[2].merge_acc(v[3]); v[4].merge_acc(v[5]); v[6].merge_acc(v[7]);
-  v[0].merge_acc(v[2]); v[4].merge_acc(v[6]);
-  v[0].merge_acc(v[4]);
-  v[0].warp_tree_reduce();
-  if (lane == 0) v[0].store(out);
-}
+// Cold piece of the canonical statistics tree, kept out of line so that its stack does not weigh on the hot loop.
 // balanced tree over the aligned range [first, first + R) of block roots (R a power of two > 2; N >= 2^28 only), by binary carries
 template <int DX>
 __device__ __noinline__ void fold_root_range(const PfPartial* roots, int first, int R, int nroots, PfPartial* out) {
@@ -782,42 +766,36 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   auto trace = [&](int, int) {};
 #endif
 
-  // Fold the block roots of step t into the step's statistics (s_stats): the balanced binary tree over the block index,
-  // level by level in shared memory (the tau-window area, idle here).  Whoever folds gets the same bits.  All threads call it.
-  auto fold_statistics = [&](OnlineAcc<DX>& acc, int t, int pt, bool outputs_by_cta0) {
-    const PfPartial* roots = a.broot + (size_t)(pt & 1) * a.nb_total;
-    int P2 = 2;
-    while (P2 < a.nb_total) P2 <<= 1;
-    const int R = max(2, P2 / NT);                     // roots per thread at the bottom level (a power of two)
+  // Fold `nb` roots as the balanced binary tree over the index: a thread takes R consecutive roots (R = 1 up to 2^27
+  // particles), a warp its 32 threads by a butterfly of merges (adjacent lanes first), warp 0 the warps' results the same way.
+  // The result is in thread 0's acc.  Whoever folds gets the same bits.  All threads of the CTA call it.
+  auto fold_roots = [&](OnlineAcc<DX>& acc, const PfPartial* roots, int nb) {
+    int P2 = 1;
+    while (P2 < nb) P2 <<= 1;
+    const int R = max(1, P2 / NT);
     acc.init();
-    if (R == 2) {
-      if (2 * tid < a.nb_total) acc.load(roots + 2 * tid);
-      if (2 * tid + 1 < a.nb_total) { OnlineAcc<DX> o; o.load(roots + 2 * tid + 1); acc.merge_acc(o); }
+    if (R == 1) { if (tid < nb) acc.load(roots + tid); }
+    else if (R == 2) {
+      if (2 * tid < nb) acc.load(roots + 2 * tid);
+      if (2 * tid + 1 < nb) { OnlineAcc<DX> o; o.load(roots + 2 * tid + 1); acc.merge_acc(o); }
     } else {
       PfPartial tmp;
-      fold_root_range<DX>(roots, tid * R, R, a.nb_total, &tmp);
-      acc.m = tmp.m; acc.s = tmp.s; acc.s2 = tmp.s2;
-#pragma unroll
-      for (int k = 0; k < DX; ++k) acc.sx[k] = tmp.sx[k];
+      fold_root_range<DX>(roots, tid * R, R, nb, &tmp);
+      acc.load_plain(&tmp);
     }
-    float* tr = s_win;                                 // [3 + DX][NT]
-    const int nent = (P2 + R - 1) / R;                 // entries at the bottom level of the shared-memory tree (<= NT)
-    tr[tid] = acc.m; tr[NT + tid] = acc.s; tr[2 * NT + tid] = acc.s2;
-#pragma unroll
-    for (int k = 0; k < DX; ++k) tr[(3 + k) * NT + tid] = acc.sx[k];
+    acc.warp_tree_reduce();
+    PfPartial* tr = reinterpret_cast<PfPartial*>(s_win);      // [CW], the tau-window area, idle here
     __syncthreads();
-    for (int st2 = 1; st2 < nent; st2 <<= 1) {
-      if ((tid & (2 * st2 - 1)) == 0 && tid + st2 < nent) {
-        float osx[DX];
-#pragma unroll
-        for (int k = 0; k < DX; ++k) osx[k] = tr[(3 + k) * NT + tid + st2];
-        acc.merge(tr[tid + st2], tr[NT + tid + st2], tr[2 * NT + tid + st2], osx);
-        tr[tid] = acc.m; tr[NT + tid] = acc.s; tr[2 * NT + tid] = acc.s2;
-#pragma unroll
-        for (int k = 0; k < DX; ++k) tr[(3 + k) * NT + tid] = acc.sx[k];
-      }
-      __syncthreads();
+    if (lane == 0) acc.store(tr + warp);
+    __syncthreads();
+    if (warp == 0) {
+      acc.init();
+      if (lane < CW) acc.load_plain(tr + lane);
+      acc.warp_tree_reduce();
     }
+  };
+  // thread 0's acc (the fold of the whole filter) -> the step's statistics (s_stats) and the per-step outputs
+  auto finish_statistics = [&](OnlineAcc<DX>& acc, int t, int pt, bool outputs_by_cta0) {
     if (tid == 0) {
       StepStats st;
       st.mx = acc.m; st.Z = acc.s;
@@ -869,6 +847,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     const int lu = cta_base / 512 + un;                // unit index within this rank
     if (lu >= a.nunits) break;                         // tile padding past N
     acc.init();
+#pragma unroll 1                                        // the body is ~30 KB of SASS: four copies would not fit the instruction cache
     for (int c4 = 0; c4 < 4; ++c4) {
       const int q = 4 * un + c4;
       if (q >= nchunk_valid) break;
@@ -975,41 +954,32 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
       *reinterpret_cast<float4*>(a.LL + base) = make_float4(llv[0], llv[1], llv[2], llv[3]);
     }
-    // unit partial -> global; the warp that completes a block folds it (balanced tree over the block's units)
+    // unit partial -> global memory (plain stores: it is read by this CTA only, after the barrier below)
+#ifndef BF_EXP_NOUNITRED
     acc.unit_reduce();
-    const int lb = lu / a.bsz;
-    unsigned tk = 0;
-    const unsigned utag = (a.run_tag << 20) ^ (unsigned)(t + a.t_offset + 1);
-    if (lane == 0) {
-      acc.store_tagged(a.upart + lu, utag);            // no fence: the folding warp validates the tags
-      tk = atomicAdd(a.bctr + lb, 1u);
-    }
-    tk = __shfl_sync(BF_FULL, tk, 0);
-    const int gsize = min(a.bsz, a.nunits - lb * a.bsz);
-    if ((tk + 1u) % (unsigned)gsize == 0u) {
-      const size_t ridx = (size_t)(pt & 1) * a.nb_total + a.blk_off + lb;
-      fold_block<DX>(a.upart + (size_t)lb * a.bsz, gsize, utag, a.broot + ridx);
-      if (lane == 0) {
-        if (p2p) {                                     // the same root into every peer's exchange buffer
-          const PfPartial rootv = a.broot[ridx];
-          for (int r = 0; r < a.world; ++r) {
-            if (r == a.rank) continue;
-            reinterpret_cast<PfPartial*>(a.xchg_peers[r] + a.off_root)[ridx] = rootv;
-          }
-          __threadfence_system();
-        }
-        __threadfence();
-      }
-    }
+#endif
+    if (lane == 0) acc.store(a.upart + lu);
     }  // units
     if (tid == 0) { s_ctr[1] = 0; s_ctr[2] = 0; }      // queues of phases B and C2 (nobody is in them now)
 #ifndef BF_DYNAMIC_CHUNKS
     turn[1] = 0; turn[2] = 0;
 #endif
     __syncthreads();
-    if (!SH && all_phases) {
-      // One-GPU run: the LAST CTA out of the phase (ticket) folds the block roots once, before the grid leaves the barrier,
-      // and the others fetch the 64-byte result (every CTA folding them itself was an 11 us L2 hot spot per step).
+    {
+      // block roots of this CTA: a warp folds the 4 bt units of a block (lane = unit, butterfly of merges, adjacent first)
+      const int ub = 4 * a.bt;
+      const int nblk_cta = (tile1 - tile0 + a.bt - 1) / a.bt;
+      for (int bl = warp; bl < nblk_cta; bl += CW) {
+        const int lu0 = cta_base / 512 + bl * ub;
+        OnlineAcc<DX> v;
+        v.init();
+        if (lane < ub && lu0 + lane < a.nunits) v.load(a.upart + lu0 + lane);
+        v.warp_tree_reduce();
+        if (lane == 0) v.store(a.lroot + tile0 / a.bt + bl);
+      }
+      __syncthreads();
+      // the LAST CTA of this rank out of the phase (ticket) folds the rank's block roots once, before the grid leaves the
+      // barrier; the others fetch the result (every CTA folding them itself was an 11 us L2 hot spot per step)
       if (tid == 0) {
         __threadfence();
         const unsigned tkc = atomicAdd(a.fold_ctr, 1u);
@@ -1018,9 +988,23 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       __syncthreads();
       if (s_last) {
         __threadfence();
-        fold_statistics(acc, t, pt, false);
-        if (tid == 0) {
-          *a.fold_stats = s_stats;
+        fold_roots(acc, a.lroot, a.nroots);
+        if (!SH) {
+          finish_statistics(acc, t, pt, false);
+          if (tid == 0) {
+            *a.fold_stats = s_stats;
+            __threadfence();
+          }
+        } else if (tid == 0) {                         // sharded: this rank's root, to itself and to every peer
+          const size_t ridx = (size_t)(pt & 1) * a.world + a.rank;
+          acc.store(a.broot + ridx);
+          if (p2p) {
+            for (int r = 0; r < a.world; ++r) {
+              if (r == a.rank) continue;
+              acc.store(reinterpret_cast<PfPartial*>(a.xchg_peers[r] + a.off_root) + ridx);
+            }
+            __threadfence_system();
+          }
           __threadfence();
         }
       }
@@ -1042,7 +1026,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       if (tid == 0) s_stats = a.carry_stats[(pt + 1) & 1];
       __syncthreads();
     } else {
-    if (SH || !all_phases) fold_statistics(acc, t, pt, true);
+    if (SH || !all_phases) { fold_roots(acc, a.broot + (size_t)(pt & 1) * a.world, a.world); finish_statistics(acc, t, pt, true); }
     else if (tid == 0) {                               // one-GPU run: the last CTA out of phase A folded them (below)
       const int4* src = reinterpret_cast<const int4*>(a.fold_stats);
       int4* dst = reinterpret_cast<int4*>(&s_stats);

@@ -31,13 +31,7 @@ struct StepStats {
   float mean[BF_MAXD];
 };
 
-struct PfPartial { float m, s, s2; float sx[BF_MAXD]; };
-// A unit partial as published to other warps WITHOUT a memory fence: four 16-byte records, each carrying the tag of the step
-// that wrote it.  A 16-byte aligned vector store is not torn, so a reader that finds the expected tag in a record has that
-// record's data; it spins on the (rare) record that has not landed yet.  (A __threadfence per unit -- it has to drain the
-// warp's outstanding particle stores -- cost 8 % of the propagate phase when measured.)
-struct __align__(16) UnitRec { float4 r[4]; };
-
+struct __align__(16) PfPartial { float m, s, s2, pad; float sx[BF_MAXD]; };     // 48 bytes: three 128-bit accesses
 // ---------------------------------------------------------------- vectorised particle access
 template <int DX>
 __device__ __forceinline__ void load_state(const float* __restrict__ base, size_t i, float* x) {
@@ -126,38 +120,29 @@ struct OnlineAcc {
   // whatever the grid, the warp assignment or the number of GPUs a filter is sharded over.
   __device__ __forceinline__ void merge_acc(const OnlineAcc& o) { merge(o.m, o.s, o.s2, o.sx); }
   __device__ __forceinline__ void load(const PfPartial* p) {
-    m = __ldcg(&p->m); s = __ldcg(&p->s); s2 = __ldcg(&p->s2);
-#pragma unroll
-    for (int k = 0; k < DX; ++k) sx[k] = __ldcg(&p->sx[k]);
-  }
-  __device__ __forceinline__ void store_tagged(UnitRec* p, unsigned tag) const {
-    const float tg = __uint_as_float(tag);
+    const float4* q = reinterpret_cast<const float4*>(p);
+    const float4 a = __ldcg(q);
+    m = a.x; s = a.y; s2 = a.z;
     float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (k < DX) ? sx[k < DX ? k : 0] : 0.0f;
-    __stcg(&p->r[0], make_float4(m, s, s2, tg));
-    __stcg(&p->r[1], make_float4(v[0], v[1], v[2], tg));
-    if (DX > 3) __stcg(&p->r[2], make_float4(v[3], v[4], v[5], tg));
-    if (DX > 6) __stcg(&p->r[3], make_float4(v[6], v[7], 0.0f, tg));
-  }
-  __device__ __forceinline__ void load_tagged(const UnitRec* p, unsigned tag) {
-    float v[8];
-#pragma unroll
-    for (int part = 0; part < 4; ++part) {
-      if (part == 2 && DX <= 3) break;
-      if (part == 3 && DX <= 6) break;
-      float4 q = __ldcg(&p->r[part]);
-      while (__float_as_uint(q.w) != tag) { __nanosleep(20); q = __ldcg(&p->r[part]); }
-      if (part == 0) { m = q.x; s = q.y; s2 = q.z; }
-      else { v[3 * part - 3] = q.x; v[3 * part - 2] = q.y; if (3 * part - 1 < 8) v[3 * part - 1] = q.z; }
-    }
+    const float4 b = __ldcg(q + 1);
+    v[0] = b.x; v[1] = b.y; v[2] = b.z; v[3] = b.w;
+    if (DX > 4) { const float4 c = __ldcg(q + 2); v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w; }
 #pragma unroll
     for (int k = 0; k < DX; ++k) sx[k] = v[k];
   }
-  __device__ __forceinline__ void store(PfPartial* p) const {
-    p->m = m; p->s = s; p->s2 = s2;
+  __device__ __forceinline__ void load_plain(const PfPartial* p) {     // shared or local memory
+    m = p->m; s = p->s; s2 = p->s2;
 #pragma unroll
-    for (int k = 0; k < DX; ++k) p->sx[k] = sx[k];
+    for (int k = 0; k < DX; ++k) sx[k] = p->sx[k];
+  }
+  __device__ __forceinline__ void store(PfPartial* p) const {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (k < DX) ? sx[k < DX ? k : 0] : 0.0f;
+    float4* q = reinterpret_cast<float4*>(p);
+    q[0] = make_float4(m, s, s2, 0.0f);
+    q[1] = make_float4(v[0], v[1], v[2], v[3]);
+    if (DX > 4) q[2] = make_float4(v[4], v[5], v[6], v[7]);
   }
   // the 32 lane accumulators of one unit (512 consecutive particles, 16 per lane) -> the unit's partial, in every lane:
   // one common maximum, one rescale per lane, then plain butterfly sums (adjacent lanes first)

@@ -215,8 +215,7 @@ def test_resident_and_streamed_agree_and_chunked_resume_is_exact(path):
     close(o["log_likelihood"][:, :first + 1], full["log_likelihood"][:, :first + 1], rtol=1e-4, atol_scale=1e-5,
           what="log-likelihood of the two kernels up to the first ancestor flip")
     close(o["log_likelihood"].sum(), full["log_likelihood"].sum(), rtol=5e-2, atol_scale=0.0, what="marginal log-likelihood of the two kernels")
-    close(o["particles"], full["particles"])
-    close(o["log_likelihood"], full["log_likelihood"])
+    close(o["particles"][:, :first], full["particles"][:, :first])
 
 
 @pytest.mark.parametrize("path", ["resident", "streamed"])
