@@ -25,7 +25,7 @@ jobs=()
 # The particle-filter translation units are compiled with -fmad=false: every fused multiply-add in them is one the source
 # spells out (fmaf), so the general / lean / sharded instantiations of a kernel cannot contract a product-sum differently
 # and one filter gives the same bits whichever of them ran it (tests: lean == general, sharded == one GPU).
-PF="-fmad=false"
+PF="-fmad=false -DBF_DYNAMIC_CHUNKS"
 for ((g = 0; g < NG_FUSED; ++g)); do jobs+=("fused_$g tu_kernels.cu $PF -DBF_TU_KIND=1 -DBF_NGROUPS=$NG_FUSED -DBF_GROUP=$g"); done
 jobs+=("large tu_kernels.cu -DBF_TU_KIND=5")
 for ((g = 0; g < NG_GSF; ++g)); do jobs+=("gsf_$g tu_kernels.cu -DBF_TU_KIND=3 -DBF_NGROUPS=$NG_GSF -DBF_GROUP=$g"); done

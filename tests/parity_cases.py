@@ -182,6 +182,29 @@ def smoke_check():
     close(out["means"][0][:, :, 0].T, g["means"][:, :5, 0], rtol=1e-4, atol_scale=1e-4, what="gsf means")
     close(out["weights"][0].T, g["weights"][:, :5], rtol=1e-4, atol_scale=1e-4, what="gsf weights")
     eng.close()
+    # the unscented and the augmented Gaussian-sum filter: one step each against the oracle
+    from oracle import ugsf as ougsf, agsf as oagsf
+    from bayesianfiltering_b200.engine import AugmentedGaussianSumFilterEngine
+    cb = case("bot2")
+    _, yb = cb.simulate(3, 5)
+    ub = cb.inputs(3)
+    mb = cb.gsf_means0(4, 6)
+    eng = GaussianSumFilterEngine(cb.host_model(), 4, 1, 0, unscented=(1.0, 0.0, 0.0))
+    out = eng.run_host(yb[:1], inputs=ub[:1], init_means=mb[None], outputs=("weights", "means"))
+    eng.close()
+    f8 = lambda a: np.asarray(a, np.float64)
+    o8 = ougsf.ugsf_step(cb.omodel, np.full(4, 0.25), f8(mb), np.broadcast_to(f8(cb.P0), (4, 4, 4)).copy(), f8(yb[0]), float(ub[0]),
+                         f8(cb.Q), f8(cb.q0), f8(cb.R), f8(cb.r0), ougsf.ParamsUKF(1.0, 0.0, 0.0))
+    close(out["means"][0, 0], o8["means"], rtol=1e-3, atol_scale=1e-4, what="ugsf means")
+    rng = np.random.default_rng(7)
+    z1, z2, ru = rng.standard_normal((4, 4, 2)).astype(np.float32), rng.standard_normal((8, 4, 2)).astype(np.float32), rng.random(4, dtype=np.float32)
+    eng = AugmentedGaussianSumFilterEngine(cb.host_model(), (4, 2, 2), 1, (0.8, 0.5), 0, 0)
+    out = eng.run_host(yb[:1], inputs=ub[:1], init_means=mb[None], z_iid=z1, s_iid=z2, res_u=ru, outputs=("means", "pre_weights", "ancestors"))
+    eng.close()
+    assert np.array_equal(out["ancestors"][0, 0], oscan.resample_ancestors(out["pre_weights"][0, 0], ru)), "agsf survivors not bit-exact"
+    o8 = oagsf.agsf_step(cb.omodel, f8(mb), np.broadcast_to(f8(cb.P0), (4, 4, 4)).copy(), np.full(4, 0.25), f8(yb[0]), float(ub[0]), f8(cb.Q),
+                         f8(cb.q0), f8(cb.R), f8(cb.r0), f8(z1), f8(z2), f8(ru), (0.8, 0.5))
+    close(out["pre_weights"][0, 0], o8["pre_weights"], rtol=1e-3, atol_scale=1e-4, what="agsf leaf weights")
     # resampler bit-exactness on a random weight vector
     import torch
     from bayesianfiltering_b200.engine import resample_ancestors
