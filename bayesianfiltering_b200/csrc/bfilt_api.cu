@@ -272,6 +272,7 @@ struct bf_pf_s {
   ncclComm_t comm = nullptr;
   bool peers_ready = false;
   void* peer_ptr[4][8] = {};          // imported tau / xa / xb / exchange buffer of every rank (own entries = own buffers)
+  DevBuf stg_tau, stg_x;              // bulk staging of remote ancestor ranges (sharded)
   DevBuf peer_tab, barrier_buf;       // device tables [4][8] of the pointers above; 1 float for the step barrier
   DevBuf xchg;                        // exchange buffer: flags [3][8] u64 | epoch | err | partials | tilesum | V  (pf_fused.cuh)
   size_t off_part = 0, off_ts = 0, off_V = 0;
@@ -382,7 +383,7 @@ extern "C" int bf_pf_destroy(bf_pf_handle h) {
       for (int r = 0; r < h->world; ++r)
         if (r != h->rank && h->peer_ptr[k][r]) cudaIpcCloseMemHandle(h->peer_ptr[k][r]);
   DevBuf* all[] = {&h->carry_x, &h->carry_w, &h->carry_uniform, &h->carry_stats, &h->xa, &h->xb, &h->LL, &h->E, &h->anc,
-                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V, &h->peer_tab, &h->barrier_buf, &h->xchg};
+                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V, &h->peer_tab, &h->barrier_buf, &h->xchg, &h->stg_tau, &h->stg_x};
   for (DevBuf* b : all) b->release();
   for (DevBuf& b : h->hbuf) b.release();
   delete h;
@@ -674,6 +675,16 @@ struct PfRun {
         a.epoch = reinterpret_cast<unsigned long long*>(xb + 256);
         a.err = reinterpret_cast<int*>(xb + 264);
         a.xstage = xstage ? 1 : 0;
+        // bulk staging of the remote part of each CTA's ancestor range (BF_SHARD_BULK=0 turns it off)
+        const char* benv = getenv("BF_SHARD_BULK");
+        if (!(benv && benv[0] == '0')) {
+          const size_t cap = (size_t)std::min<int64_t>((int64_t)N, (int64_t)2 * tpc * PF_FUSED_TILE_CHUNKS * 128);
+          if (h->stg_tau.ensure((size_t)grid * cap * 4) == cudaSuccess && h->stg_x.ensure((size_t)grid * cap * DX * 4) == cudaSuccess) {
+            a.stg_tau = h->stg_tau.as<float>(); a.stg_x = h->stg_x.as<float>(); a.stg_cap = (int)cap;
+          } else {
+            cudaGetLastError();
+          }
+        }
       }
       a.carry_stats = h->carry_stats.as<StepStats>() + 2 * b;
       a.noise = io->noise ? io->noise + (size_t)b * N * DQ : nullptr;

@@ -103,6 +103,11 @@ struct PfFusedArgs {
   // buffer over NVLink and raises a sequence-numbered flag there; the readers spin on their own (local) flags.
   int p2p, off_part, off_ts, off_V;          // byte offsets of partials / tilesum / V inside an exchange buffer
   int xstage;                                // stage remote ancestor ranges in shared memory (needs the extra dynamic shared memory)
+  // Bulk staging (sharded): before its units, a CTA copies the part of its ancestor range [s_lo[0], s_lo[last]] that lives on
+  // other ranks -- tau and the particle state -- into these LOCAL buffers with every thread's loads in flight at once; the
+  // units then never wait for an NVLink round trip (they cost the boundary CTAs 70 % when fetched chunk by chunk).
+  float* stg_tau; float* stg_x;              // [gridDim.x][stg_cap], [gridDim.x][stg_cap][DX]
+  int stg_cap;
   char* const* xchg_peers;                   // device table [world] of the exchange buffers (own entry = own buffer)
   unsigned long long* flags;                 // own flags [3][8]
   unsigned long long* epoch;                 // runs completed on this handle (device side: CUDA-graph replays need no new arguments)
@@ -525,7 +530,18 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   const bool all_phases = a.phases == PF_PH_ALL;
   const int ns_mask = (1 << (a.log2ns < 0 ? 0 : a.log2ns)) - 1;
   // global accessors: entry j of the (virtual) global tau array, particle j of the previous step's state
-  auto tauG = [&](int j) -> float { if constexpr (!SH) return a.E[j]; else return a.tau_peers[j >> a.log2ns][j & ns_mask]; };
+  bool stg_on = false;                                // this CTA's remote ancestor range is staged locally (sharded)
+  int stg_lo = 0, stg_hi = -1;
+  const float* stg_tau_c = SH ? a.stg_tau + (size_t)blockIdx.x * a.stg_cap : nullptr;
+  const float* stg_x_c = SH ? a.stg_x + (size_t)blockIdx.x * a.stg_cap * M::DX : nullptr;
+  auto tauG = [&](int j) -> float {
+    if constexpr (!SH) return a.E[j];
+    else {
+      if ((j >> a.log2ns) == a.rank) return a.E[j & ns_mask];
+      if (stg_on && j >= stg_lo && j <= stg_hi) return __ldcg(stg_tau_c + (j - stg_lo));
+      return a.tau_peers[j >> a.log2ns][j & ns_mask];
+    }
+  };
   const bool w_vec = (reinterpret_cast<size_t>(a.W) & 15) == 0;     // carry of trial b starts at b*N floats
   const bool use_win = use_tau && a.resampler == 1;      // sorted positions: windowed search
   // (i + u) / 2^k is an exact scaling: multiplying by 2^-k gives the same bits as the oracle's division
@@ -569,6 +585,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 
   // Once per phase that gathers: total and the systematic uniform.  ts = local step whose resampling is gathered.
   auto begin_gather = [&](int ts) {
+    stg_on = false;                                  // (the staged copies of the previous step are stale)
     res_total = __ldcg(a.total);
     res_scale = __fdiv_rn((float)Ng, res_total);
     if (a.resampler == 1)
@@ -597,6 +614,43 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       s_lo[q] = lb;
     }
     __syncthreads();
+    if constexpr (SH) {
+      stg_on = false;
+      if (a.stg_tau && nchunk_valid > 0) {
+        const int wlo = s_lo[0], whi = min(s_lo[nchunk_valid], Ng - 1);
+        const bool remote = ((wlo >> a.log2ns) != a.rank) || ((whi >> a.log2ns) != a.rank);
+        if (remote && whi - wlo + 1 <= a.stg_cap) {
+          float* dt_ = a.stg_tau + (size_t)blockIdx.x * a.stg_cap;
+          float* dx_ = a.stg_x + (size_t)blockIdx.x * a.stg_cap * DX;
+          const int cnt = whi - wlo + 1;
+          for (int i0 = 0; i0 < cnt; i0 += 4 * NT) {       // four peer loads of each kind in flight per thread
+            float tv[4], xv[4][DX];
+            bool rm[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int i = i0 + tid + m * NT;
+              const int g = wlo + min(i, cnt - 1);
+              const int r = g >> a.log2ns;
+              rm[m] = i < cnt && r != a.rank;
+              if (rm[m]) {
+                tv[m] = a.tau_peers[r][g & ns_mask];
+                load_state_cg<DX>(xp_stage[r], (size_t)(g & ns_mask), xv[m]);
+              }
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              if (rm[m]) {
+                const int i = i0 + tid + m * NT;
+                dt_[i] = tv[m];
+                store_state<DX>(dx_, (size_t)i, xv[m]);
+              }
+            }
+          }
+          stg_on = true; stg_lo = wlo; stg_hi = whi;
+        }
+      }
+      __syncthreads();
+    }
   };
 
   // Ancestors of the 4 slots base..base+3 of the chunk starting at cbase.  Warp-synchronous (all lanes call it).
@@ -702,7 +756,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #endif
         // Sharded filter, ancestors (partly) on another rank: x[lo .. lo+wn] is a contiguous range -- fetch it with
         // coalesced 512-byte peer reads into shared memory instead of one 16-byte NVLink round trip per particle.
-        if (SH && a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
+        if (SH && !stg_on && a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
           float* xs = s_xst + (size_t)warp * PF_FUSED_XCAP * DX;
           for (int i0 = 0; i0 <= wn; i0 += 128) {       // four peer loads in flight per lane (an NVLink round trip is ~3 us)
             float xv[4][DX];
@@ -746,6 +800,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   // particle `g` (GLOBAL index) of the state the step reads: own shard or a peer's
   auto load_prev = [&](int g, const float* xp_local, const float* const* xp_peers, float* x) {
     if (!SH) load_state_cg<DX>(xp_local, (size_t)g, x);
+    else if (stg_on && (g >> a.log2ns) != a.rank && g >= stg_lo && g <= stg_hi) load_state_cg<DX>(stg_x_c, (size_t)(g - stg_lo), x);
     else load_state_cg<DX>(xp_peers[g >> a.log2ns], (size_t)(g & ns_mask), x);
   };
 
@@ -840,7 +895,10 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 
     // ------------------------------------------------------------------ phase A
     if (a.phases & PF_PH_A) {
+    trace(t, 9);
+    xp_stage = xp_peers;
     if (gather) begin_gather(t - 1);
+    trace(t, 10);
     // Warps take UNITS of 4 consecutive chunks (512 particles): a lane's 16 particles are accumulated in index order and the
     // unit is reduced at once, so the unit partial is a function of the data alone (see PfFusedArgs::upart).
     for (int un = next_chunk(0); un < nchunk_cta / 4; un = next_chunk(0)) {
@@ -960,6 +1018,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #endif
     if (lane == 0) acc.store(a.upart + lu);
     }  // units
+    trace(t, 11);
     if (tid == 0) { s_ctr[1] = 0; s_ctr[2] = 0; }      // queues of phases B and C2 (nobody is in them now)
 #ifndef BF_DYNAMIC_CHUNKS
     turn[1] = 0; turn[2] = 0;
@@ -1014,6 +1073,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (all_phases) grid.sync();
     trace(t, 1);
     if (p2p) xbarrier(0, t);
+    trace(t, 12);
     lap(0);
     if (!(a.phases & (PF_PH_B | PF_PH_C))) break;
 
@@ -1115,6 +1175,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (all_phases) grid.sync();
     trace(t, 3);
     if (p2p) xbarrier(1, t);
+    trace(t, 13);
     lap(1);
     if (!(a.phases & PF_PH_C)) break;
 
@@ -1212,6 +1273,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
                                                        //  which is where the peers' NVLink reads are served from)
     trace(t, 7);
     if (p2p) xbarrier(2, t);
+    trace(t, 14);
     lap(3);
     w_uni = true; gather = true;
   }
@@ -1220,6 +1282,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   // ------------------------------------------------------------------ materialise the carry
   const int ptf = all_phases ? T : a.t_offset;          // number of steps behind the carry
   const float* const* xpf_peers = (ptf & 1) ? a.xa_peers : a.xb_peers;
+  xp_stage = xpf_peers;
   if (gather) begin_gather(T - 1);
   for (int q = next_chunk(0); q < nchunk_valid; q = next_chunk(0)) {
     const int base = cta_base + 128 * q + lane * 4;
