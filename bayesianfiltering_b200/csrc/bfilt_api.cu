@@ -675,9 +675,11 @@ struct PfRun {
         a.epoch = reinterpret_cast<unsigned long long*>(xb + 256);
         a.err = reinterpret_cast<int*>(xb + 264);
         a.xstage = xstage ? 1 : 0;
-        // bulk staging of the remote part of each CTA's ancestor range (BF_SHARD_BULK=0 turns it off)
+        // Bulk staging of the remote part of each CTA's ancestor range: OFF unless BF_SHARD_BULK=1.  Measured (profiles/README.md):
+        // it removes the per-chunk NVLink round trips of the boundary CTAs but serialises their whole transfer before their
+        // compute -- 366 vs 320 us per step on 2 GPUs (67 MB per rank cross the link), 188 vs 184 on 8.
         const char* benv = getenv("BF_SHARD_BULK");
-        if (!(benv && benv[0] == '0')) {
+        if (benv && benv[0] == '1') {
           const size_t cap = (size_t)std::min<int64_t>((int64_t)N, (int64_t)2 * tpc * PF_FUSED_TILE_CHUNKS * 128);
           if (h->stg_tau.ensure((size_t)grid * cap * 4) == cudaSuccess && h->stg_x.ensure((size_t)grid * cap * DX * 4) == cudaSuccess) {
             a.stg_tau = h->stg_tau.as<float>(); a.stg_x = h->stg_x.as<float>(); a.stg_cap = (int)cap;

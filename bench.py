@@ -45,8 +45,8 @@ BYTES_PER_PARTICLE_STEP = 84     # 4*(4*dx + 5) for dx=4, in-kernel
 # DRAM bytes the fused kernel actually moves per particle-step, from the ncu --set full capture named in MOVED_SOURCE
 # (dram__bytes_read + dram__bytes_write of one launch / (N*T)).  Below the algorithmic figure because the resampled copy
 # of the particles is never materialised (the gather is fused into the next step's propagate).  NOT measured in this run.
-MOVED_BYTES_PER_PARTICLE_STEP = 52.0
-MOVED_SOURCE = "profiles/r1_m_pf_fused_T40_ncu.txt"
+MOVED_BYTES_PER_PARTICLE_STEP = 52.3
+MOVED_SOURCE = "profiles/r2_j_pf_fused_T40_ncu.txt"
 GSF_BYTES = 20                   # 4*(2 dx + 2 dx^2 + 1), dx = 1: the five posterior fields
 GSF_FLOPS = 60                   # ~60 flop per component-step incl. exp / log
 L96_BYTES = 8 * (40 + 1600 + 1) + 4 * (1 + 40.0 / 256)     # carry read + write, weights + mixture mean out: ~13.1 KB
