@@ -259,12 +259,12 @@ struct bf_pf_s {
   bool have_carry;
   DevBuf carry_x, carry_w, carry_uniform, carry_stats;
   // streamed scratch
-  DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats, phase_ns, V;
+  DevBuf xa, xb, LL, E, anc, tilesum, Etile, partials, counter, stats, phase_ns, V, cells;
   unsigned run_id = 0;                // runs launched on this handle (tags of the unit partials)
   int ntiles;
   // Independent trials of the streamed path run CONCURRENTLY (one cooperative kernel each, on its own stream, with its
   // own scratch): at the reference's sizes (Nsim = 100 trials of N = 10^4) one trial fills a few SMs only.
-  struct Slot { DevBuf xa, xb, LL, E, tilesum, Etile, V, partials; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; };
+  struct Slot { DevBuf xa, xb, LL, E, tilesum, Etile, V, partials, cells; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; };
   Slot extra[31];                     // slots 1..31 (slot 0 = the members above), allocated on first use
   cudaEvent_t ev_fork = nullptr;
   // sharded filter
@@ -646,11 +646,18 @@ struct PfRun {
       a.use_tau = (log2ng >= 3 && log2n >= 0) ? 1 : 0;
       {   // two-level search for unsorted positions: needs whole tiles and the table in the tau-window area
         constexpr int FT = PF_FUSED_TILE_CHUNKS * 128;
-        const bool coarse = world == 1 && a.use_tau && h->cfg.resampler == BF_RESAMPLE_MULTINOMIAL && N >= 2 * FT &&
-                            N / FT <= NW * PF_FUSED_WINCAP;
+        const bool coarse = world == 1 && a.use_tau && N >= 2 * FT && N / FT <= NW * PF_FUSED_WINCAP;
         a.coarse_log2 = -1;
         if (coarse) { a.coarse_log2 = 0; while ((FT << a.coarse_log2) < N) ++a.coarse_log2; }
         a.tau_tile = a.Etile + ntiles_g + 4;
+        // cell table of the unsorted search (pf_fused.cuh, begin_gather): pays for its build pass from N ~ 2^18 on
+        const char* cenv = getenv("BF_PF_CELL_TABLE");
+        const bool cells = coarse && h->cfg.resampler == BF_RESAMPLE_MULTINOMIAL && (cenv ? cenv[0] == '1' : N >= (1 << 18));
+        if (cells) {
+          DevBuf& cb = sl ? sl->cells : h->cells;
+          if (cb.ensure(((size_t)N + 4) * 4)) return fail(BF_ENOMEM, "cudaMalloc of the resampling cell table failed");
+          a.cell_lb = cb.as<int>();
+        }
       }
       a.stage_ts = stage_ts ? 1 : 0;
       {

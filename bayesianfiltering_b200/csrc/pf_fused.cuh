@@ -91,6 +91,7 @@ struct PfFusedArgs {
   unsigned int* fold_ctr;                    // ticket counter of the one-GPU statistics fold (zeroed by the host per run)
   StepStats* fold_stats;                     // its result
   float* tau_tile;                           // [N / 2048] last tau of each tile (one GPU, multinomial: two-level search)
+  int* cell_lb;                              // [Ng + 1] one GPU, multinomial: lower bound of tau at the cell edges c * total / Ng, or NULL
   int coarse_log2;                           // log2 of its length, or -1: off
   int stage_ts;                              // C1 stages the tile sums in shared memory first (the host sized it for that)
   int tile_off, ntiles_g;                    // global index of local tile 0; tiles of the whole filter (tilesum/Etile/V are global)
@@ -220,6 +221,23 @@ __device__ __forceinline__ void lower_bound4_two_level(const float* s_last, int 
   l2 += (r[2] <= t2[l2]) ? 0u : 1u; l3 += (r[3] <= t3[l3]) ? 0u : 1u;
   anc[0] = min((int)(min(k0, nt - 1) * TILE + l0), nm1); anc[1] = min((int)(min(k1, nt - 1) * TILE + l1), nm1);
   anc[2] = min((int)(min(k2, nt - 1) * TILE + l2), nm1); anc[3] = min((int)(min(k3, nt - 1) * TILE + l3), nm1);
+}
+
+// ONE query, two levels: the tile from the table of last thresholds in shared memory, then the 11 levels inside it.
+// Same result as lower_bound_tau_pow2 on the monotone tau (NaN r: n), 11 dependent global loads instead of log2(n).
+__device__ __forceinline__ int lower_bound_two_level(const float* s_last, int log2nt, const float* tau, float r) {
+  unsigned k = 0;
+  for (unsigned s = 1u << (log2nt - 1); s != 0; s >>= 1)
+    if (!(r <= s_last[k + s])) k += s;
+  k += (r <= s_last[k]) ? 0u : 1u;
+  constexpr unsigned TILE = PF_FUSED_TILE_CHUNKS * 128;
+  if (k >= (1u << log2nt)) return (int)(TILE << log2nt);
+  const float* t = tau + (size_t)k * TILE;
+  unsigned l = 0;
+  for (unsigned s = TILE / 2; s != 0; s >>= 1)
+    if (!(r <= t[l + s])) l += s;
+  l += (r <= t[l]) ? 0u : 1u;
+  return (int)(k * TILE + l);
 }
 
 // fixed bisection / lower bound of ONE query on the monotone thresholds tau[0..2^log2n); result in [0, n]
@@ -544,6 +562,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   };
   const bool w_vec = (reinterpret_cast<size_t>(a.W) & 15) == 0;     // carry of trial b starts at b*N floats
   const bool use_win = use_tau && a.resampler == 1;      // sorted positions: windowed search
+  const bool use_cells = !SH && use_tau && a.resampler != 1 && a.cell_lb != nullptr && a.log2ng >= 0;   // unsorted positions: cell table
   // (i + u) / 2^k is an exact scaling: multiplying by 2^-k gives the same bits as the oracle's division
   const float invn_pow2 = (a.log2ng >= 0) ? __int_as_float((127 - a.log2ng) << 23) : 0.0f;
   // ---- cross-GPU barrier of the persistent sharded kernel.  Every thread that stored into a peer's buffer has run
@@ -576,11 +595,64 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   float res_total = 0.0f, res_u0 = 0.0f, res_scale = 0.0f;   // of the resampling being gathered (scale = Ng / total)
   const float* const* xp_stage = nullptr;             // peers' copies of the state being gathered (sharded filter)
 
+  // systematic position of a slot when Ng is a power of two (the tau path): exact scaling, then one rounding
+  auto pos_sys = [&](int slot, float u) -> float { return __fmul_rn(res_total, __fmul_rn(__fadd_rn((float)slot, u), invn_pow2)); };
   auto position = [&](int slot, float u) -> float {
     if (a.log2ng >= 0)
       return (a.resampler == 1) ? __fmul_rn(res_total, __fmul_rn(__fadd_rn((float)slot, u), invn_pow2))
                                 : __fmul_rn(res_total, __fsub_rn(1.0f, u));
     return resample_position(a.resampler, res_total, u, slot, Ng);
+  };
+
+  // Lower bounds of the 128 SORTED positions (s0 + i + u0) * total / Ng, i < 128, by counting: out[k] belongs to slot
+  // s0 + 4 lane + k; [lo, lo + wn] brackets the answers.  Warp-synchronous; wn <= 32 * 128.
+  auto count_window = [&](int lo, int wn, int s0, float u0, int out[4]) {
+    // Counting instead of searching.  Slot i's answer is lo + #{j in the window : tau_j < r_i}; positions are
+    // non-decreasing in i, so tau_j is below the positions of exactly the slots i >= k_j, k_j = first slot of the
+    // chunk whose position exceeds tau_j.  Every lane turns its share of the window (about one tau per slot) into
+    // k_j -- an estimate from the inverse of the position formula, corrected against the formula itself, so the
+    // result is exact whatever the rounding of the estimate -- and counts it in a 129-bin histogram in shared
+    // memory; a warp prefix sum of the histogram gives all 128 answers.  ~30 instructions per slot where the
+    // bounded bisections took ~75, and no staging of the window.
+    int* hist = reinterpret_cast<int*>(s_win) + warp * 160;
+    *reinterpret_cast<int4*>(hist + lane * 4) = make_int4(0, 0, 0, 0);
+    if (lane == 0) hist[128] = 0;
+    __syncwarp();
+    const float fs0 = (float)s0;                    // a multiple of 128 below 2^31: exact
+    for (int j0 = 0; j0 < wn; j0 += 128) {          // four independent loads in flight per lane
+      float tv[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { const int i = j0 + lane + 32 * m; tv[m] = (i < wn) ? tauG(lo + i) : 0.0f; }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        if (j0 + lane + 32 * m < wn) {
+          const float tj = tv[m];
+          // estimate: pos_sys(s, u) > tj  <=>  s > tj * Ng / total - u
+          float tr = __fsub_rn(__fsub_rn(__fmul_rn(tj, res_scale), u0), fs0);
+          tr = fminf(fmaxf(tr, -1.0f), 128.0f);     // (NaN -> -1)
+          int g = min((int)floorf(tr) + 1, 128);
+          while (g > 0 && pos_sys(s0 + g - 1, u0) > tj) --g;
+          while (g < 128 && !(pos_sys(s0 + g, u0) > tj)) ++g;
+          atomicAdd(hist + g, 1);
+        }
+      }
+    }
+    __syncwarp();
+    const int4 h4 = *reinterpret_cast<const int4*>(hist + lane * 4);
+    const int c0 = h4.x, c1 = c0 + h4.y, c2 = c1 + h4.z, c3 = c2 + h4.w;
+    int incl = c3;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(BF_FULL, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const int ex = lo + incl - c3;
+    out[0] = min(ex + c0, Ng - 1); out[1] = min(ex + c1, Ng - 1); out[2] = min(ex + c2, Ng - 1); out[3] = min(ex + c3, Ng - 1);
+    if (!(res_total == res_total)) {               // NaN total: every comparison of the bisection fails -> last index
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out[k] = Ng - 1;
+    }
+    __syncwarp();                                    // the histogram is reused by this warp's next chunk
   };
 
   // Once per phase that gathers: total and the systematic uniform.  ts = local step whose resampling is gathered.
@@ -591,19 +663,64 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (a.resampler == 1)
       res_u0 = a.res_u ? a.res_u[(ptrdiff_t)ts * a.B]
                        : philox_uniform(a.seed, BF_STREAM_RESAMPLE, (uint32_t)(ts + a.t_offset), (uint32_t)a.trial, 0ull);
+    if (!SH && use_cells) {
+      // Unsorted (multinomial) positions, one GPU: first the CELL TABLE  cell_lb[c] = lower_bound(tau, c * total / Ng),
+      // c = 0 .. Ng -- the systematic search with u = 0, i.e. sorted queries answered by the counting scheme at streaming
+      // cost.  A position r = total * w, w = 1 - u in [0, 1], lies between the edges of cell c = floor(w * Ng) (computed
+      // exactly: Ng is a power of two) and both are rounded by the same monotone multiplication, so its lower bound lies in
+      // [cell_lb[c], cell_lb[c + 1]]: two adjacent table entries and a search over the ~1 tau of the cell replace the 11
+      // dependent probes of a tile (and when w * Ng is an integer, r IS the edge and cell_lb[c] is the answer).
+      const bool two = a.coarse_log2 >= 0;
+      if (two) {
+        for (int k = tid; k < (1 << a.coarse_log2); k += NT) s_win[k] = __ldcg(a.tau_tile + k);
+        __syncthreads();
+      }
+      for (int q = tid; q <= nchunk_valid; q += NT) {
+        const int slot = (q < nchunk_valid) ? cta_base + 128 * q : min(cta_base + 128 * nchunk_cta, N);
+        const float r = pos_sys(slot, 0.0f);
+        s_lo[q] = (nchunk_valid <= 0) ? 0 : two ? lower_bound_two_level(s_win, a.coarse_log2, a.E, r) : lower_bound_tau_pow2(a.E, a.log2ng, r);
+      }
+      __syncthreads();
+#ifndef BF_EXP_MN_NOBUILD
+      for (int q = warp; q < nchunk_valid; q += CW) {
+        const int lo = s_lo[q], wn = s_lo[q + 1] - lo, s0 = cta_base + 128 * q;
+        int lb[4];
+        if (wn <= 32 * 128) count_window(lo, wn, s0, 0.0f, lb);
+        else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) lb[k] = min(lower_bound_tau_pow2(a.E, a.log2ng, pos_sys(s0 + 4 * lane + k, 0.0f)), Ng - 1);
+        }
+        const int c = s0 + 4 * lane;
+        if (c + 3 < N) *reinterpret_cast<int4*>(a.cell_lb + c) = make_int4(lb[0], lb[1], lb[2], lb[3]);
+        else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (c + k < N) a.cell_lb[c + k] = lb[k];
+        }
+      }
+#endif
+      if (blockIdx.x == 0 && tid == 0) a.cell_lb[Ng] = Ng - 1;
+      grid.sync();
+    }
     if (!SH && !use_win && use_tau && a.coarse_log2 >= 0) {        // the tiles' last thresholds into shared memory
       for (int k = tid; k < (1 << a.coarse_log2); k += NT) s_win[k] = __ldcg(a.tau_tile + k);
       __syncthreads();
     }
     if (!use_win) return;
     // Sorted positions: every answer of chunk q lies in [lower_bound(first slot of q), lower_bound(first slot of q+1)].
-    // One bisection per chunk, all of them in flight together (one latency per step instead of one per chunk).
+    // One bisection per chunk, all of them in flight together (one latency per step instead of one per chunk); on one
+    // GPU its upper levels run on the table of the tiles' last thresholds in shared memory (11 dependent loads, not 24).
+    const bool two = !SH && a.coarse_log2 >= 0;
+    if (two) {
+      for (int k = tid; k < (1 << a.coarse_log2); k += NT) s_win[k] = __ldcg(a.tau_tile + k);
+      __syncthreads();
+    }
     for (int q = tid; q <= nchunk_valid; q += NT) {
       const int slot = a.goff + ((q < nchunk_valid) ? cta_base + 128 * q : min(cta_base + 128 * nchunk_cta, N) - 1);
       int lb = 0;
       if (nchunk_valid > 0) {
         const float r = position(slot, res_u0);
-        if (!SH) lb = lower_bound_tau_pow2(a.E, a.log2ng, r);
+        if (two) lb = lower_bound_two_level(s_win, a.coarse_log2, a.E, r);
+        else if (!SH) lb = lower_bound_tau_pow2(a.E, a.log2ng, r);
         else {                                        // same bisection over the ranks' shards (peer loads)
           unsigned low = 0;
           for (unsigned sft = 1u << (a.log2ng - 1); sft != 0; sft >>= 1)
@@ -686,52 +803,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #endif
 #if PF_FUSED_COUNTING
       if (wn <= 32 * 128) {
-        // Counting instead of searching.  Slot i's answer is lo + #{j in the window : tau_j < r_i}; positions are
-        // non-decreasing in i, so tau_j is below the positions of exactly the slots i >= k_j, k_j = first slot of the
-        // chunk whose position exceeds tau_j.  Every lane turns its share of the window (about one tau per slot) into
-        // k_j -- an estimate from the inverse of the position formula, corrected against the formula itself, so the
-        // result is exact whatever the rounding of the estimate -- and counts it in a 129-bin histogram in shared
-        // memory; a warp prefix sum of the histogram gives all 128 answers.  ~30 instructions per slot where the
-        // bounded bisections took ~75, and no staging of the window.
-        int* hist = reinterpret_cast<int*>(s_win) + warp * 160;
-        const int s0 = a.goff + cta_base + 128 * q;                 // first slot of the chunk (global)
-        *reinterpret_cast<int4*>(hist + lane * 4) = make_int4(0, 0, 0, 0);
-        if (lane == 0) hist[128] = 0;
-        __syncwarp();
-        const float fs0 = (float)s0;                    // a multiple of 128 below 2^31: exact
-        for (int j0 = 0; j0 < wn; j0 += 128) {          // four independent loads in flight per lane
-          float tv[4];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) { const int i = j0 + lane + 32 * m; tv[m] = (i < wn) ? tauG(lo + i) : 0.0f; }
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            if (j0 + lane + 32 * m < wn) {
-              const float tj = tv[m];
-              // estimate: position(s, u) > tj  <=>  s > tj * Ng / total - u
-              float tr = __fsub_rn(__fsub_rn(__fmul_rn(tj, res_scale), res_u0), fs0);
-              tr = fminf(fmaxf(tr, -1.0f), 128.0f);     // (NaN -> -1)
-              int g = min((int)floorf(tr) + 1, 128);
-              while (g > 0 && position(s0 + g - 1, res_u0) > tj) --g;
-              while (g < 128 && !(position(s0 + g, res_u0) > tj)) ++g;
-              atomicAdd(hist + g, 1);
-            }
-          }
-        }
-        __syncwarp();
-        const int4 h4 = *reinterpret_cast<const int4*>(hist + lane * 4);
-        const int c0 = h4.x, c1 = c0 + h4.y, c2 = c1 + h4.z, c3 = c2 + h4.w;
-        int incl = c3;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int up = __shfl_up_sync(BF_FULL, incl, o);
-          if (lane >= o) incl += up;
-        }
-        const int ex = lo + incl - c3;
-        anc[0] = min(ex + c0, Ng - 1); anc[1] = min(ex + c1, Ng - 1); anc[2] = min(ex + c2, Ng - 1); anc[3] = min(ex + c3, Ng - 1);
-        if (!(res_total == res_total)) {               // NaN total: every comparison of the bisection fails -> last index
-#pragma unroll
-          for (int k = 0; k < 4; ++k) anc[k] = Ng - 1;
-        }
+        count_window(lo, wn, a.goff + cta_base + 128 * q, res_u0, anc);
 #else
       if (wn <= WINCAP) {
         float* win = s_win + warp * WINCAP;
@@ -785,6 +857,41 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     }
     if (nv <= 0) return;
     if (use_tau) {
+      if (use_cells) {
+        // w = 1 - u as position() rounds it; cells only for w in [0, 1] (anything else -- a caller's own "uniforms" -- takes
+        // the general search below)
+        float wq[4]; int c[4], lo[4], hi[4];
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          wq[k] = __fmul_rn(__fsub_rn(1.0f, u[k]), (float)Ng);          // exact (power of two)
+          ok = ok && (wq[k] >= 0.0f) && (wq[k] <= (float)Ng);
+          c[k] = min(max((int)wq[k], 0), Ng - 1);
+        }
+        if (ok) {
+#if defined(BF_EXP_MN_NOLOOKUP)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) anc[k] = a.goff + base + k;
+          return;
+#elif defined(BF_EXP_MN_XONLY)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) anc[k] = c[k];
+          return;
+#endif
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { lo[k] = a.cell_lb[c[k]]; hi[k] = a.cell_lb[c[k] + 1]; }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            int pos = lo[k], len = (wq[k] == (float)c[k]) ? 0 : hi[k] - lo[k];     // r == the cell's lower edge: no search
+            while (len > 0) {
+              const int half = len >> 1;
+              if (!(r[k] <= a.E[pos + half])) { pos += half + 1; len -= half + 1; } else len = half;
+            }
+            anc[k] = min(pos, Ng - 1);
+          }
+          return;
+        }
+      }
       if (!SH && a.coarse_log2 >= 0) lower_bound4_two_level(s_win, a.coarse_log2, a.E, r, Ng - 1, anc);
       else if (!SH) bisect4_left_exclusive_pow2(a.E - 1, a.log2ng, r, anc);       // ex[j+1] == tau[j]
       else {

@@ -394,6 +394,36 @@ def test_philox_pf_loglik_converges_to_exact_kalman():
     assert errs[1 << 18] < errs[1 << 14] < errs[1 << 10], errs
 
 
+@pytest.mark.parametrize("name,T,N,thr", [
+    ("bot2", 6, 4096, 1.0),            # two tiles
+    ("bot2", 6, 32768, 1.0),
+    ("ungm", 8, 65536, 0.5),           # resampling and non-resampling steps
+    ("bot2", 4, 1 << 18, 1.0),         # the size from which the table is the default
+])
+def test_multinomial_cell_table(name, T, N, thr, monkeypatch):
+    """Unsorted positions through the cell table (pf_fused.cuh begin_gather: lower bounds of tau at the Ng + 1 cell edges,
+    built by the counting search; a position then searches only the tau of its cell): every ancestor equals the
+    reference's searchsorted, step by step, with the caller's own uniforms (arbitrary floats: the in-cell search) --
+    the Philox uniforms are multiples of 2^-24 and take the edge shortcut at N = 2^24 (the headline-size test)."""
+    monkeypatch.setenv("BF_PF_CELL_TABLE", "1")
+    c = case(name)
+    _, ys = c.simulate(T, 7)
+    u = c.inputs(T)
+    x0, noise, ru = c.pf_randomness(T, N, 8, "multinomial")
+    ru = ru.copy()
+    ru[:, :4] = np.array([0.0, 1.0 - 2.0 ** -24, 0.5, 2.0 ** -24], np.float32)       # w = 1 (the last edge), the first cell, an edge
+    ru[:, 4:512] *= np.float32(0.999)                                                  # not multiples of 2^-24
+    eng = _engine(c, N, 1, thr, "multinomial", "streamed")
+    out = eng.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=ALL_OUT)
+    assert _stepwise(c, out, ys, u, x0, noise, ru, thr, "multinomial") > 0
+    monkeypatch.setenv("BF_PF_CELL_TABLE", "0")
+    eng2 = _engine(c, N, 1, thr, "multinomial", "streamed")
+    out2 = eng2.run_host(ys, inputs=u, init_particles=x0, noise=noise, resample_u=ru, outputs=ALL_OUT)
+    for k in ("ancestors", "log_likelihood", "particles"):
+        np.testing.assert_array_equal(out[k], out2[k], err_msg=k)
+    eng.close(); eng2.close()
+
+
 def test_large_streamed_properties_2pow22():
     """Size-independent properties at a large N (the oracle is too slow for whole trajectories there):
     weights sum to one, ancestors in range and non-decreasing for systematic positions, every gathered particle is
