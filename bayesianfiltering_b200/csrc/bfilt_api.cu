@@ -538,10 +538,14 @@ struct PfRun {
     // optional inputs / per-particle outputs of the call are all absent, see pf_fused.cuh)
     const bool pow2 = N >= 8 && (N & (N - 1)) == 0;
     const char* lenv = getenv("BF_PF_LEAN");
-    const bool lean = h->world == 1 && pow2 && h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC && !io->noise && !io->resample_u &&
-                      !io->out_particles && !io->out_propagated && !io->out_ancestors && !io->out_norm_weights && !io->out_weights &&
-                      !(lenv && lenv[0] == '0');
-    const void* kern = ks.fused[h->world > 1 ? 1 : (lean ? 2 : 0)];
+    const bool lean_ok = pow2 && h->cfg.resampler == BF_RESAMPLE_SYSTEMATIC && !io->noise && !io->resample_u &&
+                         !io->out_particles && !io->out_propagated && !io->out_ancestors && !io->out_norm_weights && !io->out_weights &&
+                         !(lenv && lenv[0] == '0');
+    const bool lean = h->world == 1 && lean_ok;
+    // the sharded filter has a lean instantiation as well: one persistent launch (p2p transport), power-of-two rank count
+    const char* smode_env = getenv("BF_SHARD_MODE");
+    const bool lean_sh = h->world > 1 && lean_ok && (h->world & (h->world - 1)) == 0 && !(smode_env && strcmp(smode_env, "nccl") == 0);
+    const void* kern = ks.fused[h->world > 1 ? (lean_sh ? 3 : 1) : (lean ? 2 : 0)];
     const int ntiles = h->ntiles;
     const int ntiles_scan = h->world > 1 ? h->world * ntiles + 1 : ntiles;       // the scan covers the whole filter's tiles
     const int nchunk = (ntiles_scan + 1 + NW * 128 - 1) / (NW * 128); // chunks of the one-CTA scan of the tile sums
@@ -685,14 +689,18 @@ struct PfRun {
         // Bulk staging of the remote part of each CTA's ancestor range: OFF unless BF_SHARD_BULK=1.  Measured (profiles/README.md):
         // it removes the per-chunk NVLink round trips of the boundary CTAs but serialises their whole transfer before their
         // compute -- 366 vs 320 us per step on 2 GPUs (67 MB per rank cross the link), 188 vs 184 on 8.
+        // The thresholds of the bracket are always staged (BF_SHARD_STAGE_TAU=0 turns it off): 4 bytes per ancestor, and the
+        // window bisections then run on local memory (pf_fused.cuh begin_gather).
         const char* benv = getenv("BF_SHARD_BULK");
-        if (benv && benv[0] == '1') {
-          const size_t cap = (size_t)std::min<int64_t>((int64_t)N, (int64_t)2 * tpc * PF_FUSED_TILE_CHUNKS * 128);
-          if (h->stg_tau.ensure((size_t)grid * cap * 4) == cudaSuccess && h->stg_x.ensure((size_t)grid * cap * DX * 4) == cudaSuccess) {
-            a.stg_tau = h->stg_tau.as<float>(); a.stg_x = h->stg_x.as<float>(); a.stg_cap = (int)cap;
-          } else {
-            cudaGetLastError();
-          }
+        const char* tenv = getenv("BF_SHARD_STAGE_TAU");
+        const size_t cap = (size_t)std::min<int64_t>((int64_t)N * world, (int64_t)(2 * tpc + 4) * PF_FUSED_TILE_CHUNKS * 128);
+        if (!(tenv && tenv[0] == '0')) {
+          if (h->stg_tau.ensure((size_t)grid * cap * 4) == cudaSuccess) { a.stg_tau = h->stg_tau.as<float>(); a.stg_cap = (int)cap; }
+          else cudaGetLastError();
+        }
+        if (a.stg_tau && benv && benv[0] == '1') {
+          if (h->stg_x.ensure((size_t)grid * cap * DX * 4) == cudaSuccess) a.stg_x = h->stg_x.as<float>();
+          else cudaGetLastError();
         }
       }
       a.carry_stats = h->carry_stats.as<StepStats>() + 2 * b;

@@ -8,7 +8,7 @@
 #include "common.cuh"
 
 struct BfKernelSet {
-  const void* fused[3];       // k_pf_fused<M, ...>: general / sharded / lean   args (ModelConst, PfFusedArgs)
+  const void* fused[4];       // k_pf_fused<M, ...>: general / sharded / lean / sharded lean   args (ModelConst, PfFusedArgs)
   int fused_warps;            // warps per CTA of the fused kernels of this model
   const void* resident[2];    // k_pf_resident<M, 8 / 32>                       args (ModelConst, PfResidentArgs)
   const void* gsf_cta;        // k_gsf<M, TV = false>                           args (ModelConst, GsfArgs)

@@ -511,6 +511,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   __shared__ __align__(16) StepStats s_stats;
   __shared__ int s_last;                              // this CTA took the last ticket of the step (it folds the statistics)
   __shared__ int s_ctr[4];                            // chunk queues of phases A / B / C2
+  __shared__ int s_br[2];                             // sharded filter: bracket of this CTA's ancestor range (begin_gather)
 
   const int N = a.N, T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
@@ -548,8 +549,8 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   const bool all_phases = a.phases == PF_PH_ALL;
   const int ns_mask = (1 << (a.log2ns < 0 ? 0 : a.log2ns)) - 1;
   // global accessors: entry j of the (virtual) global tau array, particle j of the previous step's state
-  bool stg_on = false;                                // this CTA's remote ancestor range is staged locally (sharded)
-  int stg_lo = 0, stg_hi = -1;
+  bool stg_on = false, stg_x_on = false;              // this CTA's remote tau range (and, BF_SHARD_BULK=1, particles) is staged locally (sharded)
+  int stg_lo = 0, stg_hi = -1, stg_xlo = 0, stg_xhi = -1;
   const float* stg_tau_c = SH ? a.stg_tau + (size_t)blockIdx.x * a.stg_cap : nullptr;
   const float* stg_x_c = SH ? a.stg_x + (size_t)blockIdx.x * a.stg_cap * M::DX : nullptr;
   auto tauG = [&](int j) -> float {
@@ -657,7 +658,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 
   // Once per phase that gathers: total and the systematic uniform.  ts = local step whose resampling is gathered.
   auto begin_gather = [&](int ts) {
-    stg_on = false;                                  // (the staged copies of the previous step are stale)
+    stg_on = false; stg_x_on = false;                // (the staged copies of the previous step are stale)
     res_total = __ldcg(a.total);
     res_scale = __fdiv_rn((float)Ng, res_total);
     if (a.resampler == 1)
@@ -714,6 +715,61 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       for (int k = tid; k < (1 << a.coarse_log2); k += NT) s_win[k] = __ldcg(a.tau_tile + k);
       __syncthreads();
     }
+    // Sharded filter: BRACKET FIRST.  Every rank holds the prefix of all tiles (Etile, phase C1), so the tiles between which
+    // this CTA's ancestors lie are found without touching a peer; two probes of tau confirm the bracket [blo, bhi) (tau equals
+    // the cdf only up to its last bits); the part of it that lives on other ranks is copied here in one coalesced sweep, and
+    // the per-chunk bisections below run on local data.  (Before: 24 dependent NVLink round trips per bisection, ~65 us
+    // in the CTAs whose ancestors are remote -- profiles/r2_k_shard_trace_g2.txt.)
+    int blo = 0, bhi = Ng;
+    if constexpr (SH) {
+      const int ntg = a.ntiles_g - 1;                  // tiles of the whole filter; Etile[ntg] = total
+      if (nchunk_valid > 0 && ntg <= CW * WINCAP) {
+        for (int k = tid; k < ntg; k += NT) s_win[k] = __ldcg(a.Etile + k);
+        __syncthreads();
+        if (tid < 2) {
+          const int slot = a.goff + (tid == 0 ? cta_base : min(cta_base + 128 * nchunk_cta, N) - 1);
+          const float r = position(slot, res_u0);
+          // tid 0: tiles that END below r (Etile[k + 1] < r), less one;  tid 1: tiles that START at or below r, plus one
+          int lo_ = 0, n_ = ntg;
+          while (n_ > 0) {
+            const int h = n_ >> 1, k = lo_ + h;
+            const float v = (tid == 0) ? ((k + 1 < ntg) ? s_win[k + 1] : res_total) : s_win[k];
+            const bool below = (tid == 0) ? (v < r) : (v <= r);
+            if (below) { lo_ += h + 1; n_ -= h + 1; } else n_ = h;
+          }
+          int b = (tid == 0) ? max(lo_ - 1, 0) * TILE : min(min(lo_ + 1, ntg) * TILE, Ng);
+          // confirm against tau itself (NaN fails): nothing below blo can be an answer, every answer is below bhi
+          if (tid == 0) { if (b > 0 && (r <= tauG(b - 1))) b = 0; if (!(r == r)) b = 0; }
+          else          { if (b < Ng && !(r <= tauG(b - 1))) b = Ng; if (!(r == r)) b = Ng; }
+          s_br[tid] = b;
+        }
+        __syncthreads();
+        blo = s_br[0]; bhi = max(s_br[1], blo);
+        const bool remote = ((blo >> a.log2ns) != a.rank) || (((bhi - 1) >> a.log2ns) != a.rank);
+        if (a.stg_tau && remote && bhi - blo <= a.stg_cap) {
+          // 16-byte peer loads, eight in flight per thread (128 KB per CTA and NVLink round trip); blo, bhi and the ranks'
+          // boundaries are multiples of the tile length, so a vector never straddles two ranks
+          float4* dt4 = reinterpret_cast<float4*>(a.stg_tau + (size_t)blockIdx.x * a.stg_cap);
+          const int cnt4 = (bhi - blo) >> 2;
+          for (int i0 = 0; i0 < cnt4; i0 += 8 * NT) {
+            float4 tv[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const int i = i0 + tid + m * NT, g = blo + 4 * min(i, cnt4 - 1), r = g >> a.log2ns;
+              tv[m] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+              if (i < cnt4 && r != a.rank) tv[m] = __ldcg(reinterpret_cast<const float4*>(a.tau_peers[r] + (g & ns_mask)));
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const int i = i0 + tid + m * NT;
+              if (i < cnt4 && ((blo + 4 * i) >> a.log2ns) != a.rank) dt4[i] = tv[m];
+            }
+          }
+          __syncthreads();
+          stg_on = true; stg_lo = blo; stg_hi = bhi - 1;
+        }
+      }
+    }
     for (int q = tid; q <= nchunk_valid; q += NT) {
       const int slot = a.goff + ((q < nchunk_valid) ? cta_base + 128 * q : min(cta_base + 128 * nchunk_cta, N) - 1);
       int lb = 0;
@@ -721,27 +777,29 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         const float r = position(slot, res_u0);
         if (two) lb = lower_bound_two_level(s_win, a.coarse_log2, a.E, r);
         else if (!SH) lb = lower_bound_tau_pow2(a.E, a.log2ng, r);
-        else {                                        // same bisection over the ranks' shards (peer loads)
-          unsigned low = 0;
-          for (unsigned sft = 1u << (a.log2ng - 1); sft != 0; sft >>= 1)
-            if (!(r <= tauG((int)(low + sft)))) low += sft;
-          lb = (int)(low + ((r <= tauG((int)low)) ? 0u : 1u));
+        else {                                        // lower bound inside the bracket (tau is monotone: any search order)
+          int pos = blo, len = bhi - blo;
+          while (len > 0) {
+            const int half = len >> 1;
+            if (!(r <= tauG(pos + half))) { pos += half + 1; len -= half + 1; } else len = half;
+          }
+          lb = pos;
         }
       }
       s_lo[q] = lb;
     }
     __syncthreads();
     if constexpr (SH) {
-      stg_on = false;
-      if (a.stg_tau && nchunk_valid > 0) {
+      // BF_SHARD_BULK=1: the particles of the remote part of the range as well (measured slower: the transfer is serialised
+      // in front of the compute; the default fetches them chunk by chunk into shared memory, ancestors4)
+      if (a.stg_x && stg_on && nchunk_valid > 0) {
         const int wlo = s_lo[0], whi = min(s_lo[nchunk_valid], Ng - 1);
         const bool remote = ((wlo >> a.log2ns) != a.rank) || ((whi >> a.log2ns) != a.rank);
-        if (remote && whi - wlo + 1 <= a.stg_cap) {
-          float* dt_ = a.stg_tau + (size_t)blockIdx.x * a.stg_cap;
+        if (remote && wlo >= stg_lo && whi <= stg_hi) {
           float* dx_ = a.stg_x + (size_t)blockIdx.x * a.stg_cap * DX;
           const int cnt = whi - wlo + 1;
-          for (int i0 = 0; i0 < cnt; i0 += 4 * NT) {       // four peer loads of each kind in flight per thread
-            float tv[4], xv[4][DX];
+          for (int i0 = 0; i0 < cnt; i0 += 4 * NT) {       // four peer loads in flight per thread
+            float xv[4][DX];
             bool rm[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
@@ -749,21 +807,13 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
               const int g = wlo + min(i, cnt - 1);
               const int r = g >> a.log2ns;
               rm[m] = i < cnt && r != a.rank;
-              if (rm[m]) {
-                tv[m] = a.tau_peers[r][g & ns_mask];
-                load_state_cg<DX>(xp_stage[r], (size_t)(g & ns_mask), xv[m]);
-              }
+              if (rm[m]) load_state_cg<DX>(xp_stage[r], (size_t)(g & ns_mask), xv[m]);
             }
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              if (rm[m]) {
-                const int i = i0 + tid + m * NT;
-                dt_[i] = tv[m];
-                store_state<DX>(dx_, (size_t)i, xv[m]);
-              }
-            }
+            for (int m = 0; m < 4; ++m)
+              if (rm[m]) store_state<DX>(dx_, (size_t)(wlo - stg_lo + i0 + tid + m * NT), xv[m]);
           }
-          stg_on = true; stg_lo = wlo; stg_hi = whi;
+          stg_x_on = true; stg_xlo = wlo; stg_xhi = whi;
         }
       }
       __syncthreads();
@@ -828,7 +878,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #endif
         // Sharded filter, ancestors (partly) on another rank: x[lo .. lo+wn] is a contiguous range -- fetch it with
         // coalesced 512-byte peer reads into shared memory instead of one 16-byte NVLink round trip per particle.
-        if (SH && !stg_on && a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
+        if (SH && !stg_x_on && a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
           float* xs = s_xst + (size_t)warp * PF_FUSED_XCAP * DX;
           for (int i0 = 0; i0 <= wn; i0 += 128) {       // four peer loads in flight per lane (an NVLink round trip is ~3 us)
             float xv[4][DX];
@@ -907,7 +957,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   // particle `g` (GLOBAL index) of the state the step reads: own shard or a peer's
   auto load_prev = [&](int g, const float* xp_local, const float* const* xp_peers, float* x) {
     if (!SH) load_state_cg<DX>(xp_local, (size_t)g, x);
-    else if (stg_on && (g >> a.log2ns) != a.rank && g >= stg_lo && g <= stg_hi) load_state_cg<DX>(stg_x_c, (size_t)(g - stg_lo), x);
+    else if (stg_x_on && (g >> a.log2ns) != a.rank && g >= stg_xlo && g <= stg_xhi) load_state_cg<DX>(stg_x_c, (size_t)(g - stg_lo), x);
     else load_state_cg<DX>(xp_peers[g >> a.log2ns], (size_t)(g & ns_mask), x);
   };
 

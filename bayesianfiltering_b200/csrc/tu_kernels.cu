@@ -24,6 +24,7 @@ struct Fill {
     k->fused[0] = (const void*)k_pf_fused<M, NW, 1, false, false>;
     k->fused[1] = (const void*)k_pf_fused<M, NW, 1, true, false>;
     k->fused[2] = (const void*)k_pf_fused<M, NW, 1, false, true>;
+    k->fused[3] = (const void*)k_pf_fused<M, NW, 1, true, true>;
     return 0;
   }
 };
