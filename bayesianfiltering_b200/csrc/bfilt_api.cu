@@ -272,7 +272,7 @@ struct bf_pf_s {
   ncclComm_t comm = nullptr;
   bool peers_ready = false;
   void* peer_ptr[4][8] = {};          // imported tau / xa / xb / exchange buffer of every rank (own entries = own buffers)
-  DevBuf stg_tau, stg_x;              // bulk staging of remote ancestor ranges (sharded)
+  DevBuf stg_tau;                     // staged thresholds of the remote ancestor brackets (sharded)
   DevBuf peer_tab, barrier_buf;       // device tables [4][8] of the pointers above; 1 float for the step barrier
   DevBuf xchg;                        // exchange buffer: flags [3][8] u64 | epoch | err | partials | tilesum | V  (pf_fused.cuh)
   size_t off_part = 0, off_ts = 0, off_V = 0;
@@ -383,7 +383,7 @@ extern "C" int bf_pf_destroy(bf_pf_handle h) {
       for (int r = 0; r < h->world; ++r)
         if (r != h->rank && h->peer_ptr[k][r]) cudaIpcCloseMemHandle(h->peer_ptr[k][r]);
   DevBuf* all[] = {&h->carry_x, &h->carry_w, &h->carry_uniform, &h->carry_stats, &h->xa, &h->xb, &h->LL, &h->E, &h->anc,
-                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V, &h->peer_tab, &h->barrier_buf, &h->xchg, &h->stg_tau, &h->stg_x};
+                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V, &h->peer_tab, &h->barrier_buf, &h->xchg, &h->stg_tau};
   for (DevBuf* b : all) b->release();
   for (DevBuf& b : h->hbuf) b.release();
   delete h;
@@ -555,8 +555,8 @@ struct PfRun {
     int grid = 1, tpc = ntiles;
     size_t smem = 0;
     const int stage_ts = (ntiles_scan + 1 <= 16384) ? ((ntiles_scan + 3) & ~3) + 256 : 0;   // tile sums staged in shared memory by C1 (+ scratch)
-    auto smem_for = [&](int t) { return (size_t)((3 * TW + 2) * t + 2 + std::max(NW * PF_FUSED_WINCAP, stage_ts + nchunk + 1 + NW + 8) +
-                                                (xstage ? NW * PF_FUSED_XCAP * DX : 0) + 8) * sizeof(float); };
+    auto smem_for = [&](int t) { return (size_t)((3 * TW + 3) * t + 2 + std::max(NW * PF_FUSED_WINCAP, stage_ts + nchunk + 1 + NW + 8) +
+                                                (xstage ? 2 * NW * PF_FUSED_XCAP * DX : 0) + 8) * sizeof(float); };
     for (int round = 0; round < 3; ++round) {
       smem = smem_for(round == 0 ? 64 : tpc);
       if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -686,20 +686,19 @@ struct PfRun {
         a.epoch = reinterpret_cast<unsigned long long*>(xb + 256);
         a.err = reinterpret_cast<int*>(xb + 264);
         a.xstage = xstage ? 1 : 0;
-        // Bulk staging of the remote part of each CTA's ancestor range: OFF unless BF_SHARD_BULK=1.  Measured (profiles/README.md):
-        // it removes the per-chunk NVLink round trips of the boundary CTAs but serialises their whole transfer before their
-        // compute -- 366 vs 320 us per step on 2 GPUs (67 MB per rank cross the link), 188 vs 184 on 8.
-        // The thresholds of the bracket are always staged (BF_SHARD_STAGE_TAU=0 turns it off): 4 bytes per ancestor, and the
-        // window bisections then run on local memory (pf_fused.cuh begin_gather).
-        const char* benv = getenv("BF_SHARD_BULK");
+        // Ownership of the blocks (bt tiles) is dealt round the CTAs (pf_fused.cuh, "Ownership"); BF_SHARD_STRIDED=0 keeps the
+        // contiguous split.  The thresholds of each window block's ancestor bracket are staged here (BF_SHARD_STAGE_TAU=0: off).
+        const char* senv = getenv("BF_SHARD_STRIDED");
+        int log2bt = 0;
+        while ((1 << log2bt) < bt) ++log2bt;
+        a.log2bt = log2bt;
+        a.strided = (!(senv && senv[0] == '0') && ntiles % bt == 0 && tpc / bt <= PF_FUSED_MAXWB) ? 1 : 0;
         const char* tenv = getenv("BF_SHARD_STAGE_TAU");
-        const size_t cap = (size_t)std::min<int64_t>((int64_t)N * world, (int64_t)(2 * tpc + 4) * PF_FUSED_TILE_CHUNKS * 128);
+        const int64_t FT = (int64_t)PF_FUSED_TILE_CHUNKS * 128;
+        a.stg_blocks = a.strided ? tpc / bt : 1;
+        const size_t cap = (size_t)std::min<int64_t>((int64_t)N * world, a.strided ? (int64_t)(bt + 4) * FT : (int64_t)(2 * tpc + 4) * FT);
         if (!(tenv && tenv[0] == '0')) {
-          if (h->stg_tau.ensure((size_t)grid * cap * 4) == cudaSuccess) { a.stg_tau = h->stg_tau.as<float>(); a.stg_cap = (int)cap; }
-          else cudaGetLastError();
-        }
-        if (a.stg_tau && benv && benv[0] == '1') {
-          if (h->stg_x.ensure((size_t)grid * cap * DX * 4) == cudaSuccess) a.stg_x = h->stg_x.as<float>();
+          if (h->stg_tau.ensure((size_t)grid * a.stg_blocks * cap * 4) == cudaSuccess) { a.stg_tau = h->stg_tau.as<float>(); a.stg_cap = (int)cap; }
           else cudaGetLastError();
         }
       }

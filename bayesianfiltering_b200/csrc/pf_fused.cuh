@@ -43,8 +43,9 @@ namespace cg = cooperative_groups;
 #define PF_FUSED_WARPS 32                   // warps per CTA, one CTA per SM (64 registers per thread)
 #endif
 #define PF_FUSED_WARPS_LARGE 16             // states with dx > 4: 16 warps at 128 registers per thread
-#define PF_FUSED_WINCAP 512                 // floats of tau a warp stages in shared memory for one chunk of 128 slots
-#define PF_FUSED_XCAP 256                   // particles a warp of a SHARDED filter stages when a chunk's ancestors live on a peer
+#define PF_FUSED_WINCAP 256                 // floats of shared memory per warp for the histogram / tile tables / scan scratch
+#define PF_FUSED_XCAP 160                   // particles a warp of a SHARDED filter stages when a chunk's ancestors live on a peer (two buffers)
+#define PF_FUSED_MAXWB 32          // window blocks (runs of consecutive owned tiles) per CTA, sharded filter with dealt blocks
 
 struct PfFusedArgs {
   int N, T, t_offset, trial, B;
@@ -107,8 +108,9 @@ struct PfFusedArgs {
   // Bulk staging (sharded): before its units, a CTA copies the part of its ancestor range [s_lo[0], s_lo[last]] that lives on
   // other ranks -- tau and the particle state -- into these LOCAL buffers with every thread's loads in flight at once; the
   // units then never wait for an NVLink round trip (they cost the boundary CTAs 70 % when fetched chunk by chunk).
-  float* stg_tau; float* stg_x;              // [gridDim.x][stg_cap], [gridDim.x][stg_cap][DX]
-  int stg_cap;
+  float* stg_tau;                            // [gridDim.x][stg_blocks][stg_cap] staged thresholds of the ancestor brackets (sharded)
+  int stg_cap, stg_blocks;
+  int strided, log2bt;                       // sharded: CTA c owns the blocks (bt tiles) c, c + grid, c + 2 grid, ... of its rank
   char* const* xchg_peers;                   // device table [world] of the exchange buffers (own entry = own buffer)
   unsigned long long* flags;                 // own flags [3][8]
   unsigned long long* epoch;                 // runs completed on this handle (device side: CUDA-graph replays need no new arguments)
@@ -505,23 +507,48 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   float* s_wsum = s_dyn;
   float* s_v0 = s_wsum + TW * tpc;
   float* s_meta_f = s_v0 + TW * tpc;
-  int* s_lo = reinterpret_cast<int*>(s_meta_f + 2 * tpc);       // [TW*tpc + 2] tau window start of each chunk
-  float* s_win = s_dyn + (((3 * TW + 2) * tpc + 2 + 3) & ~3);   // 16-byte aligned (vector accesses to the histogram)
-  float* s_xst = s_win + CW * WINCAP;                           // [CW][XCAP*DX], sharded filters only (host sizes it)
+  int* s_lo = reinterpret_cast<int*>(s_meta_f + 2 * tpc);       // [(TW+1)*tpc + 2] tau window start of each chunk (+ one end per window block)
+  float* s_win = s_dyn + (((3 * TW + 3) * tpc + 2 + 3) & ~3);   // 16-byte aligned (vector accesses to the histogram)
+  float* s_xst = s_win + CW * WINCAP;                           // [CW][2][XCAP*DX], sharded filters only (host sizes it)
+  // the particles of a remote ancestor window are fetched ONE CHUNK AHEAD with cp.async (16-byte rows): the NVLink round
+  // trip (3-10 us under load) overlaps the propagation of the chunk in hand instead of stalling the warp
+  constexpr bool XPIPE = SH && (DX == 4);
+  bool x_pre = false;                                 // the chunk's window is (being) staged by the pipeline
+  int x_buf = 0;                                      // ... in this buffer of the warp
   __shared__ __align__(16) StepStats s_stats;
   __shared__ int s_last;                              // this CTA took the last ticket of the step (it folds the statistics)
   __shared__ int s_ctr[4];                            // chunk queues of phases A / B / C2
-  __shared__ int s_br[2];                             // sharded filter: bracket of this CTA's ancestor range (begin_gather)
+  __shared__ int s_br[2 * PF_FUSED_MAXWB];            // sharded filter: bracket [lo, hi) of the ancestors of each window block (begin_gather)
+  __shared__ int s_stg[PF_FUSED_MAXWB];               // ... its remote thresholds are staged in this CTA's part of a.stg_tau
 
   const int N = a.N, T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
-  const int tile0 = blockIdx.x * tpc;
-  const int tile1 = min(tile0 + tpc, a.ntiles);
-  // chunks (128 consecutive particles) of this CTA: chunk q starts at particle cta_base + 128 q; warps take them
+  // Ownership.  One GPU: CTA c owns the tiles [c tpc, (c + 1) tpc).  Sharded filter (a.strided): CTA c owns the BLOCKS (bt
+  // consecutive tiles, the unit of the statistics tree) c, c + G, c + 2G, ... of its rank -- the slots whose ancestors live
+  // on another rank are a contiguous part of the rank's range, and dealing the blocks round gives every CTA the same share
+  // of them (contiguous ownership left a few CTAs with nothing but NVLink round trips, and everyone else waiting).
+  // Nothing that is computed depends on who owns what: every reduction is a fixed tree over the particle index.
+  const bool strided = SH && a.strided != 0;
+  const int log2bt = a.log2bt, btm = (1 << log2bt) - 1;
+  const int tile0 = blockIdx.x * tpc;                  // (contiguous ownership)
+  int ntile_cta = max(0, min(tile0 + tpc, a.ntiles) - tile0);
+  if (strided) {
+    const int nblk_rank = a.ntiles >> log2bt;          // (the host makes ntiles a multiple of bt)
+    ntile_cta = ((int)blockIdx.x < nblk_rank) ? (((nblk_rank - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) << log2bt) : 0;
+  }
+  auto tile_of = [&](int tl) -> int {                  // tile tl of this CTA -> tile of the rank
+    return strided ? ((((tl >> log2bt) * (int)gridDim.x + (int)blockIdx.x) << log2bt) + (tl & btm)) : tile0 + tl;
+  };
+  auto pbase = [&](int q) -> int { return tile_of(q / TW) * TILE + (q % TW) * 128; };     // first particle of chunk q of this CTA
+  // chunks (128 consecutive particles) of this CTA; warps take them
   // from a shared queue (the SM's warp arbiter favours some warps: a static split leaves the others as a tail)
-  const int nchunk_cta = TW * (tile1 - tile0);
-  const int cta_base = tile0 * TILE;
-  const int nchunk_valid = max(0, min(nchunk_cta, (N - cta_base + 127) / 128));
+  const int nchunk_cta = TW * ntile_cta;
+  const int cta_base = tile0 * TILE;                   // (contiguous ownership)
+  const int nchunk_valid = strided ? nchunk_cta : max(0, min(nchunk_cta, (N - cta_base + 127) / 128));
+  // window blocks: runs of consecutive chunks, whose tau windows share their end points -- the whole CTA, or one block
+  const int wb = strided ? (TW << log2bt) : max(nchunk_cta, 1);
+  const int nwb = strided ? (ntile_cta >> log2bt) : 1;
+  auto sidx = [&](int q) -> int { return strided ? (q / wb) * (wb + 1) + (q % wb) : q; };
 #ifdef BF_DYNAMIC_CHUNKS
   auto next_chunk = [&](int which) -> int {
     int q = 0;
@@ -549,10 +576,13 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   const bool all_phases = a.phases == PF_PH_ALL;
   const int ns_mask = (1 << (a.log2ns < 0 ? 0 : a.log2ns)) - 1;
   // global accessors: entry j of the (virtual) global tau array, particle j of the previous step's state
-  bool stg_on = false, stg_x_on = false;              // this CTA's remote tau range (and, BF_SHARD_BULK=1, particles) is staged locally (sharded)
-  int stg_lo = 0, stg_hi = -1, stg_xlo = 0, stg_xhi = -1;
-  const float* stg_tau_c = SH ? a.stg_tau + (size_t)blockIdx.x * a.stg_cap : nullptr;
-  const float* stg_x_c = SH ? a.stg_x + (size_t)blockIdx.x * a.stg_cap * M::DX : nullptr;
+  bool stg_on = false;                                // the remote thresholds of the window block in hand are staged locally (sharded)
+  int stg_lo = 0, stg_hi = -1;
+  const float* stg_cta = (SH && a.stg_tau) ? a.stg_tau + (size_t)blockIdx.x * a.stg_blocks * a.stg_cap : nullptr;
+  const float* stg_tau_c = stg_cta;
+  auto set_stage = [&](int b) {                        // window block b of this CTA: where tauG finds its remote thresholds
+    if constexpr (SH) { stg_on = s_stg[b] != 0; stg_lo = s_br[2 * b]; stg_hi = s_br[2 * b + 1] - 1; stg_tau_c = stg_cta + (size_t)b * a.stg_cap; }
+  };
   auto tauG = [&](int j) -> float {
     if constexpr (!SH) return a.E[j];
     else {
@@ -658,7 +688,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 
   // Once per phase that gathers: total and the systematic uniform.  ts = local step whose resampling is gathered.
   auto begin_gather = [&](int ts) {
-    stg_on = false; stg_x_on = false;                // (the staged copies of the previous step are stale)
+    stg_on = false;                                  // (the staged copies of the previous step are stale)
     res_total = __ldcg(a.total);
     res_scale = __fdiv_rn((float)Ng, res_total);
     if (a.resampler == 1)
@@ -720,65 +750,97 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     // the cdf only up to its last bits); the part of it that lives on other ranks is copied here in one coalesced sweep, and
     // the per-chunk bisections below run on local data.  (Before: 24 dependent NVLink round trips per bisection, ~65 us
     // in the CTAs whose ancestors are remote -- profiles/r2_k_shard_trace_g2.txt.)
-    int blo = 0, bhi = Ng;
     if constexpr (SH) {
       const int ntg = a.ntiles_g - 1;                  // tiles of the whole filter; Etile[ntg] = total
-      if (nchunk_valid > 0 && ntg <= CW * WINCAP) {
+      const bool bracket = nchunk_valid > 0 && ntg <= CW * WINCAP && nwb <= PF_FUSED_MAXWB;
+      if (bracket) {
         for (int k = tid; k < ntg; k += NT) s_win[k] = __ldcg(a.Etile + k);
         __syncthreads();
-        if (tid < 2) {
-          const int slot = a.goff + (tid == 0 ? cta_base : min(cta_base + 128 * nchunk_cta, N) - 1);
+      }
+      if (tid < 2 * PF_FUSED_MAXWB) {
+        const int b = tid >> 1, up = tid & 1;
+        int v = up ? Ng : 0;
+        if (bracket && b < nwb) {
+          const int slot = a.goff + (!strided ? (up ? min(cta_base + 128 * nchunk_cta, N) - 1 : cta_base)
+                                              : (up ? pbase(b * wb + wb - 1) + 127 : pbase(b * wb)));
           const float r = position(slot, res_u0);
-          // tid 0: tiles that END below r (Etile[k + 1] < r), less one;  tid 1: tiles that START at or below r, plus one
+          // lower end: the tiles that END below r (Etile[k + 1] < r) hold no answer;  upper end: nor do the tiles that START above r
           int lo_ = 0, n_ = ntg;
           while (n_ > 0) {
             const int h = n_ >> 1, k = lo_ + h;
-            const float v = (tid == 0) ? ((k + 1 < ntg) ? s_win[k + 1] : res_total) : s_win[k];
-            const bool below = (tid == 0) ? (v < r) : (v <= r);
+            const float e = up ? s_win[k] : ((k + 1 < ntg) ? s_win[k + 1] : res_total);
+            const bool below = up ? (e <= r) : (e < r);
             if (below) { lo_ += h + 1; n_ -= h + 1; } else n_ = h;
           }
-          int b = (tid == 0) ? max(lo_ - 1, 0) * TILE : min(min(lo_ + 1, ntg) * TILE, Ng);
-          // confirm against tau itself (NaN fails): nothing below blo can be an answer, every answer is below bhi
-          if (tid == 0) { if (b > 0 && (r <= tauG(b - 1))) b = 0; if (!(r == r)) b = 0; }
-          else          { if (b < Ng && !(r <= tauG(b - 1))) b = Ng; if (!(r == r)) b = Ng; }
-          s_br[tid] = b;
+          // confirm against tau itself, which equals the cdf only up to its last bits: widen by a tile, then give up (NaN: give up)
+          if (!up) {
+            v = min(lo_ * TILE, Ng);
+            if (v > 0 && (r <= tauG(v - 1))) v = max(v - TILE, 0);
+            if (v > 0 && (r <= tauG(v - 1))) v = 0;
+            if (!(r == r)) v = 0;
+          } else {
+            v = (lo_ > 0) ? min(lo_ * TILE, Ng) : Ng;
+            if (v < Ng && !(r <= tauG(v - 1))) v = min(v + TILE, Ng);
+            if (v < Ng && !(r <= tauG(v - 1))) v = Ng;
+            if (!(r == r)) v = Ng;
+          }
+        }
+        s_br[tid] = v;
+      }
+      __syncthreads();
+      if (tid < PF_FUSED_MAXWB) {
+        int on = 0;
+        if (bracket && tid < nwb && a.stg_tau && tid < a.stg_blocks) {
+          const int blo = s_br[2 * tid], bhi = s_br[2 * tid + 1];
+          const bool remote = bhi > blo && (((blo >> a.log2ns) != a.rank) || (((bhi - 1) >> a.log2ns) != a.rank));
+          on = (remote && bhi - blo <= a.stg_cap) ? 1 : 0;
+        }
+        s_stg[tid] = on;
+      }
+      __syncthreads();
+      if (bracket && a.stg_tau) {
+        // 16-byte peer loads, eight in flight per thread (128 KB per CTA and NVLink round trip), all blocks in one sweep; the
+        // brackets and the ranks' boundaries are multiples of the tile length, so a vector never straddles two ranks
+        float4* dt4 = reinterpret_cast<float4*>(a.stg_tau + (size_t)blockIdx.x * a.stg_blocks * a.stg_cap);
+        const int cap4 = a.stg_cap >> 2, items = min(nwb, a.stg_blocks) * cap4;
+        for (int i0 = 0; i0 < items; i0 += 8 * NT) {
+          float4 tv[8];
+          bool rm[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int i = min(i0 + tid + m * NT, items - 1), b = i / cap4, o = i - b * cap4;
+            const int g = s_br[2 * b] + 4 * o;
+            const bool in = (i0 + tid + m * NT < items) && s_stg[b] && g < s_br[2 * b + 1];
+            const int r = in ? (g >> a.log2ns) : a.rank;
+            rm[m] = in && r != a.rank;
+            tv[m] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (rm[m]) tv[m] = __ldcg(reinterpret_cast<const float4*>(a.tau_peers[r] + (g & ns_mask)));
+          }
+#pragma unroll
+          for (int m = 0; m < 8; ++m)
+            if (rm[m]) dt4[i0 + tid + m * NT] = tv[m];
         }
         __syncthreads();
-        blo = s_br[0]; bhi = max(s_br[1], blo);
-        const bool remote = ((blo >> a.log2ns) != a.rank) || (((bhi - 1) >> a.log2ns) != a.rank);
-        if (a.stg_tau && remote && bhi - blo <= a.stg_cap) {
-          // 16-byte peer loads, eight in flight per thread (128 KB per CTA and NVLink round trip); blo, bhi and the ranks'
-          // boundaries are multiples of the tile length, so a vector never straddles two ranks
-          float4* dt4 = reinterpret_cast<float4*>(a.stg_tau + (size_t)blockIdx.x * a.stg_cap);
-          const int cnt4 = (bhi - blo) >> 2;
-          for (int i0 = 0; i0 < cnt4; i0 += 8 * NT) {
-            float4 tv[8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const int i = i0 + tid + m * NT, g = blo + 4 * min(i, cnt4 - 1), r = g >> a.log2ns;
-              tv[m] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-              if (i < cnt4 && r != a.rank) tv[m] = __ldcg(reinterpret_cast<const float4*>(a.tau_peers[r] + (g & ns_mask)));
-            }
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const int i = i0 + tid + m * NT;
-              if (i < cnt4 && ((blo + 4 * i) >> a.log2ns) != a.rank) dt4[i] = tv[m];
-            }
-          }
-          __syncthreads();
-          stg_on = true; stg_lo = blo; stg_hi = bhi - 1;
-        }
       }
     }
-    for (int q = tid; q <= nchunk_valid; q += NT) {
-      const int slot = a.goff + ((q < nchunk_valid) ? cta_base + 128 * q : min(cta_base + 128 * nchunk_cta, N) - 1);
+    // one lower bound per chunk boundary: per window block, its wb chunk starts and its last slot
+    const int nbound = strided ? nwb * (wb + 1) : nchunk_valid + 1;
+    for (int kb = tid; kb < nbound; kb += NT) {
+      int slot, blk = 0;
+      if (!strided) slot = (kb < nchunk_valid) ? cta_base + 128 * kb : min(cta_base + 128 * nchunk_cta, N) - 1;
+      else {
+        blk = kb / (wb + 1);
+        const int e = kb - blk * (wb + 1);
+        slot = (e < wb) ? pbase(blk * wb + e) : pbase(blk * wb + wb - 1) + 127;
+      }
       int lb = 0;
       if (nchunk_valid > 0) {
-        const float r = position(slot, res_u0);
+        const float r = position(a.goff + slot, res_u0);
         if (two) lb = lower_bound_two_level(s_win, a.coarse_log2, a.E, r);
         else if (!SH) lb = lower_bound_tau_pow2(a.E, a.log2ng, r);
         else {                                        // lower bound inside the bracket (tau is monotone: any search order)
-          int pos = blo, len = bhi - blo;
+          set_stage(blk);
+          int pos = s_br[2 * blk], len = s_br[2 * blk + 1] - pos;
           while (len > 0) {
             const int half = len >> 1;
             if (!(r <= tauG(pos + half))) { pos += half + 1; len -= half + 1; } else len = half;
@@ -786,38 +848,9 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
           lb = pos;
         }
       }
-      s_lo[q] = lb;
+      s_lo[kb] = lb;
     }
     __syncthreads();
-    if constexpr (SH) {
-      // BF_SHARD_BULK=1: the particles of the remote part of the range as well (measured slower: the transfer is serialised
-      // in front of the compute; the default fetches them chunk by chunk into shared memory, ancestors4)
-      if (a.stg_x && stg_on && nchunk_valid > 0) {
-        const int wlo = s_lo[0], whi = min(s_lo[nchunk_valid], Ng - 1);
-        const bool remote = ((wlo >> a.log2ns) != a.rank) || ((whi >> a.log2ns) != a.rank);
-        if (remote && wlo >= stg_lo && whi <= stg_hi) {
-          float* dx_ = a.stg_x + (size_t)blockIdx.x * a.stg_cap * DX;
-          const int cnt = whi - wlo + 1;
-          for (int i0 = 0; i0 < cnt; i0 += 4 * NT) {       // four peer loads in flight per thread
-            float xv[4][DX];
-            bool rm[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int i = i0 + tid + m * NT;
-              const int g = wlo + min(i, cnt - 1);
-              const int r = g >> a.log2ns;
-              rm[m] = i < cnt && r != a.rank;
-              if (rm[m]) load_state_cg<DX>(xp_stage[r], (size_t)(g & ns_mask), xv[m]);
-            }
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
-              if (rm[m]) store_state<DX>(dx_, (size_t)(wlo - stg_lo + i0 + tid + m * NT), xv[m]);
-          }
-          stg_x_on = true; stg_xlo = wlo; stg_xhi = whi;
-        }
-      }
-      __syncthreads();
-    }
   };
 
   // Ancestors of the 4 slots base..base+3 of the chunk starting at cbase.  Warp-synchronous (all lanes call it).
@@ -847,13 +880,14 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #pragma unroll
     for (int k = 0; k < 4; ++k) r[k] = position(a.goff + base + k, u[k]);
     if (use_win) {
-      const int lo = s_lo[q], wn = s_lo[q + 1] - lo;             // warp-uniform
+      const int lo = s_lo[sidx(q)], wn = s_lo[sidx(q) + 1] - lo;    // warp-uniform
+      if (SH) set_stage(strided ? q / wb : 0);
 #ifndef PF_FUSED_COUNTING
 #define PF_FUSED_COUNTING 1
 #endif
 #if PF_FUSED_COUNTING
       if (wn <= 32 * 128) {
-        count_window(lo, wn, a.goff + cta_base + 128 * q, res_u0, anc);
+        count_window(lo, wn, a.goff + pbase(q), res_u0, anc);
 #else
       if (wn <= WINCAP) {
         float* win = s_win + warp * WINCAP;
@@ -878,8 +912,10 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
 #endif
         // Sharded filter, ancestors (partly) on another rank: x[lo .. lo+wn] is a contiguous range -- fetch it with
         // coalesced 512-byte peer reads into shared memory instead of one 16-byte NVLink round trip per particle.
-        if (SH && !stg_x_on && a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
-          float* xs = s_xst + (size_t)warp * PF_FUSED_XCAP * DX;
+        if (SH && a.xstage && wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
+          if (x_pre) { xs_lo = lo; }                   // already on its way (xprefetch), same window, same test
+          else {
+          float* xs = s_xst + (size_t)(2 * warp + x_buf) * PF_FUSED_XCAP * DX;
           for (int i0 = 0; i0 <= wn; i0 += 128) {       // four peer loads in flight per lane (an NVLink round trip is ~3 us)
             float xv[4][DX];
 #pragma unroll
@@ -897,6 +933,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
             }
           }
           xs_lo = lo;
+          }
         }
         __syncwarp();                                  // the window is overwritten by this warp's next chunk
       } else if (nv > 0) {                             // window larger than the cap (very uneven weights): rare
@@ -957,7 +994,6 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   // particle `g` (GLOBAL index) of the state the step reads: own shard or a peer's
   auto load_prev = [&](int g, const float* xp_local, const float* const* xp_peers, float* x) {
     if (!SH) load_state_cg<DX>(xp_local, (size_t)g, x);
-    else if (stg_x_on && (g >> a.log2ns) != a.rank && g >= stg_xlo && g <= stg_xhi) load_state_cg<DX>(stg_x_c, (size_t)(g - stg_lo), x);
     else load_state_cg<DX>(xp_peers[g >> a.log2ns], (size_t)(g & ns_mask), x);
   };
 
@@ -1058,22 +1094,54 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     trace(t, 10);
     // Warps take UNITS of 4 consecutive chunks (512 particles): a lane's 16 particles are accumulated in index order and the
     // unit is reduced at once, so the unit partial is a function of the data alone (see PfFusedArgs::upart).
-    for (int un = next_chunk(0); un < nchunk_cta / 4; un = next_chunk(0)) {
-    const int lu = cta_base / 512 + un;                // unit index within this rank
+    // (sharded) rows of chunk q's ancestor window -> buffer b of this warp, asynchronously; always commits one group
+    auto xprefetch = [&](int q, int b) {
+      if constexpr (XPIPE) {
+        if (q >= 0 && q < nchunk_valid) {
+          const int lo = s_lo[sidx(q)], wn = s_lo[sidx(q) + 1] - lo;
+          if (wn + 1 <= PF_FUSED_XCAP && (((lo >> a.log2ns) != a.rank) || ((min(lo + wn, Ng - 1) >> a.log2ns) != a.rank))) {
+            float* xs = s_xst + (size_t)(2 * warp + b) * PF_FUSED_XCAP * DX;
+            for (int i = lane; i <= wn; i += 32) {
+              const int g = min(lo + i, Ng - 1);
+              const float* src = xp_stage[g >> a.log2ns] + (size_t)(g & ns_mask) * DX;
+              const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + (size_t)i * DX);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+      }
+    };
+    const int nunit_cta = nchunk_cta / 4;
+    const bool xpipe = XPIPE && gather && use_win && a.xstage != 0;
+    int un = next_chunk(0);
+    x_pre = xpipe; x_buf = 0;
+    if (xpipe) xprefetch(un < nunit_cta ? 4 * un : -1, 0);
+    while (un < nunit_cta) {
+    const int un_next = xpipe ? next_chunk(0) : 0;      // taken early: its first chunk is prefetched during this unit's last
+    const int lu = pbase(4 * un) / 512;                // unit index within this rank
     if (lu >= a.nunits) break;                         // tile padding past N
     acc.init();
 #pragma unroll 1                                        // the body is ~30 KB of SASS: four copies would not fit the instruction cache
     for (int c4 = 0; c4 < 4; ++c4) {
       const int q = 4 * un + c4;
       if (q >= nchunk_valid) break;
-      const int base = cta_base + 128 * q + lane * 4;
+      const int base = pbase(q) + lane * 4;
       const int nv = max(0, min(4, N - base));
       int anc[4] = {a.goff + base, a.goff + base + 1, a.goff + base + 2, a.goff + base + 3};     // global indices
       int xs_lo = -1;
       xp_stage = xp_peers;
+      if (xpipe) {                                     // next chunk's rows on their way; this chunk's have landed
+        __syncwarp();                                  // (every lane has read the rows of the chunk before last out of that buffer)
+        xprefetch((c4 < 3) ? q + 1 : (un_next < nunit_cta ? 4 * un_next : -1), x_buf ^ 1);
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncwarp();
+      }
 #ifndef BF_EXP_NOSEARCH
       if (gather) ancestors4(t - 1, q, base, nv, anc, xs_lo);
 #endif
+      const int xb_cur = x_buf;
+      if (xpipe) x_buf ^= 1;                           // (the rows of this chunk are read below through xb_cur)
       if (nv <= 0) continue;
       if (pt > 0 && a.out_ancestors) {
         int* o = a.out_ancestors + ((ptrdiff_t)t - 1) * N + base;
@@ -1094,7 +1162,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       for (int k = 0; k < 4; ++k) {
         if (k < nv) {
           if (SH && xs_lo >= 0) {
-            const float* xsrc = s_xst + ((size_t)warp * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
+            const float* xsrc = s_xst + ((size_t)(2 * warp + xb_cur) * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
 #pragma unroll
             for (int c = 0; c < DX; ++c) xs[k][c] = xsrc[c];
           } else if (gather) load_prev(anc[k], x_prev, xp_peers, xs[k]);
@@ -1174,7 +1242,10 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     acc.unit_reduce();
 #endif
     if (lane == 0) acc.store(a.upart + lu);
+    un = xpipe ? un_next : next_chunk(0);
     }  // units
+    if (xpipe) { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+    x_pre = false; x_buf = 0;
     trace(t, 11);
     if (tid == 0) { s_ctr[1] = 0; s_ctr[2] = 0; }      // queues of phases B and C2 (nobody is in them now)
 #ifndef BF_DYNAMIC_CHUNKS
@@ -1184,14 +1255,15 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     {
       // block roots of this CTA: a warp folds the 4 bt units of a block (lane = unit, butterfly of merges, adjacent first)
       const int ub = 4 * a.bt;
-      const int nblk_cta = (tile1 - tile0 + a.bt - 1) / a.bt;
+      const int nblk_cta = (ntile_cta + a.bt - 1) / a.bt;
       for (int bl = warp; bl < nblk_cta; bl += CW) {
-        const int lu0 = cta_base / 512 + bl * ub;
+        const int gb = strided ? bl * (int)gridDim.x + (int)blockIdx.x : tile0 / a.bt + bl;      // block of the rank
+        const int lu0 = gb * ub;
         OnlineAcc<DX> v;
         v.init();
         if (lane < ub && lu0 + lane < a.nunits) v.load(a.upart + lu0 + lane);
         v.warp_tree_reduce();
-        if (lane == 0) v.store(a.lroot + tile0 / a.bt + bl);
+        if (lane == 0) v.store(a.lroot + gb);
       }
       __syncthreads();
       // the LAST CTA of this rank out of the phase (ticket) folds the rank's block roots once, before the grid leaves the
@@ -1262,7 +1334,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       float4 l4[4], wp4[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int base = cta_base + 128 * (qb + j) + lane * 4;
+        const int base = pbase(qb + j) + lane * 4;
         l4[j] = *reinterpret_cast<const float4*>(a.LL + base);
         wp4[j] = make_float4(invN, invN, invN, invN);
         if (!w_uni && w_vec && base + 3 < N) wp4[j] = *reinterpret_cast<const float4*>(a.W + base);
@@ -1273,7 +1345,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int q = qb + j, base = cta_base + 128 * q + lane * 4;
+        const int q = qb + j, base = pbase(q) + lane * 4;
         const float ll[4] = {l4[j].x, l4[j].y, l4[j].z, l4[j].w}, wp[4] = {wp4[j].x, wp4[j].y, wp4[j].z, wp4[j].w};
         float v[4];
 #pragma unroll
@@ -1307,7 +1379,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     }
     if (a.phases & PF_PH_B) {
     __syncthreads();
-    for (int i = tid; i < tile1 - tile0; i += NT) {   // tile sums: the top log2(TW) levels of the tile's tree
+    for (int i = tid; i < ntile_cta; i += NT) {       // tile sums: the top log2(TW) levels of the tile's tree
       float y16[TW];
 #pragma unroll
       for (int k = 0; k < TW; ++k) y16[k] = s_wsum[i * TW + k];
@@ -1315,7 +1387,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       for (int w = TW / 2; w >= 1; w >>= 1)
 #pragma unroll
         for (int k = 0; k < w; ++k) y16[k] = __fadd_rn(y16[2 * k], y16[2 * k + 1]);
-      const int gi = a.tile_off + tile0 + i;
+      const int gi = a.tile_off + tile_of(i);
       a.tilesum[gi] = y16[0];
       a.V[gi] = s_v0[i * TW];
       if (p2p) {
@@ -1340,7 +1412,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       // C-only launch (nccl transport): phase B ran in ANOTHER launch, whose shared memory is gone -- rebuild the chunk tree
       // sums and first weights from the normalised weights it left in E (same additions, same bits)
       for (int q = warp; q < nchunk_cta; q += CW) {
-        const float4 w4 = *reinterpret_cast<const float4*>(a.E + cta_base + 128 * q + lane * 4);
+        const float4 w4 = *reinterpret_cast<const float4*>(a.E + pbase(q) + lane * 4);
         const float v[4] = {w4.x, w4.y, w4.z, w4.w};
         const float cs = chunk_tree_sum(v);
         if (lane == 0) { s_wsum[q] = cs; s_v0[q] = v[0]; }
@@ -1374,8 +1446,8 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     if (use_tau) {
       // clamp interval of each owned tile from the bisection levels above it (half-widths N/2 .. TILE); the probe
       // value of a node whose middle is the first boundary of tile m is cdf[m*TILE] = Etile[m] + w[m*TILE]
-      for (int i = tid; i < tile1 - tile0; i += NT) {
-        const int tile = a.tile_off + tile0 + i;
+      for (int i = tid; i < ntile_cta; i += NT) {
+        const int tile = a.tile_off + tile_of(i);
         const int jt = tile * TILE;                              // global boundary index
         float lo = -INFINITY, hi = INFINITY;
         if (jt < Ng) {
@@ -1396,11 +1468,11 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       float4 w4[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)        // the weights phase B left here
-        w4[j] = *reinterpret_cast<const float4*>(a.E + cta_base + 128 * (qb + j) + lane * 4);
+        w4[j] = *reinterpret_cast<const float4*>(a.E + pbase(qb + j) + lane * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int q = qb + j, tl = q / TW, wpos = q % TW, tile = a.tile_off + tile0 + tl;
-        const int base = cta_base + 128 * q + lane * 4;
+        const int q = qb + j, tl = q / TW, wpos = q % TW, tile = a.tile_off + tile_of(tl);
+        const int base = pbase(q) + lane * 4;
         float e[4], tau[4];
         const float v[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};
         float4 out;
@@ -1442,7 +1514,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   xp_stage = xpf_peers;
   if (gather) begin_gather(T - 1);
   for (int q = next_chunk(0); q < nchunk_valid; q = next_chunk(0)) {
-    const int base = cta_base + 128 * q + lane * 4;
+    const int base = pbase(q) + lane * 4;
     const int nv = max(0, min(4, N - base));
     int anc[4] = {a.goff + base, a.goff + base + 1, a.goff + base + 2, a.goff + base + 3};
     int xs_lo = -1;
@@ -1454,7 +1526,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         const int i = base + k;
         float x[DX];
         if (SH && xs_lo >= 0) {
-          const float* xs = s_xst + ((size_t)warp * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
+          const float* xs = s_xst + ((size_t)(2 * warp + x_buf) * PF_FUSED_XCAP + (anc[k] - xs_lo)) * DX;
 #pragma unroll
           for (int c = 0; c < DX; ++c) x[c] = xs[c];
         } else if (gather) load_prev(anc[k], x_prev, xpf_peers, x);

@@ -70,20 +70,26 @@ def main():
             print(f"sharded {name}: N={N} over {world} ranks, T={T}, {n_res} resampling steps: ok", flush=True)
         dist.barrier()
     # Philox mode: the random numbers are indexed by GLOBAL particle, so the filter does not depend on the sharding
+    # (2^21 per rank: 1024 tiles over 147 CTAs -- every CTA owns several blocks dealt round the grid, pf_fused.cuh "Ownership";
+    #  summaries only: the lean sharded instantiation; with ancestors: the general one)
     c = case("bot2")
-    T, N = 40, 16384 * world
-    _, ys = c.simulate(T, 9)
-    u = c.inputs(T)
-    eng = ShardedParticleFilterEngine(c.host_model(), N, 1.0, "systematic", seed=11, device=local)
-    out = eng.run_host(ys, inputs=u, outputs=("means", "log_likelihood"))
-    eng.close()
-    if rank == 0:
-        one = ParticleFilterEngine(c.host_model(), N, 1, 1.0, "systematic", "streamed", 11, local)
-        o1 = one.run_host(ys, inputs=u, outputs=("means", "log_likelihood"))
-        one.close()
-        _same_filter(out, o1, "philox")
-        print("sharded philox run equals the one-GPU run: ok", flush=True)
-    dist.barrier()
+    for T, N, outs in ((40, 16384 * world, ("means", "log_likelihood")), (12, (1 << 21) * world, ("means", "log_likelihood")),
+                       (6, (1 << 21) * world, ("means", "log_likelihood", "resampled", "ancestors"))):
+        _, ys = c.simulate(T, 9)
+        u = c.inputs(T)
+        eng = ShardedParticleFilterEngine(c.host_model(), N, 1.0, "systematic", seed=11, device=local)
+        out = eng.run_host(ys, inputs=u, outputs=outs)
+        eng.close()
+        if rank == 0:
+            one = ParticleFilterEngine(c.host_model(), N, 1, 1.0, "systematic", "streamed", 11, local)
+            o1 = one.run_host(ys, inputs=u, outputs=outs)
+            one.close()
+            for k in outs:
+                ref = np.asarray(o1[k])
+                if k == "ancestors": ref = ref[:, :, :N // world]          # rank 0 holds its own slots (global ancestor indices)
+                assert np.array_equal(np.asarray(out[k]), ref), f"philox N={N}: {k} differs from the one-GPU filter"
+            print(f"sharded philox run N={N} equals the one-GPU run: ok", flush=True)
+        dist.barrier()
     dist.destroy_process_group()
 
 
