@@ -686,6 +686,9 @@ struct PfRun {
         a.epoch = reinterpret_cast<unsigned long long*>(xb + 256);
         a.err = reinterpret_cast<int*>(xb + 264);
         a.xstage = xstage ? 1 : 0;
+        // BF_SHARD_XPIPE=1: fetch the remote ancestor rows one chunk ahead with cp.async.  Measured on 2 GPUs: 277 vs 271 us per
+        // step without it (the NVLink round trip of a chunk is already hidden by the other 31 warps), so it is off by default.
+        { const char* penv = getenv("BF_SHARD_XPIPE"); a.xpipe = (penv && penv[0] == '1') ? 1 : 0; }
         // Ownership of the blocks (bt tiles) is dealt round the CTAs (pf_fused.cuh, "Ownership"); BF_SHARD_STRIDED=0 keeps the
         // contiguous split.  The thresholds of each window block's ancestor bracket are staged here (BF_SHARD_STAGE_TAU=0: off).
         const char* senv = getenv("BF_SHARD_STRIDED");

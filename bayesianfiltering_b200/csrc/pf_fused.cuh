@@ -110,6 +110,7 @@ struct PfFusedArgs {
   // units then never wait for an NVLink round trip (they cost the boundary CTAs 70 % when fetched chunk by chunk).
   float* stg_tau;                            // [gridDim.x][stg_blocks][stg_cap] staged thresholds of the ancestor brackets (sharded)
   int stg_cap, stg_blocks;
+  int xpipe;                                 // sharded: prefetch the remote ancestor rows one chunk ahead (cp.async); off by default
   int strided, log2bt;                       // sharded: CTA c owns the blocks (bt tiles) c, c + grid, c + 2 grid, ... of its rank
   char* const* xchg_peers;                   // device table [world] of the exchange buffers (own entry = own buffer)
   unsigned long long* flags;                 // own flags [3][8]
@@ -1113,7 +1114,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       }
     };
     const int nunit_cta = nchunk_cta / 4;
-    const bool xpipe = XPIPE && gather && use_win && a.xstage != 0;
+    const bool xpipe = XPIPE && gather && use_win && a.xstage != 0 && a.xpipe != 0;
     int un = next_chunk(0);
     x_pre = xpipe; x_buf = 0;
     if (xpipe) xprefetch(un < nunit_cta ? 4 * un : -1, 0);
