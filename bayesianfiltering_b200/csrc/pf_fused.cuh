@@ -1452,10 +1452,26 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         const int jt = tile * TILE;                              // global boundary index
         float lo = -INFINITY, hi = INFINITY;
         if (jt < Ng) {
-          for (int s = Ng >> 1; s >= TILE; s >>= 1) {
-            const int mid = (jt & ~(2 * s - 1)) + s, m = mid / TILE;
-            const float c = clampf(__fadd_rn(__ldcg(&a.Etile[m]), __ldcg(&a.V[m])), lo, hi);
-            if (jt < mid) hi = c; else lo = c;
+          // the probes do not depend on the clamps: fetch them all first (one L2 latency, not one per level)
+          constexpr int MAXLV = 20;                              // N up to 2^31 / tile of 2^11
+          float cv[MAXLV];
+#pragma unroll
+          for (int l = 0; l < MAXLV; ++l) {
+            const int s = (Ng >> 1) >> l;
+            cv[l] = 0.0f;
+            if (s >= TILE) {
+              const int m = ((jt & ~(2 * s - 1)) + s) / TILE;
+              cv[l] = __fadd_rn(__ldcg(&a.Etile[m]), __ldcg(&a.V[m]));
+            }
+          }
+#pragma unroll
+          for (int l = 0; l < MAXLV; ++l) {
+            const int s = (Ng >> 1) >> l;
+            if (s >= TILE) {
+              const int mid = (jt & ~(2 * s - 1)) + s;
+              const float c = clampf(cv[l], lo, hi);
+              if (jt < mid) hi = c; else lo = c;
+            }
           }
         }
         s_meta_f[2 * i] = lo; s_meta_f[2 * i + 1] = hi;
