@@ -63,5 +63,7 @@ def l96(d=40):
 
 
 def lg8():
-    A = 0.8 * np.eye(8) + 0.05 * np.eye(8, k=1)
-    return Workload("lg8", zoo.linear_gaussian(A, 0.5 * np.eye(8)), np.zeros(8), np.eye(8), np.eye(8), 0.1 * np.eye(8))
+    A, H = 0.8 * np.eye(8) + 0.05 * np.eye(8, k=1), 0.5 * np.eye(8)
+    w = Workload("lg8", zoo.linear_gaussian(A, H), np.zeros(8), np.eye(8), np.eye(8), 0.1 * np.eye(8))
+    w.A, w.H = A, H                                   # (for the exact Kalman yardstick of the sweep)
+    return w

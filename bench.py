@@ -17,6 +17,8 @@ Beside it, in the same JSON line:
   "gsf"      configs[1]: Gaussian-sum EKF filter, UNGM, M = 100 x 1024 trials x T = 500 per GPU
   "gsf_l96"  configs[3]: Gaussian-sum filter on Lorenz-96 d = 40, M = 256 x 512 trials per GPU (4096 over 8), T = 100
   "fp32_peak_tflops"  measured FFMA throughput (bf_measure_fp32_peak), the denominator of the fp32_frac entries
+  "c1", "c5" configs[0] (UNGM, N = 1000, T = 100 through the reference call) and one point of configs[4] (linear-Gaussian d = 8,
+             N = 2^22, checked against the exact Kalman log-likelihood computed here in float64)
 Keys beyond the base contract: roofline, cpu_baseline, e2e, gpu_launches, clocks.
 
 Synthetic data comes from the package's own generator (NonlinearSSM.sample -> bf_ssm_sample); the oracle (oracle/) is
@@ -45,8 +47,8 @@ BYTES_PER_PARTICLE_STEP = 84     # 4*(4*dx + 5) for dx=4, in-kernel
 # DRAM bytes the fused kernel actually moves per particle-step, from the ncu --set full capture named in MOVED_SOURCE
 # (dram__bytes_read + dram__bytes_write of one launch / (N*T)).  Below the algorithmic figure because the resampled copy
 # of the particles is never materialised (the gather is fused into the next step's propagate).  NOT measured in this run.
-MOVED_BYTES_PER_PARTICLE_STEP = 52.3
-MOVED_SOURCE = "profiles/r2_j_pf_fused_T40_ncu.txt"
+MOVED_BYTES_PER_PARTICLE_STEP = 51.4
+MOVED_SOURCE = "profiles/r2_o_pf_fused_T40_ncu.txt"
 GSF_BYTES = 20                   # 4*(2 dx + 2 dx^2 + 1), dx = 1: the five posterior fields
 GSF_FLOPS = 60                   # ~60 flop per component-step incl. exp / log
 L96_BYTES = 8 * (40 + 1600 + 1) + 4 * (1 + 40.0 / 256)     # carry read + write, weights + mixture mean out: ~13.1 KB
@@ -131,15 +133,8 @@ def _cpu_worker(args):
         threadpool_limits(limits=1)
     except Exception:
         pass
-    from oracle import pf as opf
-    from tests.parity_cases import case
-    c = case("bot2")
-    _, ys = c.simulate(T, 1000 + seed)
-    u = c.inputs(T)
-    x0, noise, ru = c.pf_randomness(T, N, 2000 + seed, "systematic")
-    t0 = time.perf_counter()
-    o = opf.bootstrap_particle_filter(c.omodel, ys, u, x0, noise, ru, c.r0, c.R, 1.0, "systematic", keep_trajectory=False)
-    return time.perf_counter() - t0, float(o["marginal_loglik"])
+    from oracle.bench_workload import run_bot          # (the one place bench.py executes oracle/: the CPU arm)
+    return run_bot(seed, N, T)
 
 
 def cpu_throughput(seconds_target=12.0):
@@ -196,6 +191,24 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def _kalman_loglik(A, H, Q, R, m0, P0, ys):
+    """Exact marginal log-likelihood of a linear-Gaussian SSM, float64 (update on y_t, then predict -- the order of the
+    reference's filters): the yardstick of configs[4]."""
+    Q, R, P = (np.asarray(a, np.float64) for a in (Q, R, P0))
+    m = np.asarray(m0, np.float64)
+    ll = 0.0
+    for y in np.asarray(ys, np.float64):
+        S = H @ P @ H.T + R
+        d = y - H @ m
+        L = np.linalg.cholesky(S)
+        z = np.linalg.solve(L, d)
+        ll += -0.5 * z @ z - np.log(np.diag(L)).sum() - 0.5 * len(y) * np.log(2 * np.pi)
+        K = np.linalg.solve(S, H @ P).T
+        m, P = m + K @ d, P - K @ S @ K.T
+        m, P = A @ m, A @ P @ A.T + Q
+    return float(ll)
+
+
 def run_ours(args):
     import ctypes as C
     import torch
@@ -404,6 +417,46 @@ def run_ours(args):
                             "flops_per_component_step_executed": L96_FLOPS_EXECUTED, "flops_per_component_step_dense_survey": L96_FLOPS_DENSE,
                             "note": "state streamed through HBM once per fused update+predict; the Jacobians are banded and applied as such"}}
 
+    # ---- configs[0] and configs[4] through the same entry points (rank 0; small, latency-bound / validation runs)
+    c1 = c5 = None
+    if rank == 0:
+        w1 = workloads.ungm()
+        _, y1 = w1.sample(100, 3)
+        p1, u1 = w1.params_bpf(), w1.inputs(100)
+        call1 = lambda: gf.bootstrap_particle_filter(p1, y1, 1000, PRNGKey(1), u1, 0.5)
+        call1(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5): call1()
+        torch.cuda.synchronize()
+        ms1 = (time.perf_counter() - t0) / 5 * 1e3
+        launches += 12
+        c1 = {"metric": METRIC, "value": 1000 * 100 / (ms1 * 1e-3), "unit": UNIT, "ms_per_call": ms1,
+              "config": {"workload": "configs[0]: BPF UNGM N=1000 T=100, multinomial (the reference's default call), host arrays in, "
+                                     "weights [N,T] + particles [N,T,dx] back: inference.bootstrap_particle_filter(params, emissions, 1000, key, inputs, 0.5)"},
+              "note": "one CTA, state in shared memory (k_pf_resident): latency-bound by design, no roofline"}
+        w5 = workloads.lg8()
+        _, y5 = w5.sample(100, 9)
+        exact = _kalman_loglik(np.asarray(w5.A, np.float64), np.asarray(w5.H, np.float64), w5.Q, w5.R, w5.m0, w5.P0, y5)
+        y5_d = torch.from_numpy(y5).to(dev)
+        N5 = 1 << 22
+        vals, ms5 = [], []
+        for seed in range(3):
+            e5 = ParticleFilterEngine(w5.host_model(), N5, 1, 0.5, "systematic", "auto", 100 + seed, local)
+            e5.run(y5_d, outputs=("log_likelihood",))
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            o5 = e5.run(y5_d, outputs=("log_likelihood",))
+            ev1.record(); torch.cuda.synchronize()
+            ms5.append(ev0.elapsed_time(ev1)); vals.append(float(o5["log_likelihood"].double().sum().item()))
+            e5.close()
+            launches += 4
+        c5 = {"metric": METRIC, "value": N5 * 100 / (float(np.median(ms5)) * 1e-3), "unit": UNIT, "ms_per_run": float(np.median(ms5)),
+              "config": {"workload": "configs[4] (one point of the sweep; profiles/r2_m_c5_sweep_lg8.jsonl has N = 2^10 .. 2^28): BPF on a "
+                                     "linear-Gaussian SSM d=8, N=2^22, T=100, systematic, ess_threshold=0.5, three seeds"},
+              "logZ_exact_kalman_f64": exact, "logZ_pf": vals, "abs_err_mean": float(np.mean(np.abs(np.array(vals) - exact)))}
+        if not (c5["abs_err_mean"] < 2.0):
+            raise SystemExit(f"configs[4]: particle-filter log-likelihood {vals} is not consistent with the exact Kalman filter {exact}")
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, sample = cpu_throughput()
@@ -429,7 +482,7 @@ def run_ours(args):
                              "kernel": "k_pf_fused (persistent cooperative kernel, all T steps in one launch)",
                              "phase_us_per_time_step": phases},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-                "fp32_peak_tflops": fp32_peak, "sharded": sharded, "gsf": gsf, "gsf_l96": gsf_l96}
+                "fp32_peak_tflops": fp32_peak, "sharded": sharded, "gsf": gsf, "gsf_l96": gsf_l96, "c1": c1, "c5": c5}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
