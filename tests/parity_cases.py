@@ -102,8 +102,8 @@ def case(name):
         Q = 0.2 * np.eye(4) + 0.05
         R = np.array([[0.3, 0.1], [0.1, 0.2]])
         return Case("lg42", om.LG(A, H), lambda: _zoo().linear_gaussian(A, H), np.ones(4), np.eye(4), Q, R)
-    if name in ("l96", "l96s"):   # BASELINE configs[3]: Lorenz-96 d=40 (l96s: d=8 for quick checks), Q = 0.1 I
-        d = 40 if name == "l96" else 8
+    if name in ("l96", "l96s", "l96_6", "l96_10"):   # BASELINE configs[3]: Lorenz-96 d=40 (l96s: d=8 for quick checks), Q = 0.1 I
+        d = {"l96": 40, "l96s": 8, "l96_6": 6, "l96_10": 10}[name]   # d = 6, 10: workspace sizes that are not multiples of 16 bytes
         return Case(name, om.L96(d), lambda: _zoo().lorenz96(d), 8.0 + 0.5 * np.sin(np.arange(d)), 0.5 * np.eye(d), 0.1 * np.eye(d),
                     0.5 * np.eye(d // 2))
     if name == "sin1d":     # Experiment A / ICASSP toy

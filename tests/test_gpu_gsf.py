@@ -31,6 +31,7 @@ def _engine(c, M, B=1):
     ("bot1", 20, 8), ("bot2", 20, 5), ("l63", 20, 6), ("lg3", 20, 4), ("lg42", 20, 7), ("lg8", 12, 3),
     ("sin1d", 20, 5), ("sin3d", 4, 40),      # sin3d: the fp32 EKF loses positive definiteness at t=4
     ("l96s", 12, 9), ("l96", 6, 5),          # large-state kernel (gsf_large.cuh): Lorenz-96 d=8 and BASELINE configs[3]'s d=40
+    ("l96_6", 8, 13), ("l96_10", 8, 13),     # d = 2 mod 4: every other warp's workspace would be misaligned without the padding
 ])
 def test_gsf_stepwise_parity(name, T, M):
     """Each step from the ORACLE's carry (weights, predicted means, predicted covariances): one `_step`

@@ -102,3 +102,34 @@ def test_time_varying_covariances_are_routed_like_get_params():
         zoo.host_model_from_params(p._replace(dynamics_noise_covariance=Qt))
     with pytest.raises(NotImplementedError):
         zoo.host_model_from_params(p._replace(dynamics_noise_bias=np.zeros((T, 3), np.float32)), time_varying=True)
+
+
+def test_bench_cpu_arm_and_yardsticks():
+    """bench.py's host-side pieces: the CPU arm's workload (oracle/bench_workload.py) is the `bot2` parity case with the same
+    draws; the Kalman yardstick of configs[4] equals the oracle's exact filter; the product never imports oracle/ or tests/."""
+    import ast, os
+    import bench
+    from oracle import bench_workload, gsf as ogsf, pf as opf
+    from tests.parity_cases import case
+    secs, ll = bench_workload.run_bot(3, 1 << 10, 6)
+    c = case("bot2")
+    _, ys = c.simulate(6, 1003)
+    x0, noise, ru = c.pf_randomness(6, 1 << 10, 2003, "systematic")
+    o = opf.bootstrap_particle_filter(c.omodel, ys, c.inputs(6), x0, noise, ru, c.r0, c.R, 1.0, "systematic", keep_trajectory=False)
+    assert secs > 0 and ll == float(o["marginal_loglik"])
+    c = case("lg8")
+    _, ys = c.simulate(25, 9)
+    _, _, inc = ogsf.kalman_filter_exact(c.omodel.A, c.omodel.H, c.Q, c.R, c.m0, c.P0, ys)
+    mine = bench._kalman_loglik(np.asarray(c.omodel.A, np.float64), np.asarray(c.omodel.H, np.float64), c.Q, c.R, c.m0, c.P0, ys)
+    assert abs(mine - float(inc.sum())) < 1e-9 * abs(mine)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "bayesianfiltering_b200")
+    for fn in [os.path.join(pkg, f) for f in os.listdir(pkg) if f.endswith(".py")] + [os.path.join(root, "bench.py")]:
+        tree = ast.parse(open(fn).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import): mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom): mods = [node.module or ""]
+            for m in mods:
+                assert not m.startswith("tests"), f"{fn} imports {m}"
+                if fn.startswith(pkg): assert not m.startswith("oracle"), f"{fn} imports {m}"
