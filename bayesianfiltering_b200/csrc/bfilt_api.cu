@@ -555,8 +555,15 @@ struct PfRun {
     int grid = 1, tpc = ntiles;
     size_t smem = 0;
     const int stage_ts = (ntiles_scan + 1 <= 16384) ? ((ntiles_scan + 3) & ~3) + 256 : 0;   // tile sums staged in shared memory by C1 (+ scratch)
-    auto smem_for = [&](int t) { return (size_t)((3 * TW + 3) * t + 2 + std::max(NW * PF_FUSED_WINCAP, stage_ts + nchunk + 1 + NW + 8) +
-                                                (xstage ? 2 * NW * PF_FUSED_XCAP * DX : 0) + 8) * sizeof(float); };
+    // every CTA scans the tile sums itself (pf_fused.cuh, c1_all): the prefixes live behind the window area -- on top of the
+    // particle staging buffers of a sharded filter, which are idle in phase C.  BF_PF_C1_ALL=0: CTA 0 scans, then a grid barrier.
+    const char* cenv1 = getenv("BF_PF_C1_ALL");
+    const bool c1_all = stage_ts != 0 && !(cenv1 && cenv1[0] == '0');
+    const int win_floats = std::max(NW * PF_FUSED_WINCAP, stage_ts + nchunk + 1 + NW + 8);
+    const int xst_floats = xstage ? 2 * NW * PF_FUSED_XCAP * DX : 0;
+    const int et_off = (win_floats + 3) & ~3;
+    const int tail_floats = c1_all ? std::max(win_floats + xst_floats, et_off + ntiles_scan + 8) : win_floats + xst_floats;
+    auto smem_for = [&](int t) { return (size_t)((3 * TW + 3) * t + 2 + tail_floats + 8) * sizeof(float); };
     for (int round = 0; round < 3; ++round) {
       smem = smem_for(round == 0 ? 64 : tpc);
       if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -664,6 +671,7 @@ struct PfRun {
         }
       }
       a.stage_ts = stage_ts ? 1 : 0;
+      a.c1_all = c1_all ? 1 : 0; a.et_off = et_off;
       {
         char* pb = (sl ? sl->partials : h->partials).as<char>();
         a.upart = reinterpret_cast<PfPartial*>(pb);

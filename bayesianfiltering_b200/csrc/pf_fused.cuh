@@ -95,6 +95,7 @@ struct PfFusedArgs {
   int* cell_lb;                              // [Ng + 1] one GPU, multinomial: lower bound of tau at the cell edges c * total / Ng, or NULL
   int coarse_log2;                           // log2 of its length, or -1: off
   int stage_ts;                              // C1 stages the tile sums in shared memory first (the host sized it for that)
+  int c1_all, et_off;                        // every CTA scans the tile sums itself into shared memory at s_win + et_off (no barrier after C1)
   int tile_off, ntiles_g;                    // global index of local tile 0; tiles of the whole filter (tilesum/Etile/V are global)
   int phases;                                // PF_PH_* mask; PF_PH_ALL = the whole run in one launch (world = 1)
   // device tables [world] (in global memory: indexing a kernel parameter dynamically would spill it to local memory)
@@ -511,6 +512,9 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
   int* s_lo = reinterpret_cast<int*>(s_meta_f + 2 * tpc);       // [(TW+1)*tpc + 2] tau window start of each chunk (+ one end per window block)
   float* s_win = s_dyn + (((3 * TW + 3) * tpc + 2 + 3) & ~3);   // 16-byte aligned (vector accesses to the histogram)
   float* s_xst = s_win + CW * WINCAP;                           // [CW][2][XCAP*DX], sharded filters only (host sizes it)
+  float* s_et = s_win + a.et_off;                               // [ntiles_g + 1] tile prefixes of the step (c1_all; aliases s_xst, idle in phase C)
+  const bool c1_all = a.c1_all != 0;
+  auto etile = [&](int i) -> float { return c1_all ? s_et[i] : __ldcg(&a.Etile[i]); };
   // the particles of a remote ancestor window are fetched ONE CHUNK AHEAD with cp.async (16-byte rows): the NVLink round
   // trip (3-10 us under load) overlaps the propagation of the chunk in hand instead of stalling the warp
   constexpr bool XPIPE = SH && (DX == 4);
@@ -1421,6 +1425,18 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
       __syncthreads();
     }
     // ------------------------------------------------------------------ phase C1 (CTA 0; every rank of a sharded filter)
+    if (c1_all) {
+      // EVERY CTA scans the tile sums itself, into its own shared memory: the same tree, the same bits, and the grid does not
+      // meet again between C1 and C2 (one CTA scanning while 146 wait, then a barrier: ~10 us per step).  CTA 0 keeps the
+      // global copy current (the sharded filter's ancestor brackets and E[Ng] read it in the next step).
+      for (int i = tid; i < a.ntiles_g; i += NT) s_win[i] = __ldcg(a.tilesum + i);
+      __syncthreads();
+      staged_tile_scan<CW>(s_win, s_et, a.ntiles_g, s_win + ((a.ntiles_g + 3) & ~3));
+      __syncthreads();
+      if (blockIdx.x == 0) for (int i = tid; i <= a.ntiles_g; i += NT) a.Etile[i] = s_et[i];
+      trace(t, 4);
+      trace(t, 5);
+    } else {
     if (blockIdx.x == 0) {
       if (a.stage_ts) {                                // all the loads in flight at once: one L2 latency instead of ten
         for (int i = tid; i < a.ntiles_g; i += NT) s_win[i] = __ldcg(a.tilesum + i);
@@ -1433,6 +1449,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
     trace(t, 4);
     grid.sync();
     trace(t, 5);
+    }
     lap(2);
 
     // ------------------------------------------------------------------ phase C2
@@ -1461,7 +1478,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
             cv[l] = 0.0f;
             if (s >= TILE) {
               const int m = ((jt & ~(2 * s - 1)) + s) / TILE;
-              cv[l] = __fadd_rn(__ldcg(&a.Etile[m]), __ldcg(&a.V[m]));
+              cv[l] = __fadd_rn(etile(m), __ldcg(&a.V[m]));
             }
           }
 #pragma unroll
@@ -1476,7 +1493,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         }
         s_meta_f[2 * i] = lo; s_meta_f[2 * i + 1] = hi;
         if (c2_pre)
-          tile_levels<TW>(s_wsum + i * TW, s_v0 + i * TW, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]), lo, hi, min(TILE, Ng),
+          tile_levels<TW>(s_wsum + i * TW, s_v0 + i * TW, etile(tile), etile(tile + 1), lo, hi, min(TILE, Ng),
                           s_cE + i * (TW + 1), s_clo + i * TW, s_chi + i * TW);
       }
       __syncthreads();
@@ -1500,11 +1517,11 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
           chunk_downsweep<true>(v, s01, recv, ce[0], ce[1], s_clo[q], s_chi[q], min(TILE, Ng), e, tau);
           out = make_float4(tau[0], tau[1], tau[2], tau[3]);
         } else if (use_tau) {
-          chunk_scan<TW, true>(v, wpos, s_wsum + tl * TW, s_v0 + tl * TW, __ldcg(&a.Etile[tile]), __ldcg(&a.Etile[tile + 1]),
+          chunk_scan<TW, true>(v, wpos, s_wsum + tl * TW, s_v0 + tl * TW, etile(tile), etile(tile + 1),
                                    s_meta_f[2 * tl], s_meta_f[2 * tl + 1], min(TILE, Ng), e, tau);
           out = make_float4(tau[0], tau[1], tau[2], tau[3]);
         } else {
-          chunk_scan<TW, false>(v, wpos, s_wsum + tl * TW, s_v0 + tl * TW, __ldcg(&a.Etile[tile]), 0.0f, 0.0f, 0.0f, 0, e, tau);
+          chunk_scan<TW, false>(v, wpos, s_wsum + tl * TW, s_v0 + tl * TW, etile(tile), 0.0f, 0.0f, 0.0f, 0, e, tau);
           out = make_float4(e[0], e[1], e[2], e[3]);
         }
 #pragma unroll
@@ -1513,7 +1530,7 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
         if (!SH && a.coarse_log2 >= 0 && wpos == TW - 1 && lane == 31 && base < N) a.tau_tile[tile] = tau[3];
       }
     }
-    if (SH && blockIdx.x == 0 && tid == 0) *a.total = __ldcg(&a.Etile[a.ntiles_g - 1]);   // E[Ng]
+    if (SH && blockIdx.x == 0 && tid == 0) *a.total = etile(a.ntiles_g - 1);   // E[Ng]
     trace(t, 6);
     if (all_phases) grid.sync();                       // (gpu-scope fence: tau and the particles of this step are in this GPU's L2,
                                                        //  which is where the peers' NVLink reads are served from)
