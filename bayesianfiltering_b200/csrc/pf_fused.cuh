@@ -31,7 +31,13 @@
 // lower-bound search returns the reference's ancestors bit for bit.  Systematic positions are sorted: a chunk of
 // 128 slots owns a window of tau (found by one bisection per chunk boundary at the start of the phase) and its
 // answers are the running count of window entries below each slot's position (histogram + warp prefix sum, see
-// ancestors4); multinomial positions bisect tau in global memory.  Other N keep the literal bisection on E.
+// ancestors4); multinomial positions look their cell up in a table of lower bounds rebuilt every step (begin_gather) or,
+// for small N, bisect tau in two levels.  Other N keep the literal bisection on E.
+//
+// Compile-time experiment switches (never set in the product build, csrc/build.sh): BF_EXP_TRACE records a per-CTA timeline of
+// one step (profiles/trace_summary.py); BF_EXP_NOSEARCH / NOLL / NOUNITRED and BF_EXP_MN_NOBUILD / NOLOOKUP / XONLY remove one
+// piece of phase A to time the rest -- they compute WRONG filters by construction (profiles/README.md says which numbers came
+// from them).
 #pragma once
 #include <cooperative_groups.h>
 #include "pf_kernels.cuh"
@@ -45,7 +51,7 @@ namespace cg = cooperative_groups;
 #define PF_FUSED_WARPS_LARGE 16             // states with dx > 4: 16 warps at 128 registers per thread
 #define PF_FUSED_WINCAP 256                 // floats of shared memory per warp for the histogram / tile tables / scan scratch
 #define PF_FUSED_XCAP 160                   // particles a warp of a SHARDED filter stages when a chunk's ancestors live on a peer (two buffers)
-#define PF_FUSED_MAXWB 32          // window blocks (runs of consecutive owned tiles) per CTA, sharded filter with dealt blocks
+#define PF_FUSED_MAXWB 32                    // window blocks (runs of consecutive owned tiles) per CTA, sharded filter with dealt blocks
 
 struct PfFusedArgs {
   int N, T, t_offset, trial, B;
@@ -971,10 +977,13 @@ k_pf_fused(const __grid_constant__ ModelConst mc, const __grid_constant__ PfFuse
           return;
 #endif
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { lo[k] = a.cell_lb[c[k]]; hi[k] = a.cell_lb[c[k] + 1]; }
+          for (int k = 0; k < 4; ++k) {                  // (r == the cell's lower edge: its entry is the answer, the next one is not read)
+            lo[k] = a.cell_lb[c[k]];
+            hi[k] = (wq[k] == (float)c[k]) ? 0 : a.cell_lb[c[k] + 1];
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            int pos = lo[k], len = (wq[k] == (float)c[k]) ? 0 : hi[k] - lo[k];     // r == the cell's lower edge: no search
+            int pos = lo[k], len = (wq[k] == (float)c[k]) ? 0 : hi[k] - lo[k];
             while (len > 0) {
               const int half = len >> 1;
               if (!(r[k] <= a.E[pos + half])) { pos += half + 1; len -= half + 1; } else len = half;
