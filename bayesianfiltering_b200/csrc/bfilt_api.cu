@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <memory>
 #include <algorithm>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -174,6 +175,9 @@ struct DevBuf {
   void* p = nullptr; size_t cap = 0; bool plain = false;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    // growing a buffer that has been handed out: work enqueued on a non-blocking caller stream may still read it, and the
+    // free below is ordered on the legacy stream only
+    if (p) cudaDeviceSynchronize();
     release();
     cudaError_t e = cudaMallocAsync(&p, bytes, (cudaStream_t)0);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);   // usable from any stream afterwards
@@ -182,6 +186,7 @@ struct DevBuf {
   }
   cudaError_t ensure_plain(size_t bytes) {         // cudaMalloc: CUDA IPC cannot export pool memory
     if (bytes <= cap) return cudaSuccess;
+    if (p) cudaDeviceSynchronize();
     release();
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e == cudaSuccess) { cap = bytes; plain = true; } else p = nullptr;
@@ -368,7 +373,7 @@ extern "C" int bf_pf_destroy(bf_pf_handle h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();              // as cudaFree would: nothing enqueued by this handle may still be running
   for (auto& sl : h->extra) {
-    DevBuf* bufs[] = {&sl.xa, &sl.xb, &sl.LL, &sl.E, &sl.tilesum, &sl.Etile, &sl.V, &sl.partials};
+    DevBuf* bufs[] = {&sl.xa, &sl.xb, &sl.LL, &sl.E, &sl.tilesum, &sl.Etile, &sl.V, &sl.partials, &sl.cells};
     for (DevBuf* bf : bufs) bf->release();
     if (sl.done) cudaEventDestroy(sl.done);
     if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -383,7 +388,8 @@ extern "C" int bf_pf_destroy(bf_pf_handle h) {
       for (int r = 0; r < h->world; ++r)
         if (r != h->rank && h->peer_ptr[k][r]) cudaIpcCloseMemHandle(h->peer_ptr[k][r]);
   DevBuf* all[] = {&h->carry_x, &h->carry_w, &h->carry_uniform, &h->carry_stats, &h->xa, &h->xb, &h->LL, &h->E, &h->anc,
-                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V, &h->peer_tab, &h->barrier_buf, &h->xchg, &h->stg_tau};
+                   &h->tilesum, &h->Etile, &h->partials, &h->counter, &h->stats, &h->phase_ns, &h->V, &h->cells, &h->peer_tab, &h->barrier_buf, &h->xchg,
+                   &h->stg_tau};
   for (DevBuf* b : all) b->release();
   for (DevBuf& b : h->hbuf) b.release();
   delete h;
@@ -991,7 +997,7 @@ extern "C" int bf_gsf_create(const bf_model_desc* model, const bf_gsf_config* cf
     }
     delete lch;
   }
-  if ((e = pool_setup(cfg->device)) != cudaSuccess) { delete h; return fail(BF_ECUDA, "memory pool setup: %s", cudaGetErrorString(e)); }
+  if ((e = pool_setup(cfg->device)) != cudaSuccess) { bf_gsf_destroy(h); return fail(BF_ECUDA, "memory pool setup: %s", cudaGetErrorString(e)); }
   h->nsm = 148;
   cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, cfg->device);
   const size_t bm = (size_t)cfg->num_trials * cfg->num_components, dx = h->mc.dx;
@@ -1468,9 +1474,9 @@ extern "C" int bf_ssm_sample(const bf_model_desc* model, int32_t B, int32_t T, c
     if (z0 || q_noise || r_noise || inputs) return fail(BF_EINVAL, "the Lorenz-96 generator draws its own noise and takes no inputs");
     const int dx = model->dx, dy = model->dy;
     if (dx < 4 || dx > GL_MAXDX || (dx & 1) || dy != dx / 2 || model->n_theta != 4) return fail(BF_EINVAL, "L96 needs even 4 <= dx <= %d, dy = dx/2", GL_MAXDX);
-    LargeConst* lch = new (std::nothrow) LargeConst();
+    std::unique_ptr<LargeConst> lch(new (std::nothrow) LargeConst());
     if (!lch) return fail(BF_ENOMEM, "out of host memory");
-    memset(lch, 0, sizeof *lch);
+    memset(lch.get(), 0, sizeof(LargeConst));
     lch->dx = dx; lch->dy = dy; lch->F = model->theta[0]; lch->dt = model->theta[1]; lch->c1 = model->theta[2]; lch->c2 = model->theta[3];
     for (int i = 0; i < dx; ++i) { lch->q0[i] = model->q0[i]; lch->qd[i] = model->Q[i * dx + i]; lch->m0[i] = model->m0[i]; }
     for (int i = 0; i < dy; ++i) { lch->r0[i] = model->r0[i]; lch->rd[i] = model->R[i * dy + i]; }
@@ -1483,10 +1489,9 @@ extern "C" int bf_ssm_sample(const bf_model_desc* model, int32_t B, int32_t T, c
     cudaStream_t s = (cudaStream_t)stream;
     char* dbuf;
     CUDA_OK(cudaMallocAsync((void**)&dbuf, sizeof(LargeConst) + L.size() * 4, s));
-    CUDA_OK(cudaMemcpyAsync(dbuf, lch, sizeof(LargeConst), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(dbuf, lch.get(), sizeof(LargeConst), cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(dbuf + sizeof(LargeConst), L.data(), L.size() * 4, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaStreamSynchronize(s));        // the host staging buffers go out of scope
-    delete lch;
     k_l96_sample<<<(B + 63) / 64, 64, 0, s>>>((const LargeConst*)dbuf, (const float*)(dbuf + sizeof(LargeConst)), B, T, seed, states, emissions);
     LAUNCH_OK();
     CUDA_OK(cudaFreeAsync(dbuf, s));
