@@ -125,7 +125,7 @@ static int build_model_const(const bf_model_desc* d, ModelConst* mc) {
       if (d->dx > 3) return fail(BF_ENOMODEL, "SIN1D needs dx <= 3"); break;
     case BF_MODEL_MSV: want_dx = d->dx; want_dq = d->dx; want_dy = d->dx; want_theta = 3 * d->dx + 1;
       if (d->dx > 3) return fail(BF_ENOMODEL, "MSV needs dx <= 3"); break;
-    case BF_MODEL_L96: return fail(BF_ENOMODEL, "L96 runs through the large-state path (not built in this library version)");
+    case BF_MODEL_L96: return fail(BF_ENOMODEL, "Lorenz-96 runs on the Gaussian-sum filter's large-state path only (bf_gsf_*, bf_ssm_sample)");
     default: return fail(BF_ENOMODEL, "unknown model_id %d", d->model_id);
   }
   if (d->dx != want_dx || d->dq != want_dq || d->dy != want_dy || d->dr != want_dy || d->n_theta != want_theta)

@@ -1,5 +1,6 @@
 """Unscented Gaussian-sum filter oracle (SURVEY section 8(f) rank 2 -- the next row after the hot path).
-TEST INFRASTRUCTURE ONLY; no kernel uses it yet.  PARITY UNPINNED like the rest of oracle/.
+TEST INFRASTRUCTURE ONLY: the checker of csrc/ugsf_kernels.cuh.  Pinned like the rest of oracle/: tests/test_ref_pin.py holds it
+to `tests/golden/ref_ugsf_*.npz`, outputs of the unmodified reference function run on the NumPy stand-in (oracle/refshim.py).
 
 Restates `gaussfiltax/inference.py`: `ParamsUKF` :41-49, `_ukf_predict_nonadditive` :146-174,
 `_ukf_condition_on_nonadditive` :198-224, `unscented_gaussian_sum_filter` :379-456 (its `_step` :407-440 is the

@@ -133,3 +133,28 @@ def test_bench_cpu_arm_and_yardsticks():
             for m in mods:
                 assert not m.startswith("tests"), f"{fn} imports {m}"
                 if fn.startswith(pkg): assert not m.startswith("oracle"), f"{fn} imports {m}"
+
+
+def test_model_classes_and_their_distribution_accessors():
+    # gaussfiltax/models.py:86-157 (NonlinearGaussianSSM) and :207-238 (NonlinearSSM): host-side carriers
+    from scipy.stats import multivariate_normal
+    g = models.NonlinearGaussianSSM(2, 1)
+    assert list(inspect.signature(models.NonlinearGaussianSSM.__init__).parameters)[1:] == ["state_dim", "emission_dim", "input_dim"]
+    assert g.emission_shape == (1,) and g.inputs_shape is None and g.input_dim == 0
+    P0 = np.array([[2.0, 0.3], [0.3, 1.0]], np.float32)
+    p = models.ParamsNLSSM(np.array([1.0, 2.0]), P0, lambda z, *u: 2.0 * np.asarray(z), np.zeros(2), 0.5 * np.eye(2),
+                           lambda z, *u: np.asarray(z)[:1], np.zeros(1), np.eye(1))
+    d0 = g.initial_distribution(p)
+    x = np.array([[0.5, 1.5], [2.0, 2.0]], np.float32)
+    np.testing.assert_allclose(d0.log_prob(x), multivariate_normal([1, 2], P0).logpdf(x), rtol=2e-6)
+    assert d0.sample(seed=PRNGKey(3)).shape == (2,) and d0.sample((4, 3), seed=PRNGKey(3)).shape == (4, 3, 2)
+    assert np.array_equal(d0.sample(5, seed=PRNGKey(3)), d0.sample((5,), seed=PRNGKey(3)))          # a key fixes the draw
+    s = d0.sample(200000, seed=PRNGKey(1))
+    np.testing.assert_allclose(s.mean(0), [1, 2], atol=2e-2); np.testing.assert_allclose(np.cov(s.T), P0, atol=3e-2)
+    t = g.transition_distribution(p, np.ones(2))
+    assert np.array_equal(t.mean(), [2.0, 2.0]) and np.array_equal(t.covariance(), 0.5 * np.eye(2, dtype=np.float32))
+    assert np.array_equal(g.emission_distribution(p, np.ones(2), inputs=0.0).mean(), [1.0])
+    n = models.NonlinearSSM(2, 2, 1, 1)
+    assert np.array_equal(n.initial_distribution(p).mean(), [1.0, 2.0]) and np.array_equal(n.transition_distribution(p, np.ones(2)).mean(), [2.0, 2.0])
+    with pytest.raises(ValueError):
+        models.MVN(np.zeros(2), np.eye(3))
