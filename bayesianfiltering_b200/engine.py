@@ -430,8 +430,9 @@ def optimal_resampling_device(weights, N, uniforms):
     u = uniforms.contiguous().float()
     idx = torch.empty(int(N), dtype=torch.int32, device=w.device)
     wo = torch.empty(int(N), dtype=torch.float32, device=w.device)
-    _lib.check(lib.bf_optimal_resampling(w.data_ptr(), w.numel(), int(N), u.data_ptr(), idx.data_ptr(), wo.data_ptr(),
-                                         torch.cuda.current_stream(w.device).cuda_stream))
+    with torch.cuda.device(w.device):         # the library launches on the current device
+        _lib.check(lib.bf_optimal_resampling(w.data_ptr(), w.numel(), int(N), u.data_ptr(), idx.data_ptr(), wo.data_ptr(),
+                                             torch.cuda.current_stream(w.device).cuda_stream))
     return idx, wo
 
 
@@ -441,7 +442,8 @@ def cumsum_canonical(w):
     lib = _lib.load()
     w = w.contiguous().float()
     out = torch.empty_like(w)
-    _lib.check(lib.bf_cumsum(w.data_ptr(), out.data_ptr(), w.numel(), torch.cuda.current_stream(w.device).cuda_stream))
+    with torch.cuda.device(w.device):
+        _lib.check(lib.bf_cumsum(w.data_ptr(), out.data_ptr(), w.numel(), torch.cuda.current_stream(w.device).cuda_stream))
     return out
 
 
@@ -454,6 +456,7 @@ def resample_ancestors(w, u, resampler="multinomial"):
     if resampler == "multinomial" and u.numel() != w.numel():
         raise ValueError("multinomial resampling needs one uniform per particle")
     anc = torch.empty(w.numel(), dtype=torch.int32, device=w.device)
-    _lib.check(lib.bf_resample(w.data_ptr(), u.data_ptr(), anc.data_ptr(), w.numel(), _RESAMPLERS[resampler],
-                               torch.cuda.current_stream(w.device).cuda_stream))
+    with torch.cuda.device(w.device):
+        _lib.check(lib.bf_resample(w.data_ptr(), u.data_ptr(), anc.data_ptr(), w.numel(), _RESAMPLERS[resampler],
+                                   torch.cuda.current_stream(w.device).cuda_stream))
     return anc

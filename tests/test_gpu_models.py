@@ -78,3 +78,20 @@ def test_ssm_sample_philox_statistics():
     np.testing.assert_allclose(v, 1.0 / 0.36, rtol=0.1)
     s2, _ = ssm.sample(c.params_nlssm(), 5, 50, num_trials=4000)
     assert np.array_equal(s, s2)                         # counter-based: same key, same draws
+
+
+def test_model_classes_hand_out_distributions_of_registry_functions():
+    """NonlinearGaussianSSM / NonlinearSSM accessors (models.py:126-157, :207-238) with a registry model: the mean is the
+    model function evaluated on the GPU at zero noise."""
+    from bayesianfiltering_b200.models import NonlinearGaussianSSM, NonlinearSSM
+    c = case("l63")                     # additive noise of the state's dimension, as these accessors assume
+    p, m = c.params_nlssm(), c.omodel
+    x = np.array([1.0, -2.0, 20.0], np.float32)
+    for ssm in (NonlinearGaussianSSM(3, 1), NonlinearSSM(3, 3, 1, 1)):
+        t = ssm.transition_distribution(p, x, inputs=1.0)
+        close(t.mean(), m.f(x[None], np.zeros((1, 3), np.float32), 1.0)[0], what="transition mean")
+        assert np.array_equal(t.covariance(), c.Q)
+        e = ssm.emission_distribution(p, x)
+        close(e.mean(), m.h(x[None], np.zeros((1, 1), np.float32), 0.0)[0], what="emission mean")
+        assert np.isfinite(e.log_prob(e.sample(seed=3)))
+        assert np.array_equal(ssm.initial_distribution(p).mean(), c.m0)
