@@ -32,6 +32,7 @@ def _engine(c, M, B=1):
     ("sin1d", 20, 5), ("sin3d", 4, 40),      # sin3d: the fp32 EKF loses positive definiteness at t=4
     ("l96s", 12, 9), ("l96", 6, 5),          # large-state kernel (gsf_large.cuh): Lorenz-96 d=8 and BASELINE configs[3]'s d=40
     ("l96_6", 8, 13), ("l96_10", 8, 13),     # d = 2 mod 4: every other warp's workspace would be misaligned without the padding
+    ("l96", 10, 256),                        # configs[3]'s mixture size: every warp of k_gsf_large<40> loops over ~43 components
 ])
 def test_gsf_stepwise_parity(name, T, M):
     """Each step from the ORACLE's carry (weights, predicted means, predicted covariances): one `_step`
