@@ -159,3 +159,39 @@ def resample_ancestors(w, u, mode="multinomial"):
         raise ValueError(mode)
     idx = searchsorted_bisect(cdf, r)
     return np.minimum(idx, n - 1).astype(np.int32)
+
+
+def cell_table_ancestors(w, u):
+    """The multinomial ancestors again, computed the way the large-N kernel does from N = 2^18 on (csrc/pf_fused.cuh,
+    `begin_gather` + the `use_cells` branch of the ancestor search) -- a runnable statement of why that shortcut is exact.
+
+      tau     = effective_thresholds_pow2(cumsum_associative(w))            monotone, same lower bounds as the bisection
+      L[c]    = lower_bound(tau, total * (c / N)),  c = 0 .. N - 1;  L[N] = N - 1      the CELL TABLE (sorted queries)
+      r       = total * (1 - u),  cell c = floor((1 - u) * N)                           exact: N is a power of two
+      answer  = L[c] + lower_bound(tau[L[c] : L[c + 1]], r)        (L[c] itself when (1 - u) * N is an integer: r IS the edge)
+
+    c / N <= 1 - u < (c + 1) / N and rounding a product by `total` is monotone, so edge_c <= r <= edge_{c+1} and, tau being
+    sorted, L[c] <= lower_bound(tau, r) <= L[c + 1].  tests/test_oracle.py holds this to `resample_ancestors`."""
+    w = np.asarray(w)
+    n = w.shape[0]
+    dt = w.dtype
+    cdf = cumsum_associative(w)
+    tau = effective_thresholds_pow2(cdf)
+    total = cdf[-1]
+    edges = systematic_positions(total, dt.type(0), n)
+    L = np.empty(n + 1, dtype=np.int64)
+    L[:n] = np.minimum(np.searchsorted(tau, edges, side="left"), n - 1)
+    L[n] = n - 1
+    one_minus_u = (dt.type(1) - np.asarray(u, dtype=dt)).astype(dt)
+    wq = (one_minus_u * dt.type(n)).astype(dt)
+    c = np.clip(wq.astype(np.int64), 0, n - 1)
+    r = multinomial_positions(total, np.asarray(u, dtype=dt))
+    out = np.empty(r.shape[0], dtype=np.int32)
+    for i in range(r.shape[0]):
+        lo = L[c[i]]
+        if wq[i] == dt.type(c[i]):
+            out[i] = lo
+            continue
+        hi = L[c[i] + 1]
+        out[i] = min(lo + int(np.searchsorted(tau[lo:hi], r[i], side="left")), n - 1)
+    return out

@@ -218,3 +218,20 @@ def test_unscented_oracle_sigma_points_and_linear_exactness():
                                          c.R.astype(np.float64), c.r0.astype(np.float64), ou.ParamsUKF(1.0, 0.0, 0.0))
     assert np.all(np.isfinite(g["means"])) and np.all(np.isfinite(g["loglik_inc"]))
     np.testing.assert_allclose(g["weights"].sum(axis=0), 1.0, rtol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["flat", "lognormal", "sparse", "peaked"])
+@pytest.mark.parametrize("n", [8, 256, 4096])
+def test_cell_table_search_is_the_fixed_bisection(n, kind):
+    """The large-N kernel's multinomial shortcut (two adjacent entries of a table of lower bounds at the cell edges + a search
+    inside the cell, csrc/pf_fused.cuh) restated in NumPy: the reference's ancestors for every uniform, including the ends."""
+    rng = np.random.default_rng(n + len(kind))
+    w = {"flat": lambda: rng.random(n, dtype=np.float32),
+         "lognormal": lambda: np.exp(6 * rng.standard_normal(n)).astype(np.float32),
+         "sparse": lambda: np.where(rng.random(n) < 0.7, 0, rng.random(n, dtype=np.float32)).astype(np.float32) + np.float32(1e-3) * (np.arange(n) == n // 3),
+         "peaked": lambda: rng.random(n, dtype=np.float32) ** 20}[kind]()
+    w = (w / w.sum(dtype=np.float32)).astype(np.float32)
+    for u in (rng.random(n, dtype=np.float32),                                                   # any float32 uniform
+              rng.integers(0, 1 << 24, n).astype(np.float32) / np.float32(1 << 24),              # the kernel's 24-bit uniforms: r is a cell edge
+              np.concatenate([[0.0, np.float32(1) - np.float32(2.0 ** -24), 0.5], rng.random(n - 3)]).astype(np.float32)):
+        assert np.array_equal(oscan.cell_table_ancestors(w, u), oscan.resample_ancestors(w, u, "multinomial"))
