@@ -67,3 +67,46 @@ def test_wrong_theta_length_is_rejected():
     h = C.c_void_p()
     cfg = _lib.PfConfig(100, 1, 0.5, 0, 0, 0, 0, 0)
     assert lib.bf_pf_create(C.byref(bad.desc), C.byref(cfg), C.byref(h)) == _lib.BF_EINVAL
+
+
+def test_ctypes_structs_have_the_layout_of_the_header(tmp_path):
+    """include/bfilt.h is plain C: compile it with gcc, print sizeof / offsetof of every struct field, and hold the ctypes
+    mirror in _lib.py (what gaussfiltax would bind) to it -- same field names, order, offsets and sizes."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = {"bf_model_desc": _lib.ModelDesc, "bf_pf_config": _lib.PfConfig, "bf_pf_io": _lib.PfIO, "bf_gsf_config": _lib.GsfConfig,
+             "bf_gsf_io": _lib.GsfIO, "bf_agsf_config": _lib.AgsfConfig, "bf_agsf_io": _lib.AgsfIO}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "bfilt.h")}"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu %zu\\n", offsetof({cname}, {fname}), sizeof((({cname}*)0)->{fname}));')
+    lines += [f'  printf("abi {{}} %d\\n", BF_ABI_VERSION);'.replace("{}", "version"), "  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)     # also: the header is valid C99
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = {}
+    for ln in out:
+        p = ln.split()
+        if len(p) == 3 and p[1] == "size":
+            assert C.sizeof(pairs[p[0]]) == int(p[2]), ln
+        elif len(p) == 4 and p[0] in pairs:
+            f = getattr(pairs[p[0]], p[1])
+            assert (f.offset, f.size) == (int(p[2]), int(p[3])), ln
+            seen.setdefault(p[0], []).append(p[1])
+        elif len(p) == 3 and p[0] == "abi":
+            assert int(p[2]) == 4
+    # every field of the header is mirrored (a field the ctypes class lacks would shift nothing but lose an argument)
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bfilt.h")).read(), flags=re.S)
+    for cname, cls in pairs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names += [re.sub(r"[\s\*]", "", n).split("[")[0] for n in re.sub(r"^(const\s+)?\w+\s*\*?", "", decl, count=1).split(",")]
+        assert names == [n for n, _ in cls._fields_] == seen[cname], (cname, names)
