@@ -110,3 +110,26 @@ def test_ctypes_structs_have_the_layout_of_the_header(tmp_path):
             if decl:
                 names += [re.sub(r"[\s\*]", "", n).split("[")[0] for n in re.sub(r"^(const\s+)?\w+\s*\*?", "", decl, count=1).split(",")]
         assert names == [n for n, _ in cls._fields_] == seen[cname], (cname, names)
+
+
+def test_the_stub_in_integration_md_is_current():
+    """INTEGRATION.md shows the ctypes stub a gaussfiltax maintainer would add: its structs must be those of the header
+    (via the checked mirror in _lib.py) and every library symbol it names must exist."""
+    import ast
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", doc, flags=re.S)
+    assert len(blocks) >= 2
+    ns = {}
+    exec(blocks[0].replace('C.CDLL("libbfilt.so")', f"C.CDLL({_lib.LIB_PATH!r})"), ns)
+    for name, mine in (("ModelDesc", _lib.ModelDesc), ("PfConfig", _lib.PfConfig), ("PfIO", _lib.PfIO)):
+        theirs = ns[name]
+        assert C.sizeof(theirs) == C.sizeof(mine)
+        assert [(n, getattr(theirs, n).offset, getattr(theirs, n).size) for n, _ in theirs._fields_] == \
+               [(n, getattr(mine, n).offset, getattr(mine, n).size) for n, _ in mine._fields_], name
+    ast.parse(blocks[1])
+    lib = _lib.load()
+    for sym in set(re.findall(r"\b(bf_[a-z_0-9]+)\b", doc)):
+        if not sym.endswith("_"):                                      # prose like `bf_gsf_*` / `bf_pf_shard_*`
+            assert hasattr(lib, sym) or sym in ("bf_model_desc", "bf_pf_config", "bf_pf_io", "bf_gsf_io", "bf_gsf_config",
+                                                "bf_agsf_config", "bf_agsf_io", "bf_abi_version"), sym
+    assert f"BF_ABI_VERSION {lib.bf_abi_version()}" in doc
