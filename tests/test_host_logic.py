@@ -158,3 +158,22 @@ def test_model_classes_and_their_distribution_accessors():
     assert np.array_equal(n.initial_distribution(p).mean(), [1.0, 2.0]) and np.array_equal(n.transition_distribution(p, np.ones(2)).mean(), [2.0, 2.0])
     with pytest.raises(ValueError):
         models.MVN(np.zeros(2), np.eye(3))
+
+
+def test_generic_ssm_sample_follows_the_accessors():
+    # gaussfiltax/ssm.py:169-211, inherited by NonlinearGaussianSSM: x' = 0.8 x + N(0, I), y = x[0] + N(0, 0.01)
+    g = models.NonlinearGaussianSSM(2, 1)
+    p = models.ParamsNLSSM(np.zeros(2), np.eye(2), lambda z, *u: 0.8 * np.asarray(z), np.zeros(2), np.eye(2),
+                           lambda z, *u: np.asarray(z)[:1], np.zeros(1), 0.01 * np.eye(1))
+    s, e = g.sample(p, PRNGKey(0), 4000)
+    assert s.shape == (4000, 2) and e.shape == (4000, 1) and s.dtype == np.float32
+    np.testing.assert_allclose(s[200:].var(0), 1.0 / 0.36, rtol=0.2)
+    np.testing.assert_allclose((e[:, 0] - s[:, 0]).std(), 0.1, rtol=0.1)
+    s2, e2 = g.sample(p, PRNGKey(0), 4000)
+    assert np.array_equal(s, s2) and np.array_equal(e, e2)                       # a key fixes the trajectory
+    assert not np.array_equal(s[:50], g.sample(p, PRNGKey(1), 50)[0])
+    seen = []
+    pu = p._replace(dynamics_function=lambda z, u: (seen.append(float(u)), np.asarray(z) + u)[1])
+    g.sample(pu, PRNGKey(2), 4, inputs=np.array([10.0, 20.0, 30.0, 40.0]))
+    assert seen == [20.0, 30.0, 40.0]                                            # step t uses inputs[t]; the first state has no transition
+    assert g.log_prior(p) == 0.0
