@@ -17,6 +17,7 @@ Functions executed (gaussfiltax/...):
   inference.speedy_augmented_gaussian_sum_filter   inference.py:621-812   -> ref_agsf_*.npz
   inference._kalman_step                           inference.py:107-120   -> ref_kalman_step.npz
   utils.optimal_resampling                         utils.py:216-244       -> ref_optimal_resampling.npz
+  utils.psd_solve / _get_sigma_points / split_to_sigma_points / collapse / gaussian_logpdf / mse / rmse -> ref_utils.npz
   particlefilt.BootstrapPF.run                     particlefilt.py:26-52  -> ref_legacy_bpf.npz
   gausssumfilt.GaussSumFilt.run                    gausssumfilt.py:30-78  -> ref_legacy_gsf.npz
   gaussfilt.{EKF,UKF,MCF,MCLAF} via GaussFilt.run  gaussfilt.py:88-308    -> ref_legacy_gaussfilt.npz
@@ -307,6 +308,33 @@ def gen_optimal_resampling():
     save("optimal_resampling", rows)
 
 
+def gen_utils():
+    """The small helpers of gaussfiltax/utils.py the callers use next to the filters: psd_solve :256-259, _get_sigma_points
+    :247-254, split_to_sigma_points :52-65, collapse :10-18, gaussian_logpdf :75-79, mse / rmse :179-187."""
+    rng = np.random.default_rng(9)
+    rows = {}
+    for k, (dx, dy) in enumerate(((1, 1), (3, 2), (4, 4))):
+        A = rng.normal(0, 1, (dx, dx)); P = f32(A @ A.T + 0.5 * np.eye(dx))
+        B = rng.normal(0, 1, (dy, dy)); S = f32(B @ B.T + 0.3 * np.eye(dy))
+        rhs = f32(rng.normal(0, 1, (dy, dx)))
+        m = f32(rng.normal(0, 1, dx))
+        lam = np.float32(0.7 * k - 0.2)
+        means = f32(rng.normal(0, 1, (5, dx)))
+        covs = np.stack([P * (1 + 0.1 * j) for j in range(5)])
+        wts = rng.random(5); wts = wts / wts.sum()
+        mo, co = gutils.collapse(np.asarray(means, np.float64), np.asarray(covs, np.float64), wts)
+        y = f32(rng.normal(0, 1, dy)); my = f32(rng.normal(0, 1, dy))
+        xe, xb = rng.normal(0, 1, (7, dx)), rng.normal(0, 1, (7, dx))
+        rows.update({f"P{k}": P, f"S{k}": S, f"rhs{k}": rhs, f"m{k}": m, f"lam{k}": lam,
+                     f"psd_solve{k}": f32(gutils.psd_solve(jnp.array(S), jnp.array(rhs))),
+                     f"sigma{k}": f32(gutils._get_sigma_points(jnp.array(m), jnp.array(P), lam)),
+                     f"legacy_sigma{k}": np.asarray(gutils.split_to_sigma_points(np.asarray(m, np.float64), np.asarray(P, np.float64), float(lam)), np.float64),
+                     f"cmeans{k}": means, f"ccovs{k}": covs, f"cw{k}": wts, f"collapse_mean{k}": mo, f"collapse_cov{k}": co,
+                     f"y{k}": y, f"my{k}": my, f"logpdf{k}": np.float64(gutils.gaussian_logpdf(np.asarray(y, np.float64), np.asarray(my, np.float64), np.asarray(S, np.float64))),
+                     f"xe{k}": xe, f"xb{k}": xb, f"mse{k}": np.float64(gutils.mse(xe, xb)), f"rmse{k}": np.float64(gutils.rmse(xe, xb))})
+    save("utils", rows)
+
+
 # ------------------------------------------------------------------------------------------ legacy NumPy classes
 class _RecordingRandom:
     """Stands in for `numpy.random` inside the legacy modules (`from numpy import random`): every draw comes from a
@@ -443,7 +471,7 @@ def gen_legacy():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sample", "bpf", "gsf", "ugsf", "agsf", "kalman_step", "optimal_resampling", "legacy"]
+    which = sys.argv[1:] or ["sample", "bpf", "gsf", "ugsf", "agsf", "kalman_step", "optimal_resampling", "utils", "legacy"]
     os.makedirs(OUT, exist_ok=True)
     for w in which:
         globals()["gen_" + w]()

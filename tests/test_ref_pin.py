@@ -248,3 +248,20 @@ def test_legacy_bank_matches_reference_and_records_its_defects():
             np.testing.assert_allclose(a, g(f"{kind}_{k}"), rtol=1e-6, atol=1e-7, err_msg=f"{kind} {k}")
     assert "l63_EKF_error" in d.files and "ungm_MCF_error" in d.files
     assert "sdp_opt" in str(ref("legacy_gaussfilt")["l63_mclaf_error"])
+
+
+def test_utils_helpers_match_reference():
+    """The package's own host-side helper faces (bayesianfiltering_b200/utils.py) against the reference's
+    (tests/golden/ref_utils.npz, oracle/make_ref_fixtures.py gen_utils)."""
+    from bayesianfiltering_b200 import utils as bu
+    d = np.load(os.path.join(GOLD, "ref_utils.npz"))
+    for k in range(3):
+        np.testing.assert_allclose(bu.psd_solve(d[f"S{k}"], d[f"rhs{k}"]), d[f"psd_solve{k}"], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(bu._get_sigma_points(d[f"m{k}"], d[f"P{k}"], d[f"lam{k}"]), d[f"sigma{k}"], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(bu.split_to_sigma_points(d[f"m{k}"], d[f"P{k}"], float(d[f"lam{k}"])), d[f"legacy_sigma{k}"], rtol=1e-12, atol=1e-12)
+        mean, cov = bu.collapse(d[f"cmeans{k}"], d[f"ccovs{k}"], d[f"cw{k}"])
+        np.testing.assert_allclose(mean, d[f"collapse_mean{k}"], rtol=1e-12); np.testing.assert_allclose(cov, d[f"collapse_cov{k}"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(bu.gaussian_logpdf(d[f"y{k}"].astype(np.float64), d[f"my{k}"].astype(np.float64), d[f"S{k}"].astype(np.float64)),
+                                   d[f"logpdf{k}"], rtol=1e-12)
+        np.testing.assert_allclose(bu.mse(d[f"xe{k}"], d[f"xb{k}"]), d[f"mse{k}"], rtol=1e-12)
+        np.testing.assert_allclose(bu.rmse(d[f"xe{k}"], d[f"xb{k}"]), d[f"rmse{k}"], rtol=1e-12)
