@@ -38,6 +38,30 @@ class ParamsUKF(NamedTuple):
     kappa: float = 0
 
 
+# Helper faces of inference.py:21-26 (inside the filters these are index arithmetic of the kernels / of zoo.host_model_from_params)
+def _get_params(x, dim, t):
+    """inference.py:21: the t-th slice of a parameter that carries a leading time axis, else the parameter itself."""
+    x = np.asarray(x)
+    return x[t] if x.ndim == dim + 1 else x
+
+
+def _process_input(x, y):
+    """inference.py:23: zeros [T,1] when no inputs are given."""
+    return np.zeros((y, 1), np.float32) if x is None else x
+
+
+def _MVN_log_prob(mean, cov, y):
+    """inference.py:24: log N(y | mean, cov) with TFP's Cholesky arithmetic in fp32 (host face; in-kernel: `emission_log_prob`
+    of csrc/pf_kernels.cuh and the log-likelihood of `ekf_condition`)."""
+    from .models import MVN
+    return MVN(mean, cov).log_prob(np.atleast_1d(np.asarray(y, np.float32)))
+
+
+def swap_axes_on_values(outputs, axis1=0, axis2=1):
+    """inference.py:25-26: swap two axes of every array in a dict (views)."""
+    return {k: (v.transpose(axis1, axis2) if _is_torch(v) else np.swapaxes(v, axis1, axis2)) for k, v in outputs.items()}
+
+
 def _is_torch(a):
     return type(a).__module__.startswith("torch")
 

@@ -177,3 +177,17 @@ def test_generic_ssm_sample_follows_the_accessors():
     g.sample(pu, PRNGKey(2), 4, inputs=np.array([10.0, 20.0, 30.0, 40.0]))
     assert seen == [20.0, 30.0, 40.0]                                            # step t uses inputs[t]; the first state has no transition
     assert g.log_prior(p) == 0.0
+
+
+def test_inference_helper_faces():
+    # gaussfiltax/inference.py:21-26
+    import scipy.stats
+    Q = np.arange(12.0).reshape(3, 2, 2)
+    assert np.array_equal(inference._get_params(Q, 2, 1), Q[1]) and np.array_equal(inference._get_params(Q[0], 2, 1), Q[0])
+    assert inference._process_input(None, 4).shape == (4, 1) and inference._process_input("u", 4) == "u"
+    S = np.array([[0.5, 0.1], [0.1, 0.3]])
+    np.testing.assert_allclose(inference._MVN_log_prob(np.array([1.0, -1.0]), S, np.array([0.7, -0.2])),
+                               scipy.stats.multivariate_normal([1.0, -1.0], S).logpdf([0.7, -0.2]), rtol=2e-6)
+    assert inference._MVN_log_prob(np.zeros(1), np.eye(1), 0.3).shape == ()
+    out = inference.swap_axes_on_values({"w": np.zeros((5, 3)), "x": np.zeros((5, 3, 2))})
+    assert out["w"].shape == (3, 5) and out["x"].shape == (3, 5, 2)
