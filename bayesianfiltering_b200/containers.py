@@ -63,11 +63,13 @@ def _branches_from_node1(node_component: GaussianComponent, splitting_cov, num_p
 _branches_from_node2 = _branches_from_node1          # containers.py:114-141: the same function with the second branch count
 
 
-def _branches_from_tree1(components, split_covs_array, num_branch_array, key=0):
-    """containers.py:92-112: branch out every component of a mixture -> list (one per component) of lists of components."""
+def _branches_from_tree1(components, split_covs_array, num_branch_array, key=0, *, normals=None):
+    """containers.py:92-112: branch out every component of a mixture -> list (one per component) of lists of components.
+    `normals` [num_components, num_branches, dx] replaces the standard-normal draws (one key per component otherwise)."""
     from .random import split
     keys = split(key, len(num_branch_array))
-    return [_branches_from_node1(c, d, n, k) for c, d, n, k in zip(components, split_covs_array, num_branch_array, keys)]
+    zs = [None] * len(num_branch_array) if normals is None else normals
+    return [_branches_from_node1(c, d, n, k, normals=z) for c, d, n, k, z in zip(components, split_covs_array, num_branch_array, keys, zs)]
 
 
 _branches_from_tree2 = _branches_from_tree1          # containers.py:143-163

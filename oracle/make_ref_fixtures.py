@@ -18,6 +18,7 @@ Functions executed (gaussfiltax/...):
   inference._kalman_step                           inference.py:107-120   -> ref_kalman_step.npz
   utils.optimal_resampling                         utils.py:216-244       -> ref_optimal_resampling.npz
   utils.psd_solve / _get_sigma_points / split_to_sigma_points / collapse / gaussian_logpdf / mse / rmse -> ref_utils.npz
+  containers._branches_from_tree1/2, _gaussian_sum_to_components, _components_to_gaussian_sum  containers.py:43-161 -> ref_containers.npz
   particlefilt.BootstrapPF.run                     particlefilt.py:26-52  -> ref_legacy_bpf.npz
   gausssumfilt.GaussSumFilt.run                    gausssumfilt.py:30-78  -> ref_legacy_gsf.npz
   gaussfilt.{EKF,UKF,MCF,MCLAF} via GaussFilt.run  gaussfilt.py:88-308    -> ref_legacy_gaussfilt.npz
@@ -335,6 +336,37 @@ def gen_utils():
     save("utils", rows)
 
 
+def gen_containers():
+    """containers.py:43-161: _gaussian_sum_to_components / _components_to_gaussian_sum and the branching of a mixture,
+    `_branches_from_tree1` / `_branches_from_tree2` (every component split into num_prt1 / num_prt2 = 2 Gaussian particles of
+    covariance Delta whose means are drawn from N(mean, P - Delta)).  The normal draws come off the shim's tape."""
+    import gaussfiltax.containers as gc
+    rng = np.random.default_rng(10)
+    rows = {}
+    for k, dx in enumerate((1, 3, 4)):
+        M = 3
+        means = f32(rng.normal(0, 1, (M, dx)))
+        covs = []
+        for _ in range(M):
+            A = rng.normal(0, 1, (dx, dx)); covs.append(f32(A @ A.T + 0.5 * np.eye(dx)))
+        covs = np.stack(covs)
+        w = rng.random(M); w = f32(w / w.sum())
+        comps = gc._gaussian_sum_to_components(gc.GaussianSum(jnp.array(means), jnp.array(covs), jnp.array(w)))
+        back = gc._components_to_gaussian_sum(comps)
+        rows.update({f"means{k}": means, f"covs{k}": covs, f"w{k}": w, f"back_means{k}": f32(np.stack(back.means)),
+                     f"back_covs{k}": f32(np.stack(back.covariances)), f"back_w{k}": f32(np.stack(back.weights))})
+        for tag, fn, nb in (("t1", gc._branches_from_tree1, gc.num_prt1), ("t2", gc._branches_from_tree2, gc.num_prt2)):
+            deltas = f32(0.3 * covs) if tag == "t1" else f32(0.6 * covs)
+            refshim.tape_clear()
+            tree = fn(comps, [jnp.array(d) for d in deltas], [nb] * M, jr.PRNGKey(90 + k))
+            draws = refshim.tape_take("multivariate_normal")
+            rows.update({f"{tag}_delta{k}": deltas, f"{tag}_z{k}": np.stack([d["z"] for d in draws]),
+                         f"{tag}_means{k}": f32(np.stack([np.stack([c.mean for c in br]) for br in tree])),
+                         f"{tag}_covs{k}": f32(np.stack([np.stack([c.covariance for c in br]) for br in tree])),
+                         f"{tag}_w{k}": f32(np.stack([np.stack([c.weight for c in br]) for br in tree])), f"{tag}_n{k}": np.int32(nb)})
+    save("containers", rows)
+
+
 # ------------------------------------------------------------------------------------------ legacy NumPy classes
 class _RecordingRandom:
     """Stands in for `numpy.random` inside the legacy modules (`from numpy import random`): every draw comes from a
@@ -471,7 +503,7 @@ def gen_legacy():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sample", "bpf", "gsf", "ugsf", "agsf", "kalman_step", "optimal_resampling", "utils", "legacy"]
+    which = sys.argv[1:] or ["sample", "bpf", "gsf", "ugsf", "agsf", "kalman_step", "optimal_resampling", "utils", "containers", "legacy"]
     os.makedirs(OUT, exist_ok=True)
     for w in which:
         globals()["gen_" + w]()

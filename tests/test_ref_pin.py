@@ -265,3 +265,23 @@ def test_utils_helpers_match_reference():
                                    d[f"logpdf{k}"], rtol=1e-12)
         np.testing.assert_allclose(bu.mse(d[f"xe{k}"], d[f"xb{k}"]), d[f"mse{k}"], rtol=1e-12)
         np.testing.assert_allclose(bu.rmse(d[f"xe{k}"], d[f"xb{k}"]), d[f"rmse{k}"], rtol=1e-12)
+
+
+def test_containers_match_reference():
+    """containers.py:43-161 run unmodified (tests/golden/ref_containers.npz): conversions and the branching of a mixture,
+    with the reference's own normal draws."""
+    from bayesianfiltering_b200 import containers as bc
+    d = np.load(os.path.join(GOLD, "ref_containers.npz"))
+    for k in range(3):
+        comps = bc._gaussian_sum_to_components(bc.GaussianSum(d[f"means{k}"], d[f"covs{k}"], d[f"w{k}"]))
+        back = bc._components_to_gaussian_sum(comps)
+        assert np.array_equal(np.stack(back.means), d[f"back_means{k}"]) and np.array_equal(np.stack(back.covariances), d[f"back_covs{k}"])
+        assert np.array_equal(np.stack(back.weights), d[f"back_w{k}"])
+        for tag, fn in (("t1", bc._branches_from_tree1), ("t2", bc._branches_from_tree2)):
+            n = int(d[f"{tag}_n{k}"])
+            assert n == (bc.num_prt1 if tag == "t1" else bc.num_prt2)
+            tree = fn(comps, list(d[f"{tag}_delta{k}"]), [n] * len(comps), 0, normals=d[f"{tag}_z{k}"])
+            assert len(tree) == len(comps) and all(len(br) == n for br in tree)
+            np.testing.assert_allclose(np.stack([np.stack([c.mean for c in br]) for br in tree]), d[f"{tag}_means{k}"], rtol=2e-6, atol=2e-6)
+            assert np.array_equal(np.stack([np.stack([c.covariance for c in br]) for br in tree]), d[f"{tag}_covs{k}"])
+            np.testing.assert_allclose(np.stack([np.stack([c.weight for c in br]) for br in tree]), d[f"{tag}_w{k}"], rtol=1e-7)
