@@ -292,5 +292,7 @@ def augmented_gaussian_sum_filter(params: ParamsNLSSM, emissions, num_components
                                   opt_args=(0.1, 0.1), inputs=None, **kw):
     r"""inference.py:458-619: the same recursion written over `containers.GaussianComponent` trees (`_branches_from_tree1/2`,
     containers.py:63-161).  Its branch means are `jr.multivariate_normal(key, mean, P - Delta)` = `mean + chol(P - Delta) z`,
-    i.e. for the same standard-normal draws exactly the speedy filter -- which is what runs."""
+    i.e. for the same standard-normal draws exactly the speedy filter -- which is what runs.  (Pinned: the unmodified tree
+    version's outputs, tests/golden/ref_agsf_tree_*.npz, are reproduced by the speedy restatement step by step,
+    tests/test_ref_pin.py.)"""
     return speedy_augmented_gaussian_sum_filter(params, emissions, num_components, rng_key, num_iter, opt_args, inputs, **kw)

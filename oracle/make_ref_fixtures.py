@@ -15,6 +15,7 @@ Functions executed (gaussfiltax/...):
   inference.gaussian_sum_filter                    inference.py:303-377   -> ref_gsf_*.npz
   inference.unscented_gaussian_sum_filter          inference.py:379-456   -> ref_ugsf_*.npz
   inference.speedy_augmented_gaussian_sum_filter   inference.py:621-812   -> ref_agsf_*.npz
+  inference.augmented_gaussian_sum_filter          inference.py:458-619   -> ref_agsf_tree_*.npz (layout of ref_agsf_*)
   inference._kalman_step                           inference.py:107-120   -> ref_kalman_step.npz
   utils.optimal_resampling                         utils.py:216-244       -> ref_optimal_resampling.npz
   utils.psd_solve / _get_sigma_points / split_to_sigma_points / collapse / gaussian_logpdf / mse / rmse -> ref_utils.npz
@@ -269,6 +270,36 @@ def gen_agsf():
         save(f"agsf_{m['name']}", d)
 
 
+def gen_agsf_tree():
+    """inference.augmented_gaussian_sum_filter (inference.py:458-619): the same recursion written over GaussianComponent
+    trees (containers._branches_from_tree1/2; branch counts hard-coded to num_prt1 = num_prt2 = 2, containers.py:13-14).
+    Saved in the layout of the speedy filter's fixtures: its `jr.multivariate_normal(key, mean, P - Delta, (2,))` draws
+    z [2,dx] per component become z_iid[m] = z^T, so that ONE oracle / kernel serves both entry points."""
+    for m, T, M, seed, oa in ((model_ungm(), 20, 6, 51, (0.8, 0.1)), (model_bot(2), 12, 5, 52, (0.9, 0.9))):
+        dx = m["dims"][0]
+        nc = [M, 2, 2]
+        s = sample(m, T, 300 + seed)
+        d, u = consts(m, T)
+        inputs = None if u is None else jnp.array(u)
+        refshim.tape_clear()
+        post, aux = gf.augmented_gaussian_sum_filter(params_of(m), jnp.array(s["emissions"]), nc, rng_key=jr.PRNGKey(seed),
+                                                     opt_args=oa, inputs=inputs)
+        means0 = refshim.tape_take("mvn_sample")[0]["x"]
+        mv = refshim.tape_take("multivariate_normal")     # per step: M draws [2,dx] (tree 1), then 2 M draws [2,dx] (tree 2)
+        ch = refshim.tape_take("choice")
+        assert len(mv) == T * 3 * M and len(ch) == T
+        per = [mv[t * 3 * M:(t + 1) * 3 * M] for t in range(T)]
+        z_iid = np.stack([np.stack([c["z"].T for c in st[:M]]) for st in per])             # [T, M, dx, 2]
+        s_iid = np.stack([np.stack([c["z"].T for c in st[M:]]) for st in per])             # [T, 2 M, dx, 2]
+        assert z_iid.shape == (T, M, dx, 2) and s_iid.shape == (T, 2 * M, dx, 2)
+        d.update(emissions=s["emissions"], means0=f32(means0), num_components=np.asarray(nc, np.int32), opt_args=f32(oa),
+                 z_iid=f32(z_iid), s_iid=f32(s_iid),
+                 res_u=f32(np.stack([c["u"] for c in ch])), res_idx=np.stack([c["idx"] for c in ch]).astype(np.int32),
+                 pre_weights=f32(aux["pre_weights"]), updated_means=f32(aux["updated_means"]),
+                 weights=f32(post.weights), means=f32(post.means), covariances=f32(post.covariances))
+        save(f"agsf_tree_{m['name']}", d)
+
+
 def gen_kalman_step():
     """_kalman_step (inference.py:107-120): predict-then-update of one Gaussian, on the drivers' models."""
     from jax import jacfwd
@@ -503,7 +534,7 @@ def gen_legacy():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sample", "bpf", "gsf", "ugsf", "agsf", "kalman_step", "optimal_resampling", "utils", "containers", "legacy"]
+    which = sys.argv[1:] or ["sample", "bpf", "gsf", "ugsf", "agsf", "agsf_tree", "kalman_step", "optimal_resampling", "utils", "containers", "legacy"]
     os.makedirs(OUT, exist_ok=True)
     for w in which:
         globals()["gen_" + w]()

@@ -158,11 +158,13 @@ def test_bootstrap_particle_filter_matches_reference(name):
 
 
 # ------------------------------------------------------------------------------------------ augmented filter
-@pytest.mark.parametrize("name", ["ungm", "bot2", "l63", "lg42"])
+@pytest.mark.parametrize("name", ["ungm", "bot2", "l63", "lg42", "tree_ungm", "tree_bot2"])
 def test_speedy_agsf_matches_reference(name):
-    """inference.speedy_augmented_gaussian_sum_filter (inference.py:621-812), step by step from the reference's carry"""
+    """inference.speedy_augmented_gaussian_sum_filter (inference.py:621-812), step by step from the reference's carry;
+    `tree_*`: outputs of inference.augmented_gaussian_sum_filter (:458-619, the GaussianComponent-tree version) -- the same
+    recursion for the same draws, which is why ONE oracle function and one kernel serve both entry points."""
     d = ref(f"agsf_{name}")
-    m = omodel(name)
+    m = omodel(name.replace("tree_", ""))
     M, N1, N2 = (int(v) for v in d["num_components"])
     T = d["emissions"].shape[0]
     u = _inputs(d, T)
